@@ -1,0 +1,234 @@
+// C ABI (include/bt_api.h) of the fused physics + tracking-reward step: model upload, variant selection and
+// kernel launches.  The kernels themselves are in bt_tu.inc (one translation unit per variant and kernel).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <vector>
+
+#include "bt_api.h"
+#include "bt_bind.h"
+#include "bt_ops.h"
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+// (dof slots per lane, contact slots per lane): rodent nv 73 / 30 contacts -> (3,1); fly nv 42|36 / 27 -> (2,1);
+// two-rodent stress config nv 146 / 114 contacts -> (5,4).  Keep in sync with VARIANTS in build.py.
+#define BT_VARIANTS(X) X(2, 1) X(3, 1) X(5, 4)
+
+#define X(d, c)                                                                                                     \
+  cudaError_t bt_prepare_step_##d##_##c(int); cudaError_t bt_prepare_reset_##d##_##c(int);                          \
+  cudaError_t bt_prepare_physics_##d##_##c(int); cudaError_t bt_prepare_reward_##d##_##c(int);                      \
+  cudaError_t bt_prepare_debug_##d##_##c(int);                                                                      \
+  void bt_launch_step_##d##_##c(BtLaunchCfg, const BtDev&, int, int, const BtStepArgs&);                            \
+  void bt_launch_reset_##d##_##c(BtLaunchCfg, const BtDev&, int, int, const BtResetArgs&);                          \
+  void bt_launch_physics_##d##_##c(BtLaunchCfg, const BtDev&, int, int, const float*, const BtState&, int);         \
+  void bt_launch_reward_##d##_##c(BtLaunchCfg, const BtDev&, int, int, const BtRewardArgs&);                        \
+  void bt_launch_debug_##d##_##c(BtLaunchCfg, const BtDev&, int, int, const float*, const BtState&, int, float*, float*, int32_t*);
+BT_VARIANTS(X)
+#undef X
+
+static const BtVariantOps kVariants[] = {
+#define X(d, c)                                                                                                     \
+  {d, c, bt_prepare_step_##d##_##c, bt_prepare_reset_##d##_##c, bt_prepare_physics_##d##_##c, bt_prepare_reward_##d##_##c, \
+   bt_prepare_debug_##d##_##c, bt_launch_step_##d##_##c, bt_launch_reset_##d##_##c, bt_launch_physics_##d##_##c,      \
+   bt_launch_reward_##d##_##c, bt_launch_debug_##d##_##c},
+    BT_VARIANTS(X)
+#undef X
+};
+
+struct BtModel {
+  BtDev dev;        // scalars + device table pointers
+  void* blob;       // one allocation holding every table
+  int device;
+  const BtVariantOps* ops;
+  int warps;        // environments per CTA
+  int max_ctas;     // persistent grid size cap
+  int smem_bytes;   // dynamic shared memory per CTA
+};
+
+#define BT_CUDA(call)                                                                           \
+  do {                                                                                          \
+    cudaError_t e_ = (call);                                                                    \
+    if (e_ != cudaSuccess) {                                                                    \
+      snprintf(g_err, sizeof(g_err), "%s failed: %s", #call, cudaGetErrorString(e_));           \
+      return BT_E_CUDA;                                                                         \
+    }                                                                                           \
+  } while (0)
+
+static inline BtLaunchCfg cfg_for(const BtModel* m, int n_envs, void* stream) {
+  int ctas = (n_envs + m->warps - 1) / m->warps;
+  if (ctas > m->max_ctas) ctas = m->max_ctas;
+  if (ctas < 1) ctas = 1;
+  BtLaunchCfg c = {ctas, m->warps * 32, m->smem_bytes, (cudaStream_t)stream};
+  return c;
+}
+#define BT_LAUNCHED()                    \
+  do {                                   \
+    BT_CUDA(cudaGetLastError());         \
+    g_launches++;                        \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------- C ABI
+extern "C" {
+
+const char* bt_last_error(void) { return g_err; }
+int64_t bt_launch_count(void) { return g_launches.load(); }
+
+int bt_model_create(int n, const char* const* names, const void* const* data, const int64_t* counts, const int* is_float,
+                    int device, BtModel** out) {
+  if (!names || !data || !counts || !is_float || !out || n <= 0) { snprintf(g_err, sizeof(g_err), "null argument"); return BT_E_ARG; }
+  BT_CUDA(cudaSetDevice(device));
+  // one blob, every table 256-byte aligned
+  std::vector<size_t> off(n);
+  size_t total = 0;
+  for (int i = 0; i < n; i++) {
+    if (counts[i] <= 0 || !data[i]) { snprintf(g_err, sizeof(g_err), "table '%s' is empty", names[i]); return BT_E_ARG; }
+    off[i] = total;
+    total += ((size_t)counts[i] * 4 + 255) & ~(size_t)255;
+  }
+  std::vector<char> host(total, 0);
+  for (int i = 0; i < n; i++) memcpy(host.data() + off[i], data[i], (size_t)counts[i] * 4);
+  void* blob = nullptr;
+  BT_CUDA(cudaMalloc(&blob, total));
+  cudaError_t e = cudaMemcpy(blob, host.data(), total, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(blob); snprintf(g_err, sizeof(g_err), "upload failed: %s", cudaGetErrorString(e)); return BT_E_CUDA; }
+  std::vector<const void*> bound(n);
+  for (int i = 0; i < n; i++) bound[i] = (const char*)blob + off[i];
+  BtModel* m = new BtModel();
+  m->blob = blob;
+  m->device = device;
+  if (bt_bind(&m->dev, n, names, data, bound.data(), counts, is_float, g_err, sizeof(g_err))) { cudaFree(blob); delete m; return BT_E_ARG; }
+  const int need_ds = (m->dev.nv + 31) / 32, need_cs = m->dev.ncon > 0 ? (m->dev.ncon + 31) / 32 : 1;
+  m->ops = nullptr;
+  for (const BtVariantOps& v : kVariants)
+    if (v.ds >= need_ds && v.cs >= need_cs) { m->ops = &v; break; }
+  if (!m->ops) {
+    snprintf(g_err, sizeof(g_err), "model (nv=%d, ncon=%d) exceeds the compiled kernel variants", m->dev.nv, m->dev.ncon);
+    cudaFree(blob); delete m; return BT_E_UNSUPPORTED;
+  }
+  cudaDeviceProp prop;
+  BT_CUDA(cudaGetDeviceProperties(&prop, device));
+  const size_t per_env = (size_t)m->dev.smem_floats * 4;
+  int warps = (int)(prop.sharedMemPerBlockOptin / per_env);
+  if (warps > BT_MAX_WARPS) warps = BT_MAX_WARPS;
+  if (warps < 1) {
+    snprintf(g_err, sizeof(g_err), "per-environment scratch (%zu B) exceeds shared memory", per_env);
+    cudaFree(blob); delete m; return BT_E_UNSUPPORTED;
+  }
+  if (const char* w = getenv("BT_WARPS")) { int v = atoi(w); if (v >= 1 && v <= warps) warps = v; }
+  m->warps = warps;
+  m->max_ctas = prop.multiProcessorCount;
+  m->smem_bytes = (int)(per_env * warps);
+  {
+    const BtVariantOps* o = m->ops;
+    cudaError_t pe = o->prepare_step(m->smem_bytes);
+    if (pe == cudaSuccess) pe = o->prepare_reset(m->smem_bytes);
+    if (pe == cudaSuccess) pe = o->prepare_physics(m->smem_bytes);
+    if (pe == cudaSuccess) pe = o->prepare_reward(m->smem_bytes);
+    if (pe == cudaSuccess) pe = o->prepare_debug(m->smem_bytes);
+    if (pe != cudaSuccess) {
+      snprintf(g_err, sizeof(g_err), "cudaFuncSetAttribute(%d B dynamic smem) failed: %s", m->smem_bytes, cudaGetErrorString(pe));
+      cudaFree(blob); delete m; return BT_E_CUDA;
+    }
+  }
+  *out = m;
+  return BT_OK;
+}
+
+void bt_model_destroy(BtModel* m) {
+  if (!m) return;
+  cudaFree(m->blob);
+  delete m;
+}
+
+int bt_model_dims(const BtModel* m, int* dims) {
+  if (!m || !dims) { snprintf(g_err, sizeof(g_err), "null argument"); return BT_E_ARG; }
+  dims[0] = m->dev.nq; dims[1] = m->dev.nv; dims[2] = m->dev.nu; dims[3] = m->dev.na; dims[4] = m->dev.nbody;
+  dims[5] = m->dev.obs_size; dims[6] = m->dev.smem_floats; dims[7] = m->dev.ncon;
+  return BT_OK;
+}
+
+int bt_model_launch(const BtModel* m, int* out) {
+  if (!m || !out) { snprintf(g_err, sizeof(g_err), "null argument"); return BT_E_ARG; }
+  out[0] = m->warps; out[1] = m->max_ctas; out[2] = m->smem_bytes;
+  return BT_OK;
+}
+
+static int check_state(const BtModel* m, const BtStatePtrs& s, bool need_xpos) {
+  if (!s.qpos || !s.qvel || !s.qacc_warmstart || !s.time || (m->dev.na > 0 && !s.act) || (need_xpos && !s.xpos)) {
+    snprintf(g_err, sizeof(g_err), "null state pointer");
+    return BT_E_ARG;
+  }
+  return 0;
+}
+
+int bt_reset(BtModel* m, int n_envs, const uint32_t* keys, BtStatePtrs state, float* obs, float* reward, float* done,
+             float* metrics, float* info_f, int32_t* info_i, void* stream) {
+  if (!m || n_envs < 0 || !keys || !obs || !reward || !done || !metrics || !info_f || !info_i) { snprintf(g_err, sizeof(g_err), "bad argument"); return BT_E_ARG; }
+  if (check_state(m, state, true)) return BT_E_ARG;
+  if (n_envs == 0) return BT_OK;
+  BtResetArgs a = {keys, state, obs, reward, done, metrics, info_f, info_i};
+  m->ops->reset(cfg_for(m, n_envs, stream), m->dev, n_envs, m->warps, a);
+  BT_LAUNCHED();
+  return BT_OK;
+}
+
+int bt_step(BtModel* m, int n_envs, const float* action, BtStatePtrs state, BtStatePtrs first, const float* first_obs,
+            const int32_t* first_info_i, float* obs, float* reward, float* done, float* metrics, float* info_f, int32_t* info_i,
+            void* stream) {
+  if (!m || n_envs < 0 || !action || !first_obs || !first_info_i || !obs || !reward || !done || !metrics || !info_f || !info_i) {
+    snprintf(g_err, sizeof(g_err), "bad argument");
+    return BT_E_ARG;
+  }
+  if (check_state(m, state, true) || check_state(m, first, true)) return BT_E_ARG;
+  if (n_envs == 0) return BT_OK;
+  BtStepArgs a = {action, state, first, first_obs, first_info_i, obs, reward, done, metrics, info_f, info_i};
+  m->ops->step(cfg_for(m, n_envs, stream), m->dev, n_envs, m->warps, a);
+  BT_LAUNCHED();
+  return BT_OK;
+}
+
+int bt_physics_step(BtModel* m, int n_envs, const float* ctrl, BtStatePtrs state, int n_substeps, void* stream) {
+  if (!m || n_envs < 0 || n_substeps < 1 || (m->dev.nu > 0 && !ctrl)) { snprintf(g_err, sizeof(g_err), "bad argument"); return BT_E_ARG; }
+  if (check_state(m, state, false)) return BT_E_ARG;
+  if (n_envs == 0) return BT_OK;
+  m->ops->physics(cfg_for(m, n_envs, stream), m->dev, n_envs, m->warps, ctrl, state, n_substeps);
+  BT_LAUNCHED();
+  return BT_OK;
+}
+
+int bt_pipeline_init(BtModel* m, int n_envs, BtStatePtrs state, void* stream) {
+  if (!m || n_envs < 0) { snprintf(g_err, sizeof(g_err), "bad argument"); return BT_E_ARG; }
+  if (check_state(m, state, false)) return BT_E_ARG;
+  if (n_envs == 0) return BT_OK;
+  m->ops->physics(cfg_for(m, n_envs, stream), m->dev, n_envs, m->warps, nullptr, state, 0);
+  BT_LAUNCHED();
+  return BT_OK;
+}
+
+int bt_reward_obs(BtModel* m, int n_envs, const float* action, BtStatePtrs state, int32_t* info_i, float* obs, float* reward,
+                  float* done, float* metrics, float* info_f, void* stream) {
+  if (!m || n_envs < 0 || !action || !info_i || !obs || !reward || !done || !metrics || !info_f) { snprintf(g_err, sizeof(g_err), "bad argument"); return BT_E_ARG; }
+  if (check_state(m, state, true)) return BT_E_ARG;
+  if (n_envs == 0) return BT_OK;
+  BtRewardArgs a = {action, state, info_i, obs, reward, done, metrics, info_f};
+  m->ops->reward(cfg_for(m, n_envs, stream), m->dev, n_envs, m->warps, a);
+  BT_LAUNCHED();
+  return BT_OK;
+}
+
+int bt_forward_debug(BtModel* m, int n_envs, const float* ctrl, BtStatePtrs state, int stop, float* scratch, float* cdist,
+                     int32_t* niter, void* stream) {
+  if (!m || n_envs < 0 || !scratch || !cdist || !niter) { snprintf(g_err, sizeof(g_err), "bad argument"); return BT_E_ARG; }
+  if (check_state(m, state, false)) return BT_E_ARG;
+  if (n_envs == 0) return BT_OK;
+  m->ops->debug(cfg_for(m, n_envs, stream), m->dev, n_envs, m->warps, ctrl, state, stop, scratch, cdist, niter);
+  BT_LAUNCHED();
+  return BT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,1281 @@
+// Per-environment algorithm of the fused physics + tracking-reward step.
+//
+// One *lane group* of G lanes owns one environment (G = 32: a warp per environment on sm_100a; G = 1 is the
+// host emulation used by the CPU-side tests of the table logic).  All per-environment state lives in a scratch
+// block `s` (shared memory on the GPU) laid out by model.py::pack; model constants are read through BtDev.
+//
+// What this replaces (reference call path): /root/reference/envs/fruitfly.py:497-596 (env.step) ->
+// brax PipelineEnv.pipeline_step -> mujoco.mjx.step x n_frames, plus
+// custom_brax/custom_wrappers.py:54-80 and brax EpisodeWrapper.  The formulation is deliberately different
+// from MJX's dense one (fruitfly.py:78): tree-sparse L'DL, matrix-free constraint Jacobian (ancestor-chain
+// sums of cdof), constraint rows held in registers, one forward and one backward tree pass per substep.
+#pragma once
+#include "bt_math.h"
+#include "bt_model.h"
+
+template <int G>
+struct BtLanes;
+#ifdef __CUDACC__
+template <>
+struct BtLanes<32> {
+  static BT_DEV void sync() { __syncwarp(); }
+  static BT_DEV float allsum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  }
+  static BT_DEV int any(int p) { return __any_sync(0xffffffffu, p); }
+};
+#endif
+template <>
+struct BtLanes<1> {
+  static BT_DEV void sync() {}
+  static BT_DEV float allsum(float v) { return v; }
+  static BT_DEV int any(int p) { return p; }
+};
+
+// debug stop points for bt_forward_debug (parity tests of intermediates)
+enum { BT_STOP_NONE = 0, BT_STOP_TREE = 1, BT_STOP_SMOOTH = 2, BT_STOP_M = 3, BT_STOP_FACTOR = 4, BT_STOP_QACC_SMOOTH = 5,
+       BT_STOP_COLLISION = 6, BT_STOP_SOLVE = 7 };
+
+template <int G, int DS, int CS>
+struct BtEnv {
+  typedef BtLanes<G> W;
+  const BtDev& m;
+  float* s;
+  int lane;
+  int niter;       // solver iterations of the last substep (diagnostic)
+  float cdist[CS]; // contact distances of the last collision pass (diagnostic / tests)
+
+  BT_DEV BtEnv(const BtDev& m_, float* s_, int lane_) : m(m_), s(s_), lane(lane_), niter(0) {}
+
+  // ------------------------------------------------------------------ scratch regions
+  BT_DEV float* qpos() const { return s + m.o_qpos; }
+  BT_DEV float* qvel() const { return s + m.o_qvel; }
+  BT_DEV float* act() const { return s + m.o_act; }
+  BT_DEV float* ctrl() const { return s + m.o_ctrl; }
+  BT_DEV float* warm() const { return s + m.o_warm; }
+  BT_DEV float* xpos() const { return s + m.o_xpos; }
+  BT_DEV float* xquat() const { return s + m.o_xquat; }
+  BT_DEV float* cdof() const { return s + m.o_cdof; }
+  BT_DEV float* crb() const { return s + m.o_crb; }
+  BT_DEV float* LD() const { return s + m.o_LD; }
+  BT_DEV float* Dinv() const { return s + m.o_Dinv; }
+  BT_DEV float* T() const { return s + m.o_T; }
+  BT_DEV float* ref() const { return s + m.o_ref; }
+  BT_DEV float* aforce() const { return s + m.o_aforce; }
+  BT_DEV float* actdot() const { return s + m.o_actdot; }
+  BT_DEV float* qfrc_smooth() const { return s + m.o_qfrc_smooth; }
+  BT_DEV float* qacc_smooth() const { return s + m.o_qacc_smooth; }
+  BT_DEV float* qacc() const { return s + m.o_qacc; }
+  BT_DEV float* xv() const { return s + m.o_x; }
+  BT_DEV float* search() const { return s + m.o_search; }
+  BT_DEV float* qfrc_c() const { return s + m.o_qfrc_c; }
+  // T-region views during the constraint phase
+  BT_DEV float* congeo() const { return T(); }                          // [ncon][12] off(3) frame(9)
+  BT_DEV float* wrench() const { return T() + 12 * m.ncon; }            // [ncon][6]
+  BT_DEV float* cbA() const { return T() + 18 * m.ncon; }               // [ncb][6]
+
+  // ================================================================== P1: forward tree pass
+  // kinematics + cdof + cinert + cvel/cdof_dot/cacc + body-local cfrc in ONE root->leaves sweep
+  // (MJX: smooth.kinematics, com_pos, com_vel, rne forward half, passive fluid).
+  BT_DEV void body_forward(int b) {
+    const int p = BT_LDG(m.body_parentid + b);
+    float pos[3], quat[4], cvel[6], cacc[6];
+    float* cv = LD();  // cvel at 12*b, cacc at 12*b+6 (LD is not live during this pass)
+    if (p == 0) {
+      pos[0] = pos[1] = pos[2] = 0.f;
+      quat[0] = 1.f; quat[1] = quat[2] = quat[3] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 6; k++) cvel[k] = 0.f;
+      cacc[0] = cacc[1] = cacc[2] = 0.f;
+      cacc[3] = -m.grav_x; cacc[4] = -m.grav_y; cacc[5] = -m.grav_z;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 3; k++) pos[k] = xpos()[3 * p + k];
+#pragma unroll
+      for (int k = 0; k < 4; k++) quat[k] = xquat()[4 * p + k];
+#pragma unroll
+      for (int k = 0; k < 6; k++) { cvel[k] = cv[12 * p + k]; cacc[k] = cv[12 * p + 6 + k]; }
+    }
+    {
+      float bp[3] = {BT_LDG(m.body_pos + 3 * b), BT_LDG(m.body_pos + 3 * b + 1), BT_LDG(m.body_pos + 3 * b + 2)};
+      float bq[4] = {BT_LDG(m.body_quat + 4 * b), BT_LDG(m.body_quat + 4 * b + 1), BT_LDG(m.body_quat + 4 * b + 2),
+                     BT_LDG(m.body_quat + 4 * b + 3)};
+      float r[3], q2[4];
+      bt_rotate(bp, quat, r);
+      pos[0] += r[0]; pos[1] += r[1]; pos[2] += r[2];
+      bt_quat_mul(quat, bq, q2);
+      quat[0] = q2[0]; quat[1] = q2[1]; quat[2] = q2[2]; quat[3] = q2[3];
+    }
+    const int jadr = BT_LDG(m.body_jntadr + b), jnum = BT_LDG(m.body_jntnum + b);
+    const int rs = BT_LDG(m.body_ref + b);
+    float rp[3];
+    if (p == 0) {
+      if (jnum > 0 && BT_LDG(m.jnt_type + jadr) == BT_JNT_FREE) {
+        const int qa = BT_LDG(m.jnt_qposadr + jadr);
+        rp[0] = qpos()[qa]; rp[1] = qpos()[qa + 1]; rp[2] = qpos()[qa + 2];
+      } else {
+        rp[0] = pos[0]; rp[1] = pos[1]; rp[2] = pos[2];
+      }
+      ref()[3 * rs] = rp[0]; ref()[3 * rs + 1] = rp[1]; ref()[3 * rs + 2] = rp[2];
+    } else {
+      rp[0] = ref()[3 * rs]; rp[1] = ref()[3 * rs + 1]; rp[2] = ref()[3 * rs + 2];
+    }
+    for (int jj = 0; jj < jnum; jj++) {
+      const int j = jadr + jj, qa = BT_LDG(m.jnt_qposadr + j), da = BT_LDG(m.jnt_dofadr + j);
+      if (BT_LDG(m.jnt_type + j) == BT_JNT_FREE) {
+        pos[0] = qpos()[qa]; pos[1] = qpos()[qa + 1]; pos[2] = qpos()[qa + 2];
+        quat[0] = qpos()[qa + 3]; quat[1] = qpos()[qa + 4]; quat[2] = qpos()[qa + 5]; quat[3] = qpos()[qa + 6];
+        {  // x / norm(x), as mjx math.normalize
+          const float nrm = sqrtf(quat[0] * quat[0] + quat[1] * quat[1] + quat[2] * quat[2] + quat[3] * quat[3]);
+          quat[0] /= nrm; quat[1] /= nrm; quat[2] /= nrm; quat[3] /= nrm;
+        }
+        // MJX kinematics stores the normalised quaternion back into qpos
+        qpos()[qa + 3] = quat[0]; qpos()[qa + 4] = quat[1]; qpos()[qa + 5] = quat[2]; qpos()[qa + 6] = quat[3];
+        float R[9], off[3] = {rp[0] - pos[0], rp[1] - pos[1], rp[2] - pos[2]};
+        bt_quat_to_mat(quat, R);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          float* c = cdof() + 6 * (da + k);
+          c[0] = c[1] = c[2] = c[3] = c[4] = c[5] = 0.f;
+          c[3 + k] = 1.f;
+          cvel[3 + k] += qvel()[da + k];
+        }
+        float dv[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          float c[6], cd[6];
+          c[0] = R[k]; c[1] = R[3 + k]; c[2] = R[6 + k];
+          bt_cross(c, off, c + 3);
+          float* cs = cdof() + 6 * (da + 3 + k);
+          const float qv = qvel()[da + 3 + k];
+          bt_motion_cross(cvel, c, cd);
+#pragma unroll
+          for (int i = 0; i < 6; i++) { cs[i] = c[i]; cacc[i] += cd[i] * qv; dv[i] += c[i] * qv; }
+        }
+#pragma unroll
+        for (int i = 0; i < 6; i++) cvel[i] += dv[i];
+      } else {
+        float jp[3] = {BT_LDG(m.jnt_pos + 3 * j), BT_LDG(m.jnt_pos + 3 * j + 1), BT_LDG(m.jnt_pos + 3 * j + 2)};
+        float ja[3] = {BT_LDG(m.jnt_axis + 3 * j), BT_LDG(m.jnt_axis + 3 * j + 1), BT_LDG(m.jnt_axis + 3 * j + 2)};
+        float anchor[3], c[6], r[3], ql[4], q2[4], cd[6];
+        bt_rotate(jp, quat, anchor);
+        anchor[0] += pos[0]; anchor[1] += pos[1]; anchor[2] += pos[2];
+        bt_rotate(ja, quat, c);
+        const float ang = 0.5f * (qpos()[qa] - BT_LDG(m.qpos0 + qa));
+        float sn, cs_;
+#ifdef __CUDACC__
+        sincosf(ang, &sn, &cs_);
+#else
+        sn = sinf(ang); cs_ = cosf(ang);
+#endif
+        ql[0] = cs_; ql[1] = ja[0] * sn; ql[2] = ja[1] * sn; ql[3] = ja[2] * sn;
+        bt_quat_mul(quat, ql, q2);
+        quat[0] = q2[0]; quat[1] = q2[1]; quat[2] = q2[2]; quat[3] = q2[3];
+        bt_rotate(jp, quat, r);
+        pos[0] = anchor[0] - r[0]; pos[1] = anchor[1] - r[1]; pos[2] = anchor[2] - r[2];
+        float off[3] = {rp[0] - anchor[0], rp[1] - anchor[1], rp[2] - anchor[2]};
+        bt_cross(c, off, c + 3);
+        const float qv = qvel()[da];
+        bt_motion_cross(cvel, c, cd);
+        float* cs = cdof() + 6 * da;
+#pragma unroll
+        for (int i = 0; i < 6; i++) { cs[i] = c[i]; cacc[i] += cd[i] * qv; cvel[i] += c[i] * qv; }
+      }
+    }
+    bt_quat_normalize(quat);
+#pragma unroll
+    for (int k = 0; k < 3; k++) xpos()[3 * b + k] = pos[k];
+#pragma unroll
+    for (int k = 0; k < 4; k++) xquat()[4 * b + k] = quat[k];
+#pragma unroll
+    for (int k = 0; k < 6; k++) { cv[12 * b + k] = cvel[k]; cv[12 * b + 6 + k] = cacc[k]; }
+    // body inertia about the tree reference point, world axes
+    const float mass = BT_LDG(m.body_mass + b);
+    float ci[10], cf[6];
+    {
+      float ip[3] = {BT_LDG(m.body_ipos + 3 * b), BT_LDG(m.body_ipos + 3 * b + 1), BT_LDG(m.body_ipos + 3 * b + 2)};
+      float iq[4] = {BT_LDG(m.body_iquat + 4 * b), BT_LDG(m.body_iquat + 4 * b + 1), BT_LDG(m.body_iquat + 4 * b + 2),
+                     BT_LDG(m.body_iquat + 4 * b + 3)};
+      float in[3] = {BT_LDG(m.body_inertia + 3 * b), BT_LDG(m.body_inertia + 3 * b + 1), BT_LDG(m.body_inertia + 3 * b + 2)};
+      float r[3], q2[4], R[9], off[3];
+      bt_rotate(ip, quat, r);
+      off[0] = pos[0] + r[0] - rp[0]; off[1] = pos[1] + r[1] - rp[1]; off[2] = pos[2] + r[2] - rp[2];
+      bt_quat_mul(quat, iq, q2);
+      bt_quat_to_mat(q2, R);
+      const float oo = bt_dot3(off, off);
+      ci[0] = R[0] * R[0] * in[0] + R[1] * R[1] * in[1] + R[2] * R[2] * in[2] + mass * (oo - off[0] * off[0]);
+      ci[1] = R[3] * R[3] * in[0] + R[4] * R[4] * in[1] + R[5] * R[5] * in[2] + mass * (oo - off[1] * off[1]);
+      ci[2] = R[6] * R[6] * in[0] + R[7] * R[7] * in[1] + R[8] * R[8] * in[2] + mass * (oo - off[2] * off[2]);
+      ci[3] = R[0] * R[3] * in[0] + R[1] * R[4] * in[1] + R[2] * R[5] * in[2] - mass * off[0] * off[1];
+      ci[4] = R[0] * R[6] * in[0] + R[1] * R[7] * in[1] + R[2] * R[8] * in[2] - mass * off[0] * off[2];
+      ci[5] = R[3] * R[6] * in[0] + R[4] * R[7] * in[1] + R[5] * R[8] * in[2] - mass * off[1] * off[2];
+      ci[6] = mass * off[0]; ci[7] = mass * off[1]; ci[8] = mass * off[2]; ci[9] = mass;
+      float t1[6], t2[6], t3[6];
+      bt_inert_mul(ci, cacc, t1);
+      bt_inert_mul(ci, cvel, t2);
+      bt_motion_cross_force(cvel, t2, t3);
+#pragma unroll
+      for (int k = 0; k < 6; k++) cf[k] = t1[k] + t3[k];
+      // passive fluid forces (inertia-box model): a wrench on the body, folded into cfrc with opposite sign
+      if ((m.density > 0.f || m.viscosity > 0.f) && mass > 0.f) {
+        float box[3] = {BT_LDG(m.body_fluidbox + 3 * b), BT_LDG(m.body_fluidbox + 3 * b + 1), BT_LDG(m.body_fluidbox + 3 * b + 2)};
+        float c[3], lin[3], lang[3], llin[3], lf[6] = {0, 0, 0, 0, 0, 0};
+        bt_cross(off, cvel, c);
+        lin[0] = cvel[3] - c[0]; lin[1] = cvel[4] - c[1]; lin[2] = cvel[5] - c[2];
+        bt_matT_vec(R, cvel, lang);
+        bt_matT_vec(R, lin, llin);
+        if (m.viscosity > 0.f) {
+          const float diam = (box[0] + box[1] + box[2]) * (1.0f / 3.0f);
+          const float ka = 3.14159265358979f * diam * diam * diam * m.viscosity, kl = 3.0f * 3.14159265358979f * diam * m.viscosity;
+#pragma unroll
+          for (int k = 0; k < 3; k++) { lf[k] = -lang[k] * ka; lf[3 + k] = -llin[k] * kl; }
+        }
+        if (m.density > 0.f) {
+          const float b0 = box[0], b1 = box[1], b2 = box[2];
+          const float q0 = b0 * b0 * b0 * b0, q1 = b1 * b1 * b1 * b1, q2_ = b2 * b2 * b2 * b2;
+          const float sv[3] = {b1 * b2, b0 * b2, b0 * b1};
+          const float sa[3] = {b0 * (q1 + q2_), b1 * (q0 + q2_), b2 * (q0 + q1)};
+#pragma unroll
+          for (int k = 0; k < 3; k++) {
+            lf[3 + k] -= 0.5f * m.density * sv[k] * fabsf(llin[k]) * llin[k];
+            lf[k] -= m.density * sa[k] * fabsf(lang[k]) * lang[k] * (1.0f / 64.0f);
+          }
+        }
+        float tq[3], fc[3], oxf[3];
+        bt_mat_vec(R, lf, tq);
+        bt_mat_vec(R, lf + 3, fc);
+        bt_cross(off, fc, oxf);
+        cf[0] -= tq[0] + oxf[0]; cf[1] -= tq[1] + oxf[1]; cf[2] -= tq[2] + oxf[2];
+        cf[3] -= fc[0]; cf[4] -= fc[1]; cf[5] -= fc[2];
+      }
+    }
+    float* cr = crb() + 10 * b;
+#pragma unroll
+    for (int k = 0; k < 10; k++) cr[k] = ci[k];
+    float* cfs = T() + 6 * b;
+#pragma unroll
+    for (int k = 0; k < 6; k++) cfs[k] = cf[k];
+  }
+
+  BT_DEV void tree_forward() {
+    if (lane == 0) {
+      xpos()[0] = xpos()[1] = xpos()[2] = 0.f;
+      xquat()[0] = 1.f; xquat()[1] = xquat()[2] = xquat()[3] = 0.f;
+    }
+    for (int L = 0; L < m.nlevel; L++) {
+      const int a0 = BT_LDG(m.level_adr + L), a1 = BT_LDG(m.level_adr + L + 1);
+      for (int idx = a0 + lane; idx < a1; idx += G) body_forward(BT_LDG(m.level_body + idx));
+      W::sync();
+    }
+  }
+
+  // ================================================================== P2: backward tree pass (crb + cfrc)
+  BT_DEV void tree_backward() {
+    for (int L = m.nlevel - 2; L >= 0; L--) {
+      const int a0 = BT_LDG(m.level_adr + L), a1 = BT_LDG(m.level_adr + L + 1);
+      const int nitem = (a1 - a0) * 16;
+      for (int it = lane; it < nitem; it += G) {
+        const int b = BT_LDG(m.level_body + a0 + (it >> 4)), k = it & 15;
+        const int c0 = BT_LDG(m.child_adr + b), c1 = BT_LDG(m.child_adr + b + 1);
+        if (k < 10) {
+          float acc = crb()[10 * b + k];
+          for (int c = c0; c < c1; c++) acc += crb()[10 * BT_LDG(m.child_id + c) + k];
+          crb()[10 * b + k] = acc;
+        } else {
+          float acc = T()[6 * b + k - 10];
+          for (int c = c0; c < c1; c++) acc += T()[6 * BT_LDG(m.child_id + c) + k - 10];
+          T()[6 * b + k - 10] = acc;
+        }
+      }
+      W::sync();
+    }
+  }
+
+  // ================================================================== P3: actuation + smooth generalized forces
+  BT_DEV void smooth_forces() {
+    // transmission + fwd_actuation, one lane per actuator
+    for (int u = lane; u < m.nu; u += G) {
+      const float gear = BT_LDG(m.actuator_gear + u);
+      float len = 0.f, vel = 0.f;
+      for (int w = BT_LDG(m.act_wrap_adr + u); w < BT_LDG(m.act_wrap_adr + u + 1); w++) {
+        const float cf = BT_LDG(m.act_wrap_coef + w);
+        len += cf * qpos()[BT_LDG(m.act_wrap_qadr + w)];
+        vel += cf * qvel()[BT_LDG(m.act_wrap_dadr + w)];
+      }
+      len *= gear; vel *= gear;
+      float c = ctrl()[u];
+      if (BT_LDG(m.actuator_ctrllimited + u))
+        c = bt_clampf(c, BT_LDG(m.actuator_ctrlrange + 2 * u), BT_LDG(m.actuator_ctrlrange + 2 * u + 1));
+      float ca = c;
+      const int aa = BT_LDG(m.actuator_actadr + u);
+      if (aa >= 0) {
+        float tau = BT_LDG(m.actuator_dynprm + 3 * u);
+        tau = tau < BT_MINVAL ? BT_MINVAL : tau;
+        ca = act()[aa];
+        actdot()[aa] = (c - ca) / tau;
+      }
+      float gain = BT_LDG(m.actuator_gainprm + 3 * u);
+      if (BT_LDG(m.actuator_gaintype + u) == 1)
+        gain += BT_LDG(m.actuator_gainprm + 3 * u + 1) * len + BT_LDG(m.actuator_gainprm + 3 * u + 2) * vel;
+      float bias = 0.f;
+      if (BT_LDG(m.actuator_biastype + u) == 1)
+        bias = BT_LDG(m.actuator_biasprm + 3 * u) + BT_LDG(m.actuator_biasprm + 3 * u + 1) * len +
+               BT_LDG(m.actuator_biasprm + 3 * u + 2) * vel;
+      float f = gain * ca + bias;
+      if (BT_LDG(m.actuator_forcelimited + u))
+        f = bt_clampf(f, BT_LDG(m.actuator_forcerange + 2 * u), BT_LDG(m.actuator_forcerange + 2 * u + 1));
+      aforce()[u] = f;
+    }
+    W::sync();
+    for (int i = lane; i < m.nv; i += G) {
+      const float bias = bt_dot6(cdof() + 6 * i, T() + 6 * BT_LDG(m.dof_bodyid + i));
+      float f = -BT_LDG(m.dof_damping + i) * qvel()[i];
+      const int qa = BT_LDG(m.dof_qposadr + i);
+      if (qa >= 0) f -= BT_LDG(m.dof_stiffness + i) * (qpos()[qa] - BT_LDG(m.dof_springref + i));
+      float fa = 0.f;
+      for (int k = BT_LDG(m.dofact_adr + i); k < BT_LDG(m.dofact_adr + i + 1); k++)
+        fa += BT_LDG(m.dofact_coef + k) * aforce()[BT_LDG(m.dofact_u + k)];
+      qfrc_smooth()[i] = f - bias + fa;
+    }
+    W::sync();
+  }
+
+  // ================================================================== P4: tree-sparse M (+ h*damping) into LD
+  BT_DEV void build_M(float hdamp) {
+    float* buf = T();  // 6 per dof: crb[body(i)] * cdof_i
+    for (int i = lane; i < m.nv; i += G) bt_inert_mul(crb() + 10 * BT_LDG(m.dof_bodyid + i), cdof() + 6 * i, buf + 6 * i);
+    W::sync();
+    for (int e = lane; e < m.nM; e += G) {
+      const int i = BT_LDG(m.M_row + e), j = BT_LDG(m.M_col + e);
+      float v = bt_dot6(cdof() + 6 * j, buf + 6 * i);
+      if (i == j) v += BT_LDG(m.dof_armature + i) + hdamp * BT_LDG(m.dof_damping + i);
+      LD()[e] = v;
+    }
+    W::sync();
+  }
+
+  // y = M v for lane-owned dofs (reads the *unfactored* M in LD; v in scratch)
+  BT_DEV void mul_M(const float* v, float y[DS]) {
+#pragma unroll
+    for (int sl = 0; sl < DS; sl++) {
+      const int i = lane + sl * G;
+      float acc = 0.f;
+      if (i < m.nv) {
+        const int ad = BT_LDG(m.dof_Madr + i), d = BT_LDG(m.dof_depth + i);
+        for (int a = 0; a <= d; a++) acc += LD()[ad + a] * v[BT_LDG(m.M_col + ad + a)];
+        const int nd = BT_LDG(m.dof_subtreenum + i);
+        for (int i2 = i + 1; i2 < i + nd; i2++)
+          acc += LD()[BT_LDG(m.dof_Madr + i2) + BT_LDG(m.dof_depth + i2) - d] * v[i2];
+      }
+      y[sl] = acc;
+    }
+  }
+
+  // ================================================================== P6: in-place L'DL (MuJoCo mj_factorM order)
+  BT_DEV void factor() {
+    float* ld = LD();
+    for (int k = m.nv - 1; k >= 0; k--) {
+      const int ad = BT_LDG(m.dof_Madr + k), d = BT_LDG(m.dof_depth + k);
+      const float inv = 1.0f / ld[ad];
+      if (lane == 0) Dinv()[k] = inv;
+      if (d == 0) continue;
+      const int nt = d * (d + 1) / 2;
+      for (int t = lane; t < nt; t += G) {
+        const int ab = BT_LDG(m.tri_ab + t), a = ab & 255, b = ab >> 8;
+        const int ia = BT_LDG(m.M_colMadr + ad + a);
+        ld[ia + b - a] -= ld[ad + a] * inv * ld[ad + b];
+      }
+      W::sync();
+      for (int a = 1 + lane; a <= d; a += G) ld[ad + a] *= inv;
+      W::sync();
+    }
+    W::sync();
+  }
+
+  // x <- M^-1 x (in scratch), using the factor in LD / Dinv
+  BT_DEV void solve(float* x) {
+    const float* ld = LD();
+    for (int i = m.nv - 1; i > 0; i--) {
+      const int d = BT_LDG(m.dof_depth + i);
+      if (d == 0) continue;
+      const int ad = BT_LDG(m.dof_Madr + i);
+      const float xi = x[i];
+      for (int a = 1 + lane; a <= d; a += G) x[BT_LDG(m.M_col + ad + a)] -= ld[ad + a] * xi;
+      W::sync();
+    }
+    for (int i = lane; i < m.nv; i += G) x[i] *= Dinv()[i];
+    W::sync();
+    for (int j = 0; j < m.nv - 1; j++) {
+      const int nd = BT_LDG(m.dof_subtreenum + j);
+      if (nd == 1) continue;
+      const int dj = BT_LDG(m.dof_depth + j);
+      const float xj = x[j];
+      for (int i2 = j + 1 + lane; i2 < j + nd; i2 += G)
+        x[i2] -= ld[BT_LDG(m.dof_Madr + i2) + BT_LDG(m.dof_depth + i2) - dj] * xj;
+      W::sync();
+    }
+  }
+
+  // ================================================================== P8: collision (static contact list)
+  BT_DEV void geom_pose(int g, float* gp, float* gR) {
+    const int b = BT_LDG(m.cgeom_bodyid + g);
+    float lp[3] = {BT_LDG(m.cgeom_pos + 3 * g), BT_LDG(m.cgeom_pos + 3 * g + 1), BT_LDG(m.cgeom_pos + 3 * g + 2)};
+    float lq[4] = {BT_LDG(m.cgeom_quat + 4 * g), BT_LDG(m.cgeom_quat + 4 * g + 1), BT_LDG(m.cgeom_quat + 4 * g + 2),
+                   BT_LDG(m.cgeom_quat + 4 * g + 3)};
+    float r[3], q2[4];
+    bt_rotate(lp, xquat() + 4 * b, r);
+    gp[0] = xpos()[3 * b] + r[0]; gp[1] = xpos()[3 * b + 1] + r[1]; gp[2] = xpos()[3 * b + 2] + r[2];
+    bt_quat_mul(xquat() + 4 * b, lq, q2);
+    bt_quat_to_mat(q2, gR);
+  }
+  static BT_DEV void make_frame(const float* n, float* fr) {
+    float a[3] = {n[0], n[1], n[2]}, b[3] = {0.f, 0.f, 0.f};
+    if (a[1] > -0.5f && a[1] < 0.5f) b[1] = 1.f; else b[2] = 1.f;
+    const float ab = bt_dot3(a, b);
+    b[0] -= a[0] * ab; b[1] -= a[1] * ab; b[2] -= a[2] * ab;
+    const float bn = 1.0f / sqrtf(bt_dot3(b, b));
+    b[0] *= bn; b[1] *= bn; b[2] *= bn;
+    fr[0] = a[0]; fr[1] = a[1]; fr[2] = a[2];
+    fr[3] = b[0]; fr[4] = b[1]; fr[5] = b[2];
+    bt_cross(a, b, fr + 6);
+  }
+  static BT_DEV void closest_seg(const float* a0, const float* a1, const float* b0, const float* b1, float* pa, float* pb) {
+    float da[3], db[3], am[3], bm[3], tr[3];
+    for (int k = 0; k < 3; k++) { da[k] = a1[k] - a0[k]; db[k] = b1[k] - b0[k]; }
+    const float la = sqrtf(bt_dot3(da, da)), lb = sqrtf(bt_dot3(db, db));
+    const float ia = la > 0.f ? 1.0f / la : 1.0f, ib = lb > 0.f ? 1.0f / lb : 1.0f;
+    for (int k = 0; k < 3; k++) { da[k] *= ia; db[k] *= ib; }
+    const float ha = 0.5f * la, hb = 0.5f * lb;
+    for (int k = 0; k < 3; k++) { am[k] = a0[k] + da[k] * ha; bm[k] = b0[k] + db[k] * hb; tr[k] = am[k] - bm[k]; }
+    const float dab = bt_dot3(da, db), dat = bt_dot3(da, tr), dbt = bt_dot3(db, tr);
+    const float den = 1.f - dab * dab;
+    const float ota = (-dat + dab * dbt) / (den + 1e-6f), otb = dbt + ota * dab;
+    const float ta = bt_clampf(ota, -ha, ha), tb = bt_clampf(otb, -hb, hb);
+    float ba[3], bb[3], na[3], nb[3], v[3];
+    for (int k = 0; k < 3; k++) { ba[k] = am[k] + da[k] * ta; bb[k] = bm[k] + db[k] * tb; }
+    for (int k = 0; k < 3; k++) v[k] = bb[k] - am[k];
+    float t = bt_clampf(bt_dot3(v, da), -ha, ha);
+    for (int k = 0; k < 3; k++) na[k] = am[k] + da[k] * t;
+    for (int k = 0; k < 3; k++) v[k] = ba[k] - bm[k];
+    t = bt_clampf(bt_dot3(v, db), -hb, hb);
+    for (int k = 0; k < 3; k++) nb[k] = bm[k] + db[k] * t;
+    float d1[3], d2[3];
+    for (int k = 0; k < 3; k++) { d1[k] = na[k] - bb[k]; d2[k] = ba[k] - nb[k]; }
+    if (bt_dot3(d1, d1) < bt_dot3(d2, d2)) { for (int k = 0; k < 3; k++) { pa[k] = na[k]; pb[k] = bb[k]; } }
+    else { for (int k = 0; k < 3; k++) { pa[k] = ba[k]; pb[k] = nb[k]; } }
+  }
+
+  // fills congeo (contact point relative to the tree reference point + frame) and returns dist per lane-owned contact
+  BT_DEV void collide() {
+#pragma unroll
+    for (int sl = 0; sl < CS; sl++) {
+      const int c = lane + sl * G;
+      cdist[sl] = 1.0f;
+      if (c >= m.ncon) continue;
+      const int g1 = BT_LDG(m.con_g1 + c), g2 = BT_LDG(m.con_g2 + c), fn = BT_LDG(m.con_fn + c);
+      float p1[3], R1[9], p2[3], R2[9], pos[3], fr[9], dist;
+      geom_pose(g1, p1, R1);
+      geom_pose(g2, p2, R2);
+      const float s20 = BT_LDG(m.cgeom_size + 3 * g2), s21 = BT_LDG(m.cgeom_size + 3 * g2 + 1), s22 = BT_LDG(m.cgeom_size + 3 * g2 + 2);
+      if (fn == BT_FN_PLANE_CAPSULE) {
+        const float n[3] = {R1[2], R1[5], R1[8]}, ax[3] = {R2[2], R2[5], R2[8]};
+        const float na = bt_dot3(n, ax);
+        float b[3] = {ax[0] - n[0] * na, ax[1] - n[1] * na, ax[2] - n[2] * na};
+        const float bn = sqrtf(bt_dot3(b, b));
+        if (bn < 0.5f) {
+          const bool usey = n[1] > -0.5f && n[1] < 0.5f;
+          b[0] = usey ? R1[1] : R1[2]; b[1] = usey ? R1[4] : R1[5]; b[2] = usey ? R1[7] : R1[8];
+        } else {
+          const float ib = 1.0f / bn;
+          b[0] *= ib; b[1] *= ib; b[2] *= ib;
+        }
+        fr[0] = n[0]; fr[1] = n[1]; fr[2] = n[2]; fr[3] = b[0]; fr[4] = b[1]; fr[5] = b[2];
+        bt_cross(n, b, fr + 6);
+        const float sg = BT_LDG(m.con_sub + c) == 0 ? 1.f : -1.f;
+        float sp[3] = {p2[0] + sg * ax[0] * s21, p2[1] + sg * ax[1] * s21, p2[2] + sg * ax[2] * s21};
+        float df[3] = {sp[0] - p1[0], sp[1] - p1[1], sp[2] - p1[2]};
+        dist = bt_dot3(df, n) - s20;
+        for (int k = 0; k < 3; k++) pos[k] = sp[k] - n[k] * (s20 + 0.5f * dist);
+      } else if (fn == BT_FN_PLANE_ELLIPSOID || fn == BT_FN_PLANE_SPHERE) {
+        const float n[3] = {R1[2], R1[5], R1[8]};
+        if (fn == BT_FN_PLANE_SPHERE) {
+          float df[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+          dist = bt_dot3(df, n) - s20;
+          for (int k = 0; k < 3; k++) pos[k] = p2[k] - n[k] * (s20 + 0.5f * dist);
+        } else {
+          float ln[3], sup[3], w[3];
+          bt_matT_vec(R2, n, ln);
+          sup[0] = ln[0] * s20; sup[1] = ln[1] * s21; sup[2] = ln[2] * s22;
+          const float isn = 1.0f / sqrtf(bt_dot3(sup, sup));
+          sup[0] = -sup[0] * isn * s20; sup[1] = -sup[1] * isn * s21; sup[2] = -sup[2] * isn * s22;
+          bt_mat_vec(R2, sup, w);
+          for (int k = 0; k < 3; k++) pos[k] = p2[k] + w[k];
+          float df[3] = {pos[0] - p1[0], pos[1] - p1[1], pos[2] - p1[2]};
+          dist = bt_dot3(df, n);
+          for (int k = 0; k < 3; k++) pos[k] -= n[k] * dist * 0.5f;
+        }
+        make_frame(n, fr);
+      } else {  // capsule-capsule
+        const float s10 = BT_LDG(m.cgeom_size + 3 * g1), s11 = BT_LDG(m.cgeom_size + 3 * g1 + 1);
+        float a0[3], a1[3], b0[3], b1[3], pa[3], pb[3];
+        for (int k = 0; k < 3; k++) {
+          a0[k] = p1[k] - R1[3 * k + 2] * s11; a1[k] = p1[k] + R1[3 * k + 2] * s11;
+          b0[k] = p2[k] - R2[3 * k + 2] * s21; b1[k] = p2[k] + R2[3 * k + 2] * s21;
+        }
+        closest_seg(a0, a1, b0, b1, pa, pb);
+        float n[3] = {pb[0] - pa[0], pb[1] - pa[1], pb[2] - pa[2]};
+        const float len = sqrtf(bt_dot3(n, n));
+        if (len < BT_MINVAL) { n[0] = 1.f; n[1] = 0.f; n[2] = 0.f; }
+        else { const float il = 1.0f / len; n[0] *= il; n[1] *= il; n[2] *= il; }
+        dist = len - (s10 + s20);
+        for (int k = 0; k < 3; k++) pos[k] = pa[k] + n[k] * (s10 + 0.5f * dist);
+        make_frame(n, fr);
+      }
+      cdist[sl] = dist;
+      const int rs = BT_LDG(m.con_ref + c);
+      float* cg = congeo() + 12 * c;
+      cg[0] = pos[0] - ref()[3 * rs]; cg[1] = pos[1] - ref()[3 * rs + 1]; cg[2] = pos[2] - ref()[3 * rs + 2];
+#pragma unroll
+      for (int k = 0; k < 9; k++) cg[3 + k] = fr[k];
+    }
+    W::sync();
+  }
+
+  // ================================================================== matrix-free constraint Jacobian
+  // out[sl][k] = frame_k . (J_point(body2) - J_point(body1)) v   for lane-owned contacts
+  BT_DEV void jdot(const float* v, float out[CS][3]) {
+    const int nitem = m.ncb * 6;
+    for (int it = lane; it < nitem; it += G) {
+      const int cb = it / 6, k = it - cb * 6;
+      float acc = 0.f;
+      for (int e = BT_LDG(m.cb_adr + cb); e < BT_LDG(m.cb_adr + cb + 1); e++) {
+        const int d = BT_LDG(m.cb_dof + e);
+        acc += cdof()[6 * d + k] * v[d];
+      }
+      cbA()[it] = acc;
+    }
+    W::sync();
+#pragma unroll
+    for (int sl = 0; sl < CS; sl++) {
+      const int c = lane + sl * G;
+      out[sl][0] = out[sl][1] = out[sl][2] = 0.f;
+      if (c >= m.ncon) continue;
+      const int cb1 = BT_LDG(m.con_cb1 + c), cb2 = BT_LDG(m.con_cb2 + c);
+      float A[6] = {0, 0, 0, 0, 0, 0};
+      if (cb2 >= 0) for (int k = 0; k < 6; k++) A[k] += cbA()[6 * cb2 + k];
+      if (cb1 >= 0) for (int k = 0; k < 6; k++) A[k] -= cbA()[6 * cb1 + k];
+      const float* cg = congeo() + 12 * c;
+      float w[3];
+      bt_cross(A, cg, w);
+      w[0] += A[3]; w[1] += A[4]; w[2] += A[5];
+      out[sl][0] = bt_dot3(cg + 3, w); out[sl][1] = bt_dot3(cg + 6, w); out[sl][2] = bt_dot3(cg + 9, w);
+    }
+    W::sync();
+  }
+
+  // ================================================================== constraint rows (registers)
+  struct Efc {
+    float jar[CS][4];  // J qacc - aref per row
+    float D[CS][4];    // 0 => row absent / contact inactive
+    float mu[CS][2];
+    float ljar[DS];    // joint-limit rows (one per lane-owned dof)
+    float lD[DS];
+    float lsg[DS];     // +1 / -1; 0 => no row
+  };
+
+  BT_DEV void kbi(float sr0, float sr1, const float* si, float pos, float& k, float& b, float& imp) const {
+    float timeconst = sr0, dampratio = sr1;
+    float dmin = BT_LDG(si), dmax = BT_LDG(si + 1), width = BT_LDG(si + 2), mid = BT_LDG(si + 3), power = BT_LDG(si + 4);
+    if (timeconst < 2.f * m.timestep) timeconst = 2.f * m.timestep;  // refsafe
+    dmin = bt_clampf(dmin, BT_MINIMP, BT_MAXIMP);
+    dmax = bt_clampf(dmax, BT_MINIMP, BT_MAXIMP);
+    if (width < BT_MINVAL) width = BT_MINVAL;
+    mid = bt_clampf(mid, BT_MINIMP, BT_MAXIMP);
+    if (power < 1.f) power = 1.f;
+    k = 1.f / (dmax * dmax * timeconst * timeconst * dampratio * dampratio);
+    b = 2.f / (dmax * timeconst);
+    if (sr0 <= 0.f) k = -sr0 / (dmax * dmax);
+    if (sr1 <= 0.f) b = -sr1 / dmax;
+    const float x = fabsf(pos) / width;
+    const float ia = (1.f / powf(mid, power - 1.f)) * powf(x, power);
+    const float ib = 1.f - (1.f / powf(1.f - mid, power - 1.f)) * powf(1.f - x, power);
+    const float y = x < mid ? ia : ib;
+    float im = dmin + y * (dmax - dmin);
+    im = bt_clampf(im, dmin, dmax);
+    if (x > 1.f) im = dmax;
+    imp = im;
+  }
+
+  // make_constraint: fills D / mu / limit rows and the row-wise aref (returned for the jar initialisation)
+  BT_DEV void make_rows(Efc& e, float aref[CS][4], float laref[DS]) {
+    float jv[CS][3];
+    jdot(qvel(), jv);
+#pragma unroll
+    for (int sl = 0; sl < CS; sl++) {
+      const int c = lane + sl * G;
+#pragma unroll
+      for (int r = 0; r < 4; r++) { e.D[sl][r] = 0.f; e.jar[sl][r] = 0.f; aref[sl][r] = 0.f; }
+      e.mu[sl][0] = e.mu[sl][1] = 0.f;
+      if (c >= m.ncon) continue;
+      const float pos = cdist[sl] - BT_LDG(m.con_includemargin + c);
+      if (!(pos < 0.f)) continue;
+      float k, b, imp;
+      kbi(BT_LDG(m.con_solref + 2 * c), BT_LDG(m.con_solref + 2 * c + 1), m.con_solimp + 5 * c, pos, k, b, imp);
+      const float t = BT_LDG(m.con_invweight + c);
+      const int dim = BT_LDG(m.con_dim + c);
+      if (dim == 1) {
+        float R = t * (1.f - imp) / imp;
+        R = R < BT_MINVAL ? BT_MINVAL : R;
+        e.D[sl][0] = 1.f / R;
+        aref[sl][0] = -b * jv[sl][0] - k * imp * pos;
+      } else if (m.cone == BT_CONE_PYRAMIDAL) {
+#pragma unroll
+        for (int a = 0; a < 2; a++) {
+          const float mu = BT_LDG(m.con_mu + 2 * c + a);
+          e.mu[sl][a] = mu;
+          float R = (t + mu * mu * t) * 2.f * mu * mu / m.impratio * (1.f - imp) / imp;
+          R = R < BT_MINVAL ? BT_MINVAL : R;
+          e.D[sl][2 * a] = e.D[sl][2 * a + 1] = 1.f / R;
+          aref[sl][2 * a] = -b * (jv[sl][0] + mu * jv[sl][1 + a]) - k * imp * pos;
+          aref[sl][2 * a + 1] = -b * (jv[sl][0] - mu * jv[sl][1 + a]) - k * imp * pos;
+        }
+      } else {
+        // elliptic: rows 0 (normal), 1, 2 (friction); friction rows: pos 0 in aref, impedance from the normal
+        e.mu[sl][0] = BT_LDG(m.con_mu + 2 * c); e.mu[sl][1] = BT_LDG(m.con_mu + 2 * c + 1);
+        float R = t * (1.f - imp) / imp;
+        R = R < BT_MINVAL ? BT_MINVAL : R;
+        e.D[sl][0] = 1.f / R;
+        float Rf = t / m.impratio * (1.f - imp) / imp;
+        Rf = Rf < BT_MINVAL ? BT_MINVAL : Rf;
+        e.D[sl][1] = e.D[sl][2] = 1.f / Rf;
+        aref[sl][0] = -b * jv[sl][0] - k * imp * pos;
+        aref[sl][1] = -b * jv[sl][1];
+        aref[sl][2] = -b * jv[sl][2];
+      }
+    }
+#pragma unroll
+    for (int sl = 0; sl < DS; sl++) {
+      const int i = lane + sl * G;
+      e.lD[sl] = 0.f; e.lsg[sl] = 0.f; e.ljar[sl] = 0.f; laref[sl] = 0.f;
+      if (i >= m.nv || !BT_LDG(m.dof_limited + i)) continue;
+      const float q = qpos()[BT_LDG(m.dof_qposadr + i)];
+      const float dlo = q - BT_LDG(m.dof_range + 2 * i), dhi = BT_LDG(m.dof_range + 2 * i + 1) - q;
+      const float pos = (dlo < dhi ? dlo : dhi) - BT_LDG(m.dof_margin + i);
+      if (!(pos < 0.f)) continue;
+      const float sg = dlo < dhi ? 1.f : -1.f;
+      float k, b, imp;
+      kbi(BT_LDG(m.dof_solref + 2 * i), BT_LDG(m.dof_solref + 2 * i + 1), m.dof_solimp + 5 * i, pos, k, b, imp);
+      float R = BT_LDG(m.dof_invweight0 + i) * (1.f - imp) / imp;
+      R = R < BT_MINVAL ? BT_MINVAL : R;
+      e.lD[sl] = 1.f / R;
+      e.lsg[sl] = sg;
+      laref[sl] = -b * sg * qvel()[i] - k * imp * pos;
+    }
+  }
+
+  // jar for a candidate qacc (scratch vector a)
+  BT_DEV void init_jar(Efc& e, const float aref[CS][4], const float laref[DS], const float* a) {
+    float jq[CS][3];
+    jdot(a, jq);
+#pragma unroll
+    for (int sl = 0; sl < CS; sl++) row_combine(e, sl, jq[sl], e.jar[sl]);
+#pragma unroll
+    for (int sl = 0; sl < CS; sl++)
+#pragma unroll
+      for (int r = 0; r < 4; r++) e.jar[sl][r] -= aref[sl][r];
+#pragma unroll
+    for (int sl = 0; sl < DS; sl++) {
+      const int i = lane + sl * G;
+      e.ljar[sl] = (i < m.nv ? e.lsg[sl] * a[i] : 0.f) - laref[sl];
+    }
+  }
+  // base (normal, t1, t2) projections -> row values
+  BT_DEV void row_combine(const Efc& e, int sl, const float base[3], float out[4]) const {
+    if (m.cone == BT_CONE_PYRAMIDAL) {
+      out[0] = base[0] + e.mu[sl][0] * base[1]; out[1] = base[0] - e.mu[sl][0] * base[1];
+      out[2] = base[0] + e.mu[sl][1] * base[2]; out[3] = base[0] - e.mu[sl][1] * base[2];
+    } else {
+      out[0] = base[0]; out[1] = base[1]; out[2] = base[2]; out[3] = 0.f;
+    }
+  }
+
+  // elliptic cone helper: zone classification shared by cost / force / line search (oracle update_constraint)
+  // returns 0 top, 1 bottom, 2 middle
+  BT_DEV int ell_zone(const Efc& e, int sl, const float ja[3], float& mu0, float& Dm, float& N, float& Tn, float u[3]) const {
+    const float Dn = e.D[sl][0];
+    mu0 = e.mu[sl][0] * sqrtf(Dn / e.D[sl][1]);
+    Dm = Dn / (mu0 * mu0 * (1.f + mu0 * mu0));
+    u[0] = ja[0] * mu0; u[1] = ja[1] * e.mu[sl][0]; u[2] = ja[2] * e.mu[sl][1];
+    N = u[0];
+    Tn = sqrtf(u[1] * u[1] + u[2] * u[2]);
+    if (N >= mu0 * Tn || (Tn <= 0.f && N >= 0.f)) return 0;
+    if (mu0 * N + Tn <= 0.f || (Tn <= 0.f && N < 0.f)) return 1;
+    return 2;
+  }
+
+  // cost of the constraint rows at jar; optionally the base-direction forces per contact and limit forces
+  BT_DEV float rows_cost(const Efc& e, float fbase[CS][3], float lforce[DS], bool want_force) const {
+    float cost = 0.f;
+#pragma unroll
+    for (int sl = 0; sl < CS; sl++) {
+      float f[4] = {0.f, 0.f, 0.f, 0.f};
+      if (m.cone == BT_CONE_PYRAMIDAL || e.D[sl][1] == 0.f) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+          const float ja = e.jar[sl][r];
+          if (ja < 0.f) { f[r] = -e.D[sl][r] * ja; cost += 0.5f * e.D[sl][r] * ja * ja; }
+        }
+        if (want_force) {
+          fbase[sl][0] = f[0] + f[1] + f[2] + f[3];
+          fbase[sl][1] = e.mu[sl][0] * (f[0] - f[1]);
+          fbase[sl][2] = e.mu[sl][1] * (f[2] - f[3]);
+          if (m.cone != BT_CONE_PYRAMIDAL) { fbase[sl][0] = f[0]; fbase[sl][1] = fbase[sl][2] = 0.f; }
+        }
+      } else {
+        float mu0, Dm, N, Tn, u[3];
+        const int z = ell_zone(e, sl, e.jar[sl], mu0, Dm, N, Tn, u);
+        if (z == 1) {
+#pragma unroll
+          for (int r = 0; r < 3; r++) { const float ja = e.jar[sl][r]; f[r] = -e.D[sl][r] * ja; cost += 0.5f * e.D[sl][r] * ja * ja; }
+        } else if (z == 2) {
+          const float NmT = N - mu0 * Tn;
+          cost += 0.5f * Dm * NmT * NmT;
+          f[0] = -Dm * NmT * mu0;
+          f[1] = Dm * NmT * mu0 / Tn * u[1] * e.mu[sl][0];
+          f[2] = Dm * NmT * mu0 / Tn * u[2] * e.mu[sl][1];
+        }
+        if (want_force) { fbase[sl][0] = f[0]; fbase[sl][1] = f[1]; fbase[sl][2] = f[2]; }
+      }
+    }
+#pragma unroll
+    for (int sl = 0; sl < DS; sl++) {
+      const float ja = e.ljar[sl];
+      float f = 0.f;
+      if (ja < 0.f) { f = -e.lD[sl] * ja; cost += 0.5f * e.lD[sl] * ja * ja; }
+      if (want_force) lforce[sl] = f;
+    }
+    return W::allsum(cost);
+  }
+
+  // qfrc_constraint = J^T f  (per-dof gather over the contacts whose chain contains the dof) -> scratch + regs
+  BT_DEV void jt_force(const Efc& e, const float fbase[CS][3], const float lforce[DS], float qc[DS]) {
+#pragma unroll
+    for (int sl = 0; sl < CS; sl++) {
+      const int c = lane + sl * G;
+      if (c >= m.ncon) continue;
+      const float* cg = congeo() + 12 * c;
+      float F[3], tq[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) F[k] = cg[3 + k] * fbase[sl][0] + cg[6 + k] * fbase[sl][1] + cg[9 + k] * fbase[sl][2];
+      bt_cross(cg, F, tq);
+      float* w = wrench() + 6 * c;
+      w[0] = tq[0]; w[1] = tq[1]; w[2] = tq[2]; w[3] = F[0]; w[4] = F[1]; w[5] = F[2];
+    }
+    W::sync();
+#pragma unroll
+    for (int sl = 0; sl < DS; sl++) {
+      const int i = lane + sl * G;
+      float acc = 0.f;
+      if (i < m.nv) {
+        acc = e.lsg[sl] * lforce[sl];
+        for (int k = BT_LDG(m.dofcon_adr + i); k < BT_LDG(m.dofcon_adr + i + 1); k++)
+          acc += BT_LDG(m.dofcon_sign + k) * bt_dot6(cdof() + 6 * i, wrench() + 6 * BT_LDG(m.dofcon_c + k));
+        qfrc_c()[i] = acc;
+      }
+      qc[sl] = acc;
+    }
+    W::sync();
+  }
+
+  // ------------------------------------------------------------------ exact 1-D line search (MJX solver._linesearch)
+  struct LsPt { float alpha, cost, d0, d1; };
+
+  // evaluates NP trial step sizes at once: per lane partial (q0,q1,q2) sums over its rows, then warp sums
+  template <int NP>
+  BT_DEV void ls_eval(const Efc& e, const float jv[CS][4], const float ljv[DS], const float qg[3], const float* alpha, LsPt* out) const {
+    float q0[NP], q1[NP], q2[NP];
+#pragma unroll
+    for (int p = 0; p < NP; p++) { q0[p] = q1[p] = q2[p] = 0.f; }
+#pragma unroll
+    for (int sl = 0; sl < CS; sl++) {
+      if (m.cone == BT_CONE_PYRAMIDAL || e.D[sl][1] == 0.f) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+          const float D = e.D[sl][r], ja = e.jar[sl][r], v = jv[sl][r];
+          const float a0 = 0.5f * D * ja * ja, a1 = D * v * ja, a2 = 0.5f * D * v * v;
+#pragma unroll
+          for (int p = 0; p < NP; p++)
+            if (ja + alpha[p] * v < 0.f) { q0[p] += a0; q1[p] += a1; q2[p] += a2; }
+        }
+      } else if (e.D[sl][0] != 0.f) {
+        const float Dn = e.D[sl][0];
+        const float mu0 = e.mu[sl][0] * sqrtf(Dn / e.D[sl][1]);
+        const float Dm = Dn / (mu0 * mu0 * (1.f + mu0 * mu0));
+        const float u0 = e.jar[sl][0] * mu0, v0 = jv[sl][0] * mu0;
+        const float u1 = e.jar[sl][1] * e.mu[sl][0], v1 = jv[sl][1] * e.mu[sl][0];
+        const float u2 = e.jar[sl][2] * e.mu[sl][1], v2 = jv[sl][2] * e.mu[sl][1];
+        const float uu = u1 * u1 + u2 * u2, uv = u1 * v1 + u2 * v2, vv = v1 * v1 + v2 * v2;
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+          const float al = alpha[p];
+          const float N = u0 + al * v0;
+          const float Tsq = uu + al * (2.f * uv + al * vv);
+          const float Tn = sqrtf(Tsq > 0.f ? Tsq : 0.f);
+          if (N >= mu0 * Tn || (Tn <= 0.f && N >= 0.f)) {
+          } else if (mu0 * N + Tn <= 0.f || (Tn <= 0.f && N < 0.f)) {
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+              const float D = e.D[sl][r], ja = e.jar[sl][r], v = jv[sl][r];
+              q0[p] += 0.5f * D * ja * ja; q1[p] += D * v * ja; q2[p] += 0.5f * D * v * v;
+            }
+          } else {
+            const float N1 = v0, T1 = (uv + al * vv) / Tn;
+            const float T2 = vv / Tn - (uv + al * vv) * T1 / (Tn * Tn);
+            const float NmT = N - mu0 * Tn, dd = N1 - mu0 * T1;
+            const float c0 = 0.5f * Dm * NmT * NmT, c1 = Dm * NmT * dd, c2 = Dm * (dd * dd + NmT * (-mu0 * T2));
+            q0[p] += c0 - c1 * al + 0.5f * c2 * al * al;
+            q1[p] += c1 - c2 * al;
+            q2[p] += 0.5f * c2;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int sl = 0; sl < DS; sl++) {
+      const float D = e.lD[sl], ja = e.ljar[sl], v = ljv[sl];
+      const float a0 = 0.5f * D * ja * ja, a1 = D * v * ja, a2 = 0.5f * D * v * v;
+#pragma unroll
+      for (int p = 0; p < NP; p++)
+        if (ja + alpha[p] * v < 0.f) { q0[p] += a0; q1[p] += a1; q2[p] += a2; }
+    }
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+      const float s0 = W::allsum(q0[p]) + qg[0], s1 = W::allsum(q1[p]) + qg[1], s2 = W::allsum(q2[p]) + qg[2];
+      const float al = alpha[p];
+      out[p].alpha = al;
+      out[p].cost = al * al * s2 + al * s1 + s0;
+      out[p].d0 = 2.f * al * s2 + s1;
+      out[p].d1 = 2.f * s2 + (s2 == 0.f ? BT_MINVAL : 0.f);
+    }
+  }
+
+  // ================================================================== P9-P11: constraint solve (CG, primal in qacc)
+  // in: qfrc_smooth, qacc_smooth, warm (scratch), unfactored-M product Ma_warm (regs), factor in LD
+  // out: qacc, qfrc_c (scratch); warm <- qacc
+  BT_DEV void solve_constraints(const float Ma_warm[DS]) {
+    Efc e;
+    float qfs[DS], qas[DS];
+#pragma unroll
+    for (int sl = 0; sl < DS; sl++) {
+      const int i = lane + sl * G;
+      qfs[sl] = i < m.nv ? qfrc_smooth()[i] : 0.f;
+      qas[sl] = i < m.nv ? qacc_smooth()[i] : 0.f;
+    }
+    float Ma[DS], qc[DS];
+    float gauss, cost, prev_cost;
+    {
+      float aref[CS][4], laref[DS];
+      make_rows(e, aref, laref);
+      // warm-start selection (MJX solver.solve): keep the cheaper of qacc_warmstart / qacc_smooth
+      init_jar(e, aref, laref, warm());
+      float g = 0.f;
+#pragma unroll
+      for (int sl = 0; sl < DS; sl++) {
+        const int i = lane + sl * G;
+        if (i < m.nv) g += (Ma_warm[sl] - qfs[sl]) * (warm()[i] - qas[sl]);
+      }
+      const float gauss_w = 0.5f * W::allsum(g);
+      const float cost_w = rows_cost(e, nullptr, nullptr, false) + gauss_w;
+      float jw[CS][4], ljw[DS];
+#pragma unroll
+      for (int sl = 0; sl < CS; sl++)
+#pragma unroll
+        for (int r = 0; r < 4; r++) jw[sl][r] = e.jar[sl][r];
+#pragma unroll
+      for (int sl = 0; sl < DS; sl++) ljw[sl] = e.ljar[sl];
+      init_jar(e, aref, laref, qacc_smooth());
+      const float cost_s = rows_cost(e, nullptr, nullptr, false);
+      const bool use_warm = cost_w < cost_s;
+      if (use_warm) {
+#pragma unroll
+        for (int sl = 0; sl < CS; sl++)
+#pragma unroll
+          for (int r = 0; r < 4; r++) e.jar[sl][r] = jw[sl][r];
+#pragma unroll
+        for (int sl = 0; sl < DS; sl++) e.ljar[sl] = ljw[sl];
+      }
+#pragma unroll
+      for (int sl = 0; sl < DS; sl++) {
+        const int i = lane + sl * G;
+        Ma[sl] = use_warm ? Ma_warm[sl] : qfs[sl];
+        if (i < m.nv) qacc()[i] = use_warm ? warm()[i] : qas[sl];
+      }
+      gauss = use_warm ? gauss_w : 0.f;
+      W::sync();
+    }
+    float grad[DS], Mgrad[DS], mv[DS];
+    // update_constraint + update_gradient
+    {
+      float fbase[CS][3], lforce[DS];
+      const float c = rows_cost(e, fbase, lforce, true);
+      jt_force(e, fbase, lforce, qc);
+      prev_cost = INFINITY;
+      cost = c + gauss;
+    }
+    float gnorm2 = 0.f;
+#pragma unroll
+    for (int sl = 0; sl < DS; sl++) {
+      const int i = lane + sl * G;
+      grad[sl] = Ma[sl] - qfs[sl] - qc[sl];
+      if (i < m.nv) { xv()[i] = grad[sl]; gnorm2 += grad[sl] * grad[sl]; }
+    }
+    gnorm2 = W::allsum(gnorm2);
+    W::sync();
+    solve(xv());
+#pragma unroll
+    for (int sl = 0; sl < DS; sl++) {
+      const int i = lane + sl * G;
+      Mgrad[sl] = i < m.nv ? xv()[i] : 0.f;
+      mv[sl] = -grad[sl];  // M * search with search = -Mgrad
+      if (i < m.nv) search()[i] = -Mgrad[sl];
+    }
+    W::sync();
+    const float nvf = (float)(m.nv > 1 ? m.nv : 1);
+    const float scale = 1.0f / (m.meaninertia * nvf);
+    int it = 0;
+    while (true) {
+      const float improvement = (prev_cost - cost) * scale;
+      const float gradient = sqrtf(gnorm2) * scale;
+      if (it >= m.iterations || improvement < m.tolerance || gradient < m.tolerance) break;
+      // ---- line search along `search`
+      float jv[CS][4], ljv[DS];
+      {
+        float sb[CS][3];
+        jdot(search(), sb);
+#pragma unroll
+        for (int sl = 0; sl < CS; sl++) row_combine(e, sl, sb[sl], jv[sl]);
+      }
+      float sn = 0.f, g1 = 0.f, g2 = 0.f;
+#pragma unroll
+      for (int sl = 0; sl < DS; sl++) {
+        const int i = lane + sl * G;
+        const float sv = i < m.nv ? search()[i] : 0.f;
+        ljv[sl] = e.lsg[sl] * sv;
+        sn += sv * sv;
+        g1 += sv * (Ma[sl] - qfs[sl]);
+        g2 += 0.5f * sv * mv[sl];
+      }
+      sn = W::allsum(sn); g1 = W::allsum(g1); g2 = W::allsum(g2);
+      const float qg[3] = {gauss, g1, g2};
+      const float gtol = m.tolerance * m.ls_tolerance * sqrtf(sn) * m.meaninertia * nvf;
+      LsPt p0, lo, hi;
+      { const float a0 = 0.f; ls_eval<1>(e, jv, ljv, qg, &a0, &p0); }
+      { const float a1 = p0.alpha - p0.d0 / p0.d1; ls_eval<1>(e, jv, ljv, qg, &a1, &lo); }
+      if (lo.d0 < p0.d0) { hi = p0; } else { hi = lo; lo = p0; }
+      bool swap = true;
+      int li = 0;
+      while (true) {
+        bool done = li >= m.ls_iterations;
+        done |= !swap;
+        done |= (lo.d0 < 0.f) && (lo.d0 > -gtol);
+        done |= (hi.d0 > 0.f) && (hi.d0 < gtol);
+        if (done) break;
+        const float al[3] = {lo.alpha - lo.d0 / lo.d1, hi.alpha - hi.d0 / hi.d1, 0.5f * (lo.alpha + hi.alpha)};
+        LsPt pt[3];
+        ls_eval<3>(e, jv, ljv, qg, al, pt);
+        const bool s_lo_next = (lo.d0 > 0.f) || (lo.d0 < pt[0].d0);
+        if (s_lo_next) lo = pt[0];
+        const bool s_lo_mid = (pt[2].d0 < 0.f) && (lo.d0 < pt[2].d0);
+        if (s_lo_mid) lo = pt[2];
+        const bool s_hi_next = (hi.d0 < 0.f) || (hi.d0 > pt[1].d0);
+        if (s_hi_next) hi = pt[1];
+        const bool s_hi_mid = (pt[2].d0 > 0.f) && (hi.d0 > pt[2].d0);
+        if (s_hi_mid) hi = pt[2];
+        swap = s_lo_next || s_lo_mid || s_hi_next || s_hi_mid;
+        li++;
+      }
+      const bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
+      const float alpha = lo.cost < hi.cost ? lo.alpha : hi.alpha;
+      if (improved) {
+#pragma unroll
+        for (int sl = 0; sl < DS; sl++) {
+          const int i = lane + sl * G;
+          if (i < m.nv) qacc()[i] += search()[i] * alpha;
+          Ma[sl] += mv[sl] * alpha;
+          e.ljar[sl] += ljv[sl] * alpha;
+        }
+#pragma unroll
+        for (int sl = 0; sl < CS; sl++)
+#pragma unroll
+          for (int r = 0; r < 4; r++) e.jar[sl][r] += jv[sl][r] * alpha;
+      }
+      W::sync();
+      // ---- update_constraint
+      float g = 0.f;
+#pragma unroll
+      for (int sl = 0; sl < DS; sl++) {
+        const int i = lane + sl * G;
+        if (i < m.nv) g += (Ma[sl] - qfs[sl]) * (qacc()[i] - qas[sl]);
+      }
+      gauss = 0.5f * W::allsum(g);
+      {
+        float fbase[CS][3], lforce[DS];
+        const float c = rows_cost(e, fbase, lforce, true);
+        jt_force(e, fbase, lforce, qc);
+        prev_cost = cost;
+        cost = c + gauss;
+      }
+      // ---- update_gradient + Polak-Ribiere direction
+      float pg_pMg = 0.f, g_pMg = 0.f;
+      gnorm2 = 0.f;
+#pragma unroll
+      for (int sl = 0; sl < DS; sl++) {
+        const int i = lane + sl * G;
+        pg_pMg += grad[sl] * Mgrad[sl];
+        grad[sl] = Ma[sl] - qfs[sl] - qc[sl];
+        g_pMg += grad[sl] * Mgrad[sl];
+        if (i < m.nv) { xv()[i] = grad[sl]; gnorm2 += grad[sl] * grad[sl]; }
+      }
+      W::sync();
+      solve(xv());
+      float g_Mg = 0.f;
+#pragma unroll
+      for (int sl = 0; sl < DS; sl++) {
+        const int i = lane + sl * G;
+        Mgrad[sl] = i < m.nv ? xv()[i] : 0.f;
+        g_Mg += grad[sl] * Mgrad[sl];
+      }
+      pg_pMg = W::allsum(pg_pMg); g_pMg = W::allsum(g_pMg); g_Mg = W::allsum(g_Mg); gnorm2 = W::allsum(gnorm2);
+      float beta = (g_Mg - g_pMg) / (pg_pMg > BT_MINVAL ? pg_pMg : BT_MINVAL);
+      beta = beta < 0.f ? 0.f : beta;
+#pragma unroll
+      for (int sl = 0; sl < DS; sl++) {
+        const int i = lane + sl * G;
+        mv[sl] = -grad[sl] + beta * mv[sl];
+        if (i < m.nv) search()[i] = -Mgrad[sl] + beta * search()[i];
+      }
+      W::sync();
+      it++;
+    }
+    niter = it;
+    for (int i = lane; i < m.nv; i += G) warm()[i] = qacc()[i];
+    W::sync();
+  }
+
+  // ================================================================== mjx.forward
+  // returns false when stopped early by a debug stop point
+  BT_DEV bool forward(int stop = BT_STOP_NONE) {
+    tree_forward();
+    tree_backward();
+    if (stop == BT_STOP_TREE) return false;
+    smooth_forces();
+    if (stop == BT_STOP_SMOOTH) return false;
+    build_M(0.f);
+    if (stop == BT_STOP_M) return false;
+    float Ma_warm[DS];
+    mul_M(warm(), Ma_warm);
+    W::sync();
+    factor();
+    if (stop == BT_STOP_FACTOR) return false;
+    for (int i = lane; i < m.nv; i += G) qacc_smooth()[i] = qfrc_smooth()[i];
+    W::sync();
+    solve(qacc_smooth());
+    if (stop == BT_STOP_QACC_SMOOTH) return false;
+    collide();
+    if (stop == BT_STOP_COLLISION) return false;
+    solve_constraints(Ma_warm);
+    return true;
+  }
+
+  // ================================================================== mjx.euler (implicit joint damping) + _advance
+  BT_DEV void euler() {
+    const float h = m.timestep;
+    build_M(h);
+    factor();
+    for (int i = lane; i < m.nv; i += G) xv()[i] = qfrc_smooth()[i] + qfrc_c()[i];
+    W::sync();
+    solve(xv());
+    for (int u = lane; u < m.na; u += G) act()[u] += h * actdot()[u];
+    for (int i = lane; i < m.nv; i += G) {
+      const float v = qvel()[i] + h * xv()[i];
+      qvel()[i] = v;
+      const int qa = BT_LDG(m.dof_qposadr + i);
+      if (qa >= 0) qpos()[qa] += h * v;
+    }
+    W::sync();
+    for (int j = lane; j < m.njnt; j += G) {
+      if (BT_LDG(m.jnt_type + j) != BT_JNT_FREE) continue;
+      const int qa = BT_LDG(m.jnt_qposadr + j), da = BT_LDG(m.jnt_dofadr + j);
+      float* q = qpos() + qa;
+      const float* v = qvel() + da;
+      q[0] += h * v[0]; q[1] += h * v[1]; q[2] += h * v[2];
+      const float w[3] = {v[3], v[4], v[5]};
+      const float n = sqrtf(bt_dot3(w, w));
+      float ax[3] = {0.f, 0.f, 0.f};
+      if (n > 0.f) { const float in = 1.0f / n; ax[0] = w[0] * in; ax[1] = w[1] * in; ax[2] = w[2] * in; }
+      const float ha = 0.5f * h * n;
+      const float sn = sinf(ha), cs = cosf(ha);
+      float qr[4] = {cs, ax[0] * sn, ax[1] * sn, ax[2] * sn}, q2[4];
+      bt_quat_mul(q + 3, qr, q2);
+      bt_quat_normalize(q2);
+      q[3] = q2[0]; q[4] = q2[1]; q[5] = q2[2]; q[6] = q2[3];
+    }
+    W::sync();
+  }
+
+  BT_DEV void step() {
+    forward();
+    euler();
+  }
+
+  // ================================================================== state I/O ([n_envs, dim] rows, coalesced per env)
+  BT_DEV void load_state(const BtState& st, int env) {
+    for (int i = lane; i < m.nq; i += G) qpos()[i] = st.qpos[(size_t)env * m.nq + i];
+    for (int i = lane; i < m.nv; i += G) { qvel()[i] = st.qvel[(size_t)env * m.nv + i]; warm()[i] = st.qacc_warmstart[(size_t)env * m.nv + i]; }
+    for (int i = lane; i < m.na; i += G) act()[i] = st.act[(size_t)env * m.na + i];
+    W::sync();
+  }
+  BT_DEV void store_state(const BtState& st, int env, float time) {
+    for (int i = lane; i < m.nq; i += G) st.qpos[(size_t)env * m.nq + i] = qpos()[i];
+    for (int i = lane; i < m.nv; i += G) { st.qvel[(size_t)env * m.nv + i] = qvel()[i]; st.qacc_warmstart[(size_t)env * m.nv + i] = warm()[i]; }
+    for (int i = lane; i < m.na; i += G) st.act[(size_t)env * m.na + i] = act()[i];
+    if (st.xpos) for (int i = lane; i < 3 * m.nbody; i += G) st.xpos[(size_t)env * 3 * m.nbody + i] = xpos()[i];
+    if (lane == 0) st.time[env] = time;
+  }
+
+  // ================================================================== env layer
+  BT_DEV float* obsbuf() const { return s + m.o_crb; }  // staged observation row (crb/LD/T are dead by then)
+
+  // _get_obs (fruitfly.py:598-646 free root; :271-319 tethered) into obsbuf, nan_to_num applied
+  BT_DEV void build_obs(int cur_frame) {
+    float* o = obsbuf();
+    const int L = m.ref_len, nq = m.nq, nv = m.nv;
+    int start = cur_frame + 1;
+    start = start < 0 ? 0 : (start > m.clip_len - L ? m.clip_len - L : start);  // dynamic_slice clamps the start
+    for (int i = lane; i < nq; i += G) o[i] = bt_nan_to_num(qpos()[i]);
+    for (int i = lane; i < nv; i += G) o[nq + i] = bt_nan_to_num(qvel()[i]);
+    int base = nq + nv;
+    const float rq[4] = {qpos()[3], qpos()[4], qpos()[5], qpos()[6]};  // tethered quirk: four joint angles (fruitfly.py:305)
+    const int nj = m.clip_nj;
+    if (m.free_jnt) {
+      for (int l = lane; l < L; l += G) {
+        const float* cp = m.clip_position + 3 * (start + l);
+        float d[3] = {BT_LDG(cp) - qpos()[0], BT_LDG(cp + 1) - qpos()[1], BT_LDG(cp + 2) - qpos()[2]}, r[3];
+        bt_rotate(d, rq, r);
+        o[base + 3 * l] = bt_nan_to_num(r[0]); o[base + 3 * l + 1] = bt_nan_to_num(r[1]); o[base + 3 * l + 2] = bt_nan_to_num(r[2]);
+        const float* cq = m.clip_quaternion + 4 * (start + l);
+        const float tq[4] = {BT_LDG(cq), BT_LDG(cq + 1), BT_LDG(cq + 2), BT_LDG(cq + 3)};
+        const float inv[4] = {rq[0], -rq[1], -rq[2], -rq[3]};
+        float rel[4];
+        bt_quat_mul(tq, inv, rel);  // relative_quat(q_root, q_ref) = q_ref * conj(q_root)
+#pragma unroll
+        for (int k = 0; k < 4; k++) o[base + 3 * L + 4 * l + k] = bt_nan_to_num(rel[k]);
+      }
+      base += 7 * L;
+    }
+    const int qoff = m.free_jnt ? 7 : 0;
+    const int nji = m.n_joint_idxs;
+    for (int it = lane; it < L * nji; it += G) {
+      const int l = it / nji, k = it - l * nji;
+      const int col = BT_LDG(m.joint_idxs + k);
+      o[base + it] = bt_nan_to_num(BT_LDG(m.clip_joints + (size_t)(start + l) * nj + col) - qpos()[qoff + col]);
+    }
+    base += L * nji;
+    const int nbi = m.n_body_idxs;
+    for (int it = lane; it < L * nbi; it += G) {
+      const int l = it / nbi, k = it - l * nbi;
+      const int b = BT_LDG(m.body_idxs + k);
+      const float* cb = m.clip_body_positions + ((size_t)(start + l) * m.nbody + b) * 3;
+      float d[3] = {BT_LDG(cb) - xpos()[3 * b], BT_LDG(cb + 1) - xpos()[3 * b + 1], BT_LDG(cb + 2) - xpos()[3 * b + 2]}, r[3];
+      bt_rotate(d, rq, r);
+      o[base + 3 * it] = bt_nan_to_num(r[0]); o[base + 3 * it + 1] = bt_nan_to_num(r[1]); o[base + 3 * it + 2] = bt_nan_to_num(r[2]);
+    }
+    W::sync();
+  }
+
+  struct StepOut {
+    float reward, done, metrics[BT_NMETRIC], summed_pos, quat_d, joint_d;
+    int cur_frame, steps_taken;
+  };
+
+  // everything in env.step after pipeline_step (fruitfly.py:502-592); `action` = this env's row
+  BT_DEV void reward_terms(const float* action, int cur_frame_in, int steps_taken_in, StepOut& r) {
+    int stc = steps_taken_in + 1;
+    const int hit = (stc == m.steps_for_cur_frame) ? 1 : 0;
+    const int cur = cur_frame_in + hit;
+    stc = stc * (hit ? 0 : 1);
+    r.cur_frame = cur; r.steps_taken = stc;
+    const int fi = cur < 0 ? 0 : (cur > m.clip_len - 1 ? m.clip_len - 1 : cur);  // JAX gather clamps
+    float pd[3] = {0.f, 0.f, 0.f}, quat_d = 0.f, pos_r = 0.f, quat_r = 0.f;
+    const int qoff = m.free_jnt ? 7 : 0;
+    if (m.free_jnt) {
+      const float* cp = m.clip_position + 3 * fi;
+      pd[0] = qpos()[0] - BT_LDG(cp); pd[1] = qpos()[1] - BT_LDG(cp + 1); pd[2] = qpos()[2] - BT_LDG(cp + 2);
+      const float sp = (pd[0] + pd[1]) + pd[2];
+      pos_r = m.pos_reward_weight * expf(-400.f * (sp * sp));
+      const float* cq = m.clip_quaternion + 4 * fi;
+      float a[4] = {qpos()[3], qpos()[4], qpos()[5], qpos()[6]}, b[4] = {BT_LDG(cq), BT_LDG(cq + 1), BT_LDG(cq + 2), BT_LDG(cq + 3)};
+      const float na = sqrtf(a[0] * a[0] + a[1] * a[1] + a[2] * a[2] + a[3] * a[3]);
+      const float nb = sqrtf(b[0] * b[0] + b[1] * b[1] + b[2] * b[2] + b[3] * b[3]);
+      float dt = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; k++) dt += (a[k] / na) * (b[k] / nb);
+      float dd = 2.f * dt * dt - 1.f;
+      dd = dd > 1.f ? 1.f : dd;
+      const float ang = 0.5f * acosf(dd);
+      quat_d = ang * ang;
+      quat_r = m.quat_reward_weight * expf(-4.0f * quat_d);
+    }
+    float js = 0.f;
+    for (int k = lane; k < m.clip_nj; k += G) js += qpos()[qoff + k] - BT_LDG(m.clip_joints + (size_t)fi * m.clip_nj + k);
+    js = W::allsum(js);
+    const float joint_d = js * js;
+    const float joint_r = m.joint_reward_weight * expf(-0.5f * joint_d);
+    const float* ca = m.clip_angular_velocity + 3 * fi;
+    const float av = ((qvel()[3] - BT_LDG(ca)) + (qvel()[4] - BT_LDG(ca + 1))) + (qvel()[5] - BT_LDG(ca + 2));
+    const float angvel_r = m.angvel_reward_weight * expf(-0.5f * (av * av));
+    float bs = 0.f, es = 0.f, cs = 0.f;
+    for (int it = lane; it < 3 * m.n_body_idxs; it += G) {
+      const int b = BT_LDG(m.body_idxs + it / 3), k = it % 3;
+      bs += xpos()[3 * b + k] - BT_LDG(m.clip_body_positions + ((size_t)fi * m.nbody + b) * 3 + k);
+    }
+    for (int it = lane; it < 3 * m.n_endeff_idxs; it += G) {
+      const int b = BT_LDG(m.endeff_idxs + it / 3), k = it % 3;
+      es += xpos()[3 * b + k] - BT_LDG(m.clip_body_positions + ((size_t)fi * m.nbody + b) * 3 + k);
+    }
+    for (int u = lane; u < m.nu; u += G) cs += action[u] * action[u];
+    bs = W::allsum(bs); es = W::allsum(es); cs = W::allsum(cs);
+    const float bodypos_r = m.bodypos_reward_weight * expf(-6.0f * (bs * bs));
+    const float endeff_r = m.endeff_reward_weight * expf(-0.75f * (es * es));
+    const float z = xpos()[3 * m.torso_idx + 2];
+    float healthy = z < m.healthy_z_min ? 0.f : 1.f;
+    healthy = z > m.healthy_z_max ? 0.f : healthy;
+    const float healthy_r = m.terminate_when_unhealthy ? m.healthy_reward : m.healthy_reward * healthy;
+    const float w0 = pd[0], w1 = pd[1], w2 = pd[2] * 0.2f;
+    const float summed = (w0 * w0 + w1 * w1) + w2 * w2;
+    const float too_far = summed > m.too_far_dist ? 1.f : 0.f;
+    const float bad_pose = joint_d > m.bad_pose_dist ? 1.f : 0.f;
+    const float bad_quat = quat_d > m.bad_quat_dist ? 1.f : 0.f;
+    const float ctrl_cost = m.ctrl_cost_weight * cs;
+    float reward = joint_r + pos_r + quat_r + angvel_r + bodypos_r + endeff_r + healthy_r - ctrl_cost;
+    float done = m.terminate_when_unhealthy ? 1.f - healthy : 0.f;
+    done = fmaxf(fmaxf(done, too_far), fmaxf(bad_pose, bad_quat));
+    // NaN guard (fruitfly.py:569-577): any NaN in the pipeline state => done
+    int nan = 0;
+    for (int i = lane; i < m.nq; i += G) nan |= qpos()[i] != qpos()[i];
+    for (int i = lane; i < m.nv; i += G) nan |= (qvel()[i] != qvel()[i]) | (warm()[i] != warm()[i]);
+    for (int i = lane; i < m.na; i += G) nan |= act()[i] != act()[i];
+    for (int i = lane; i < 3 * m.nbody; i += G) nan |= xpos()[i] != xpos()[i];
+    nan = W::any(nan);
+    done = fmaxf(done, nan ? 1.f : 0.f);
+    r.reward = bt_nan_to_num(reward);
+    r.done = done;
+    r.metrics[BT_M_POS] = pos_r; r.metrics[BT_M_QUAT] = quat_r; r.metrics[BT_M_JOINT] = joint_r;
+    r.metrics[BT_M_ANGVEL] = angvel_r; r.metrics[BT_M_BODYPOS] = bodypos_r; r.metrics[BT_M_ENDEFF] = endeff_r;
+    r.metrics[BT_M_QUADCTRL] = -ctrl_cost; r.metrics[BT_M_ALIVE] = healthy_r; r.metrics[BT_M_TOO_FAR] = too_far;
+    r.metrics[BT_M_BAD_POSE] = bad_pose; r.metrics[BT_M_BAD_QUAT] = bad_quat; r.metrics[BT_M_FALL] = 1.f - healthy;
+    r.summed_pos = summed; r.quat_d = quat_d; r.joint_d = joint_d;
+  }
+};

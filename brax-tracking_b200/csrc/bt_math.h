@@ -1,0 +1,149 @@
+// Small fixed-size math helpers shared by every phase of the fused step (device + host-emulation builds).
+#pragma once
+#include <math.h>
+
+#ifdef __CUDACC__
+#define BT_DEV __device__ __forceinline__
+#define BT_LDG(p) __ldg(p)
+#else
+#define BT_DEV inline
+#define BT_LDG(p) (*(p))
+#endif
+
+#define BT_MINVAL 1e-15f
+#define BT_MINIMP 0.0001f
+#define BT_MAXIMP 0.9999f
+
+BT_DEV float bt_dot3(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+BT_DEV void bt_cross(const float* a, const float* b, float* o) {
+  float x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+BT_DEV void bt_quat_mul(const float* a, const float* b, float* o) {
+  float w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  float x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  float y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+  float z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+  o[0] = w; o[1] = x; o[2] = y; o[3] = z;
+}
+BT_DEV void bt_quat_normalize(float* q) {
+  float n = 1.0f / sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  q[0] *= n; q[1] *= n; q[2] *= n; q[3] *= n;
+}
+// v rotated by unit quaternion q (same formula as brax.math.rotate / mjx math.rotate)
+BT_DEV void bt_rotate(const float* v, const float* q, float* o) {
+  float s = q[0];
+  const float* u = q + 1;
+  float uv = bt_dot3(u, v), uu = bt_dot3(u, u), c[3];
+  bt_cross(u, v, c);
+  float k = s * s - uu;
+  float r0 = 2 * uv * u[0] + k * v[0] + 2 * s * c[0];
+  float r1 = 2 * uv * u[1] + k * v[1] + 2 * s * c[1];
+  float r2 = 2 * uv * u[2] + k * v[2] + 2 * s * c[2];
+  o[0] = r0; o[1] = r1; o[2] = r2;
+}
+BT_DEV void bt_quat_to_mat(const float* q, float* m) {
+  float w = q[0], x = q[1], y = q[2], z = q[3];
+  m[0] = w * w + x * x - y * y - z * z; m[1] = 2 * (x * y - w * z); m[2] = 2 * (x * z + w * y);
+  m[3] = 2 * (x * y + w * z); m[4] = w * w - x * x + y * y - z * z; m[5] = 2 * (y * z - w * x);
+  m[6] = 2 * (x * z - w * y); m[7] = 2 * (y * z + w * x); m[8] = w * w - x * x - y * y + z * z;
+}
+BT_DEV void bt_mat_vec(const float* m, const float* v, float* o) {
+  float a = m[0] * v[0] + m[1] * v[1] + m[2] * v[2];
+  float b = m[3] * v[0] + m[4] * v[1] + m[5] * v[2];
+  float c = m[6] * v[0] + m[7] * v[1] + m[8] * v[2];
+  o[0] = a; o[1] = b; o[2] = c;
+}
+BT_DEV void bt_matT_vec(const float* m, const float* v, float* o) {
+  float a = m[0] * v[0] + m[3] * v[1] + m[6] * v[2];
+  float b = m[1] * v[0] + m[4] * v[1] + m[7] * v[2];
+  float c = m[2] * v[0] + m[5] * v[1] + m[8] * v[2];
+  o[0] = a; o[1] = b; o[2] = c;
+}
+// 10-number spatial inertia [Ixx Iyy Izz Ixy Ixz Iyz, m*off(3), m] times motion vector [ang; lin]
+BT_DEV void bt_inert_mul(const float* i, const float* v, float* o) {
+  float c[3], e[3];
+  bt_cross(i + 6, v + 3, c);
+  bt_cross(i + 6, v, e);
+  float o0 = i[0] * v[0] + i[3] * v[1] + i[4] * v[2] + c[0];
+  float o1 = i[3] * v[0] + i[1] * v[1] + i[5] * v[2] + c[1];
+  float o2 = i[4] * v[0] + i[5] * v[1] + i[2] * v[2] + c[2];
+  float o3 = i[9] * v[3] - e[0], o4 = i[9] * v[4] - e[1], o5 = i[9] * v[5] - e[2];
+  o[0] = o0; o[1] = o1; o[2] = o2; o[3] = o3; o[4] = o4; o[5] = o5;
+}
+// motion cross product u x v
+BT_DEV void bt_motion_cross(const float* u, const float* v, float* o) {
+  float a[3], b[3], c[3];
+  bt_cross(u, v, a);
+  bt_cross(u + 3, v, b);
+  bt_cross(u, v + 3, c);
+  o[0] = a[0]; o[1] = a[1]; o[2] = a[2];
+  o[3] = b[0] + c[0]; o[4] = b[1] + c[1]; o[5] = b[2] + c[2];
+}
+// force cross product v x* f
+BT_DEV void bt_motion_cross_force(const float* v, const float* f, float* o) {
+  float a[3], b[3], c[3];
+  bt_cross(v, f, a);
+  bt_cross(v + 3, f + 3, b);
+  bt_cross(v, f + 3, c);
+  o[0] = a[0] + b[0]; o[1] = a[1] + b[1]; o[2] = a[2] + b[2];
+  o[3] = c[0]; o[4] = c[1]; o[5] = c[2];
+}
+BT_DEV float bt_dot6(const float* a, const float* b) {
+  return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
+}
+BT_DEV float bt_clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
+// jnp.nan_to_num (fruitfly.py:569-570)
+BT_DEV float bt_nan_to_num(float x) {
+  if (x != x) return 0.0f;
+  if (x > 3.4028234664e38f) return 3.4028234664e38f;
+  if (x < -3.4028234664e38f) return -3.4028234664e38f;
+  return x;
+}
+
+// ---- JAX threefry2x32 ----
+BT_DEV unsigned bt_rotl(unsigned x, int d) { return (x << d) | (x >> (32 - d)); }
+BT_DEV void bt_threefry2x32(unsigned k0, unsigned k1, unsigned& x0, unsigned& x1) {
+  unsigned ks[3] = {k0, k1, k0 ^ k1 ^ 0x1BD11BDAu};
+  const int r0[4] = {13, 15, 26, 6}, r1[4] = {17, 29, 16, 24};
+  x0 += ks[0];
+  x1 += ks[1];
+#pragma unroll
+  for (int g = 0; g < 5; g++) {
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      x0 += x1;
+      x1 = bt_rotl(x1, (g & 1) ? r1[r] : r0[r]);
+      x1 ^= x0;
+    }
+    x0 += ks[(g + 1) % 3];
+    x1 += ks[(g + 2) % 3] + (unsigned)(g + 1);
+  }
+}
+// element idx of threefry_2x32(key, iota(n)) with JAX's split-in-halves convention
+BT_DEV unsigned bt_random_bits(unsigned k0, unsigned k1, int idx, int n) {
+  int half = (n + 1) / 2;
+  unsigned x0, x1;
+  if (idx < half) { x0 = (unsigned)idx; x1 = (unsigned)(half + idx); }
+  else { x0 = (unsigned)(idx - half); x1 = (unsigned)idx; }
+  bt_threefry2x32(k0, k1, x0, x1);
+  return idx < half ? x0 : x1;
+}
+BT_DEV float bt_bits_to_uniform(unsigned bits, float lo, float hi) {
+  unsigned u = (bits >> 9) | 0x3F800000u;
+  float f;
+#ifdef __CUDACC__
+  f = __uint_as_float(u);
+#else
+  union { unsigned u; float f; } cv; cv.u = u; f = cv.f;
+#endif
+  f -= 1.0f;
+  // separate multiply and add (no FMA contraction) so the bits match jax.random.uniform on the XLA CPU backend
+#ifdef __CUDACC__
+  float r = __fadd_rn(__fmul_rn(f, hi - lo), lo);
+#else
+  volatile float prod = f * (hi - lo);
+  float r = prod + lo;
+#endif
+  return r < lo ? lo : r;
+}

@@ -1,0 +1,89 @@
+// Device-side model description for the fused physics + tracking-reward step.
+//
+// All model constants are uploaded once by bt_model_create() as *named* tables: the X-macro lists below
+// name exactly the arrays produced by the host packer (brax-tracking_b200/model.py::pack).  Kernels take the
+// struct by value (__grid_constant__) and read the tables through the read-only path; per-environment state
+// lives in shared memory for the duration of a control step ("data layout").
+#pragma once
+#include <stdint.h>
+
+// ---- scalar ints (1-element int tables, by name) ----
+#define BT_INT_SCALARS(X) \
+  X(nq) X(nv) X(nu) X(na) X(nbody) X(njnt) X(nM) X(nlevel) X(nroot) X(ntri) X(ncon) X(ncgeom) X(ncb)           \
+  X(cone) X(iterations) X(ls_iterations) X(n_frames)                                                            \
+  /* env layer */                                                                                               \
+  X(free_jnt) X(seed_root_from_clip) X(ref_len) X(clip_len) X(clip_nj) X(n_joint_idxs) X(n_body_idxs)           \
+  X(n_endeff_idxs) X(torso_idx) X(terminate_when_unhealthy) X(steps_for_cur_frame) X(episode_length)            \
+  X(start_frame_range) X(obs_size)                                                                              \
+  /* per-environment scratch layout (offsets in floats) */                                                      \
+  X(o_qpos) X(o_qvel) X(o_act) X(o_ctrl) X(o_warm) X(o_xpos) X(o_xquat) X(o_cdof) X(o_crb) X(o_LD) X(o_Dinv)    \
+  X(o_T) X(o_ref) X(o_aforce) X(o_actdot) X(o_qfrc_smooth) X(o_qacc_smooth) X(o_qacc) X(o_x) X(o_search)        \
+  X(o_qfrc_c) X(smem_floats)
+
+// ---- scalar floats ----
+#define BT_FLT_SCALARS(X) \
+  X(timestep) X(grav_x) X(grav_y) X(grav_z) X(density) X(viscosity) X(impratio) X(tolerance) X(ls_tolerance)    \
+  X(meaninertia)                                                                                                \
+  X(too_far_dist) X(bad_pose_dist) X(bad_quat_dist) X(ctrl_cost_weight) X(pos_reward_weight)                    \
+  X(quat_reward_weight) X(joint_reward_weight) X(angvel_reward_weight) X(bodypos_reward_weight)                 \
+  X(endeff_reward_weight) X(healthy_reward) X(healthy_z_min) X(healthy_z_max) X(reset_noise_scale)
+
+// ---- int tables ----
+#define BT_INT_TABLES(X) \
+  X(body_parentid) X(body_jntadr) X(body_jntnum) X(body_ref) X(level_adr) X(level_body) X(child_adr) X(child_id)\
+  X(jnt_type) X(jnt_qposadr) X(jnt_dofadr)                                                                      \
+  X(dof_bodyid) X(dof_parentid) X(dof_Madr) X(dof_depth) X(dof_subtreenum) X(dof_qposadr) X(dof_limited)        \
+  X(M_row) X(M_col) X(M_colMadr) X(tri_ab)                                                                      \
+  X(cgeom_bodyid) X(cb_adr) X(cb_dof) X(cb_ref)                                                                 \
+  X(con_g1) X(con_g2) X(con_cb1) X(con_cb2) X(con_ref) X(con_fn) X(con_sub) X(con_dim)                          \
+  X(dofcon_adr) X(dofcon_c)                                                                                     \
+  X(act_wrap_adr) X(act_wrap_qadr) X(act_wrap_dadr) X(dofact_adr) X(dofact_u)                                   \
+  X(actuator_dyntype) X(actuator_gaintype) X(actuator_biastype) X(actuator_ctrllimited)                         \
+  X(actuator_forcelimited) X(actuator_actadr)                                                                   \
+  X(joint_idxs) X(body_idxs) X(endeff_idxs)
+
+// ---- float tables ----
+#define BT_FLT_TABLES(X) \
+  X(body_pos) X(body_quat) X(body_ipos) X(body_iquat) X(body_mass) X(body_inertia) X(body_fluidbox)             \
+  X(jnt_pos) X(jnt_axis) X(qpos0)                                                                               \
+  X(dof_stiffness) X(dof_springref) X(dof_armature) X(dof_damping) X(dof_range) X(dof_solref) X(dof_solimp)     \
+  X(dof_margin) X(dof_invweight0)                                                                               \
+  X(cgeom_pos) X(cgeom_quat) X(cgeom_size)                                                                      \
+  X(con_mu) X(con_solref) X(con_solimp) X(con_includemargin) X(con_invweight) X(dofcon_sign)                    \
+  X(act_wrap_coef) X(dofact_coef)                                                                               \
+  X(actuator_gear) X(actuator_gainprm) X(actuator_biasprm) X(actuator_dynprm) X(actuator_ctrlrange)             \
+  X(actuator_forcerange)                                                                                        \
+  X(clip_position) X(clip_quaternion) X(clip_joints) X(clip_body_positions) X(clip_angular_velocity)
+
+struct BtDev {
+#define X(n) int n;
+  BT_INT_SCALARS(X)
+#undef X
+#define X(n) float n;
+  BT_FLT_SCALARS(X)
+#undef X
+#define X(n) const int* n;
+  BT_INT_TABLES(X)
+#undef X
+#define X(n) const float* n;
+  BT_FLT_TABLES(X)
+#undef X
+};
+
+enum { BT_JNT_FREE = 0, BT_JNT_HINGE = 3 };
+enum { BT_CONE_PYRAMIDAL = 0, BT_CONE_ELLIPTIC = 1 };
+enum { BT_FN_PLANE_CAPSULE = 0, BT_FN_PLANE_ELLIPSOID = 1, BT_FN_PLANE_SPHERE = 2, BT_FN_CAPSULE_CAPSULE = 3 };
+
+// per-env state rows handed through the C ABI: BtStatePtrs in include/bt_api.h
+#include "bt_api.h"
+typedef BtStatePtrs BtState;
+
+// metrics order (fruitfly.py:481-494)
+enum {
+  BT_M_POS = 0, BT_M_QUAT, BT_M_JOINT, BT_M_ANGVEL, BT_M_BODYPOS, BT_M_ENDEFF, BT_M_QUADCTRL, BT_M_ALIVE,
+  BT_M_TOO_FAR, BT_M_BAD_POSE, BT_M_BAD_QUAT, BT_M_FALL, BT_NMETRIC
+};
+// info_f order: summed_pos_distance, quat_distance, joint_distance, steps (float, EpisodeWrapper), truncation
+enum { BT_IF_SUMMED_POS = 0, BT_IF_QUAT, BT_IF_JOINT, BT_IF_STEPS, BT_IF_TRUNC, BT_NINFOF };
+// info_i order: cur_frame, steps_taken_cur_frame
+enum { BT_II_CUR_FRAME = 0, BT_II_STEPS_TAKEN, BT_NINFOI };

@@ -1,0 +1,357 @@
+"""Packs a compiled model (``mjcf.Model``) + env constants + reference clip into the named flat tables
+that the sm_100a kernels read (``csrc/bt_model.h``: the X-macro lists name exactly these arrays).
+
+What the reference does at this point: ``mjx.put_model`` uploads ``mjModel`` and the env keeps the clip
+and index lists as jnp arrays (/root/reference/envs/fruitfly.py:405-447).  Here the model is additionally
+*re-indexed for warp-per-environment execution*: level schedules for the body tree, tree-sparse mass
+matrix layout (MuJoCo's ``dof_Madr`` convention), per-contact ancestor chains instead of a dense ``efc_J``,
+and per-dof gather lists so every reduction in the kernels is deterministic (no atomics).
+
+Nothing here runs in the timed path.
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+import numpy as np
+
+from . import mjcf
+
+# contact functions (csrc/bt_model.h)
+FN_PLANE_CAPSULE, FN_PLANE_ELLIPSOID, FN_PLANE_SPHERE, FN_CAPSULE_CAPSULE = 0, 1, 2, 3
+
+CLIP_FIELDS = ("position", "quaternion", "joints", "body_positions", "angular_velocity")
+
+
+def _i(x):
+    return np.ascontiguousarray(np.asarray(x, dtype=np.int32).ravel())
+
+
+def _f(x):
+    return np.ascontiguousarray(np.asarray(x, dtype=np.float32).ravel())
+
+
+def _gather_idx(idx, n):
+    """JAX gather semantics of ``x[..., idx]``: negative wraps once, out of range clamps."""
+    idx = np.asarray(idx, dtype=np.int64)
+    idx = np.where(idx < 0, idx + n, idx)
+    return np.clip(idx, 0, n - 1).astype(np.int32)
+
+
+def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32) -> Dict[str, np.ndarray]:
+    """Returns {name: int32/float32 array}; 1-element arrays are the scalars of BtDev."""
+    a = m.a
+    nq, nv, nu, na, nbody, njnt = m.nq, m.nv, m.nu, m.na, m.nbody, m.njnt
+    t: Dict[str, np.ndarray] = {}
+
+    def S(name, v):
+        t[name] = np.array([v], dtype=np.int32)
+
+    def SF(name, v):
+        t[name] = np.array([v], dtype=np.float32)
+
+    # ------------------------------------------------------------------ body tree
+    parent = a["body_parentid"]
+    depth = a["body_depth"]
+    nlevel = int(depth.max())  # levels 1..max (world = 0 is not scheduled)
+    order = sorted(range(1, nbody), key=lambda b: (depth[b], b))
+    level_adr = np.zeros(nlevel + 1, dtype=np.int32)
+    for b in order:
+        level_adr[depth[b]] += 1  # count at index depth (1-based) -> shift below
+    counts = [sum(1 for b in order if depth[b] == L) for L in range(1, nlevel + 1)]
+    level_adr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    children = [[] for _ in range(nbody)]
+    for b in range(1, nbody):
+        children[parent[b]].append(b)
+    child_adr = np.zeros(nbody + 1, dtype=np.int32)
+    child_id = []
+    for b in range(nbody):
+        child_adr[b] = len(child_id)
+        child_id.extend(children[b])
+    child_adr[nbody] = len(child_id)
+    # reference point of every kinematic tree: the position of the tree's root body (a free root moves with
+    # qpos[0:3]; a static root is a model constant).  MJX uses the subtree COM here; any fixed point gives the
+    # same qM / qfrc_bias (DESIGN.md "reference point").
+    roots = [b for b in range(1, nbody) if parent[b] == 0]
+    root_slot = {b: k for k, b in enumerate(roots)}
+    body_ref = np.array([0] + [root_slot[a["body_rootid"][b]] for b in range(1, nbody)], dtype=np.int32)
+
+    S("nq", nq); S("nv", nv); S("nu", nu); S("na", na); S("nbody", nbody); S("njnt", njnt)
+    S("nM", m.nM); S("nlevel", nlevel); S("nroot", len(roots))
+    t["body_parentid"] = _i(parent)
+    t["body_jntadr"] = _i(a["body_jntadr"])
+    t["body_jntnum"] = _i(a["body_jntnum"])
+    t["body_ref"] = body_ref
+    t["level_adr"] = level_adr
+    t["level_body"] = _i(order)
+    t["child_adr"] = child_adr
+    t["child_id"] = _i(child_id) if child_id else np.zeros(1, np.int32)
+    t["body_pos"] = _f(a["body_pos"]); t["body_quat"] = _f(a["body_quat"])
+    t["body_ipos"] = _f(a["body_ipos"]); t["body_iquat"] = _f(a["body_iquat"])
+    t["body_mass"] = _f(a["body_mass"]); t["body_inertia"] = _f(a["body_inertia"])
+    # fluid (inertia-box) constants: box[3] per body; zero mass -> skipped in the kernel
+    box = np.zeros((nbody, 3))
+    for b in range(1, nbody):
+        mass = a["body_mass"][b]
+        if mass > 0:
+            I = a["body_inertia"][b]
+            bx = np.array([I[1] + I[2] - I[0], I[0] + I[2] - I[1], I[0] + I[1] - I[2]])
+            box[b] = np.sqrt(6 * np.maximum(bx, 1e-12) / max(mass, 1e-12))
+    t["body_fluidbox"] = _f(box)
+
+    # ------------------------------------------------------------------ joints / dofs
+    t["jnt_type"] = _i(a["jnt_type"]); t["jnt_qposadr"] = _i(a["jnt_qposadr"]); t["jnt_dofadr"] = _i(a["jnt_dofadr"])
+    t["jnt_pos"] = _f(a["jnt_pos"]); t["jnt_axis"] = _f(a["jnt_axis"])
+    t["qpos0"] = _f(a["qpos0"])
+    dof_jnt = a["dof_jntid"]
+    dof_qadr = np.full(nv, -1, dtype=np.int32)
+    dof_stiff = np.zeros(nv); dof_spring = np.zeros(nv)
+    dof_lim = np.zeros(nv, dtype=np.int32)
+    dof_range = np.zeros((nv, 2)); dof_solref = np.zeros((nv, 2)); dof_solimp = np.zeros((nv, 5))
+    dof_margin = np.zeros(nv)
+    for i in range(nv):
+        j = dof_jnt[i]
+        if a["jnt_type"][j] == mjcf.JNT_HINGE:
+            qa = a["jnt_qposadr"][j]
+            dof_qadr[i] = qa
+            dof_stiff[i] = a["jnt_stiffness"][j]
+            dof_spring[i] = a["qpos_spring"][qa]
+            dof_lim[i] = int(a["jnt_limited"][j])
+            dof_range[i] = a["jnt_range"][j]
+            dof_solref[i] = a["jnt_solref"][j]
+            dof_solimp[i] = a["jnt_solimp"][j]
+            dof_margin[i] = a["jnt_margin"][j]
+    t["dof_bodyid"] = _i(a["dof_bodyid"]); t["dof_parentid"] = _i(a["dof_parentid"])
+    t["dof_Madr"] = _i(a["dof_Madr"]); t["dof_depth"] = _i(a["dof_depth"]); t["dof_subtreenum"] = _i(a["dof_subtreenum"])
+    t["dof_qposadr"] = dof_qadr; t["dof_limited"] = dof_lim
+    t["dof_stiffness"] = _f(dof_stiff); t["dof_springref"] = _f(dof_spring)
+    t["dof_armature"] = _f(a["dof_armature"]); t["dof_damping"] = _f(a["dof_damping"])
+    t["dof_range"] = _f(dof_range); t["dof_solref"] = _f(dof_solref); t["dof_solimp"] = _f(dof_solimp)
+    t["dof_margin"] = _f(dof_margin); t["dof_invweight0"] = _f(a["dof_invweight0"])
+    # tree-sparse M: entry e of row i (a = e - Madr[i]) is M[i, anc_a(i)]
+    M_row = np.zeros(m.nM, dtype=np.int32); M_col = np.zeros(m.nM, dtype=np.int32)
+    for i in range(nv):
+        j, e = i, a["dof_Madr"][i]
+        while j >= 0:
+            M_row[e], M_col[e] = i, j
+            e += 1
+            j = a["dof_parentid"][j]
+    t["M_row"] = M_row; t["M_col"] = M_col
+    t["M_colMadr"] = _i(a["dof_Madr"][M_col])
+    # triangular decode table t -> (a, b), 1 <= a <= b, ordered by b (valid prefix for every depth)
+    dmax = int(a["dof_depth"].max()) if nv else 0
+    tri = [(aa, bb) for bb in range(1, dmax + 1) for aa in range(1, bb + 1)]
+    S("ntri", len(tri))
+    t["tri_ab"] = _i([aa | (bb << 8) for aa, bb in tri]) if tri else np.zeros(1, np.int32)
+
+    def chain(body):
+        out, d = [], a["body_lastdof"][body]
+        while d >= 0:
+            out.append(int(d))
+            d = a["dof_parentid"][d]
+        return out
+
+    # ------------------------------------------------------------------ contacts (static list)
+    con = []  # one record per potential contact
+    cgeoms, cgeom_slot = [], {}
+
+    def cg(g):
+        if g not in cgeom_slot:
+            cgeom_slot[g] = len(cgeoms)
+            cgeoms.append(g)
+        return cgeom_slot[g]
+
+    for p in range(len(a["pair_ncon"])):
+        g1, g2 = int(a["pair_geom"][p, 0]), int(a["pair_geom"][p, 1])
+        t1, t2 = a["geom_type"][g1], a["geom_type"][g2]
+        if (t1, t2) == (mjcf.GEOM_PLANE, mjcf.GEOM_CAPSULE):
+            fn = FN_PLANE_CAPSULE
+        elif (t1, t2) == (mjcf.GEOM_PLANE, mjcf.GEOM_ELLIPSOID):
+            fn = FN_PLANE_ELLIPSOID
+        elif (t1, t2) == (mjcf.GEOM_PLANE, mjcf.GEOM_SPHERE):
+            fn = FN_PLANE_SPHERE
+        elif (t1, t2) == (mjcf.GEOM_CAPSULE, mjcf.GEOM_CAPSULE):
+            fn = FN_CAPSULE_CAPSULE
+        else:
+            raise NotImplementedError((t1, t2))
+        b1, b2 = int(a["geom_bodyid"][g1]), int(a["geom_bodyid"][g2])
+        dim = int(a["pair_condim"][p])
+        if dim not in (1, 3):
+            raise NotImplementedError("condim 4/6 is unused by the selected assets (MJX 3.2 does not support it)")
+        for sub in range(int(a["pair_ncon"][p])):
+            con.append(dict(g1=cg(g1), g2=cg(g2), b1=b1, b2=b2, fn=fn, sub=sub, dim=dim,
+                            mu=(a["pair_friction"][p, 0], a["pair_friction"][p, 1]),
+                            solref=a["pair_solref"][p], solimp=a["pair_solimp"][p],
+                            includemargin=a["pair_margin"][p] - a["pair_gap"][p],
+                            invw=a["body_invweight0"][b1, 0] + a["body_invweight0"][b2, 0]))
+    ncon = len(con)
+    S("ncon", ncon)
+    S("ncgeom", len(cgeoms))
+    t["cgeom_bodyid"] = _i([a["geom_bodyid"][g] for g in cgeoms]) if cgeoms else np.zeros(1, np.int32)
+    t["cgeom_pos"] = _f([a["geom_pos"][g] for g in cgeoms]) if cgeoms else np.zeros(3, np.float32)
+    t["cgeom_quat"] = _f([a["geom_quat"][g] for g in cgeoms]) if cgeoms else np.zeros(4, np.float32)
+    t["cgeom_size"] = _f([a["geom_size"][g] for g in cgeoms]) if cgeoms else np.zeros(3, np.float32)
+    # contact bodies (bodies that carry dofs and appear in a contact): chain lists for the matrix-free J
+    cbs, cb_slot = [], {}
+    for c in con:
+        for b in (c["b1"], c["b2"]):
+            if a["body_lastdof"][b] >= 0 and b not in cb_slot:
+                cb_slot[b] = len(cbs)
+                cbs.append(b)
+    ncb = len(cbs)
+    S("ncb", ncb)
+    cb_adr, cb_dof = [0], []
+    for b in cbs:
+        cb_dof.extend(chain(b))
+        cb_adr.append(len(cb_dof))
+    t["cb_adr"] = _i(cb_adr)
+    t["cb_dof"] = _i(cb_dof) if cb_dof else np.zeros(1, np.int32)
+    t["cb_ref"] = _i([body_ref[b] for b in cbs]) if cbs else np.zeros(1, np.int32)
+
+    def Z(n, dt):
+        return np.zeros(max(n, 1), dtype=dt)
+
+    t["con_g1"] = _i([c["g1"] for c in con]) if con else Z(1, np.int32)
+    t["con_g2"] = _i([c["g2"] for c in con]) if con else Z(1, np.int32)
+    t["con_cb1"] = _i([cb_slot.get(c["b1"], -1) for c in con]) if con else Z(1, np.int32)
+    t["con_cb2"] = _i([cb_slot.get(c["b2"], -1) for c in con]) if con else Z(1, np.int32)
+    t["con_ref"] = _i([body_ref[c["b2"]] if a["body_lastdof"][c["b2"]] >= 0 else body_ref[c["b1"]] for c in con]) if con else Z(1, np.int32)
+    t["con_fn"] = _i([c["fn"] for c in con]) if con else Z(1, np.int32)
+    t["con_sub"] = _i([c["sub"] for c in con]) if con else Z(1, np.int32)
+    t["con_dim"] = _i([c["dim"] for c in con]) if con else Z(1, np.int32)
+    t["con_mu"] = _f([c["mu"] for c in con]) if con else Z(2, np.float32)
+    t["con_solref"] = _f([c["solref"] for c in con]) if con else Z(2, np.float32)
+    t["con_solimp"] = _f([c["solimp"] for c in con]) if con else Z(5, np.float32)
+    t["con_includemargin"] = _f([c["includemargin"] for c in con]) if con else Z(1, np.float32)
+    t["con_invweight"] = _f([c["invw"] for c in con]) if con else Z(1, np.float32)
+    # two trees in one contact need both reference points to coincide for the shared wrench; with one ref per
+    # tree the wrench is re-expressed per tree in the kernel (con_ref is the tree of body2; body1's tree uses
+    # its own ref).  All selected models have a single moving tree per contact or both bodies in one tree.
+    for c in con:
+        m1 = a["body_lastdof"][c["b1"]] >= 0
+        m2 = a["body_lastdof"][c["b2"]] >= 0
+        if m1 and m2 and body_ref[c["b1"]] != body_ref[c["b2"]]:
+            raise NotImplementedError("contacts between two different kinematic trees need per-tree wrenches")
+    # per-dof gather list of contacts (sign +1 for body2's chain, -1 for body1's chain; common ancestors cancel)
+    dofcon = [[] for _ in range(nv)]
+    for ci, c in enumerate(con):
+        ch1 = set(chain(c["b1"])); ch2 = set(chain(c["b2"]))
+        for d in ch2 - ch1:
+            dofcon[d].append((ci, 1.0))
+        for d in ch1 - ch2:
+            dofcon[d].append((ci, -1.0))
+    dofcon_adr, dofcon_c, dofcon_s = [0], [], []
+    for d in range(nv):
+        for ci, s in sorted(dofcon[d]):
+            dofcon_c.append(ci); dofcon_s.append(s)
+        dofcon_adr.append(len(dofcon_c))
+    t["dofcon_adr"] = _i(dofcon_adr)
+    t["dofcon_c"] = _i(dofcon_c) if dofcon_c else Z(1, np.int32)
+    t["dofcon_sign"] = _f(dofcon_s) if dofcon_s else Z(1, np.float32)
+
+    # ------------------------------------------------------------------ actuators
+    wrap_adr, wrap_q, wrap_coef = [0], [], []
+    dofact = [[] for _ in range(nv)]
+    for u in range(nu):
+        gear = a["actuator_gear"][u]
+        if a["actuator_trntype"][u] == mjcf.TRN_JOINT:
+            j = a["actuator_trnid"][u]
+            if a["jnt_type"][j] != mjcf.JNT_HINGE:
+                raise NotImplementedError("actuators on free joints are unused")
+            wrap_q.append(a["jnt_qposadr"][j]); wrap_coef.append(1.0)
+            dofact[a["jnt_dofadr"][j]].append((u, gear))
+        else:
+            tt = a["actuator_trnid"][u]
+            for w in range(a["tendon_adr"][tt], a["tendon_adr"][tt] + a["tendon_num"][tt]):
+                j = a["wrap_jntid"][w]
+                wrap_q.append(a["jnt_qposadr"][j]); wrap_coef.append(a["wrap_coef"][w])
+                dofact[a["jnt_dofadr"][j]].append((u, a["wrap_coef"][w] * gear))
+        wrap_adr.append(len(wrap_q))
+    t["act_wrap_adr"] = _i(wrap_adr)
+    t["act_wrap_qadr"] = _i(wrap_q) if wrap_q else Z(1, np.int32)
+    t["act_wrap_coef"] = _f(wrap_coef) if wrap_coef else Z(1, np.float32)
+    # dof index of every wrap entry (hinge: qposadr -> dofadr)
+    q2d = {int(a["jnt_qposadr"][j]): int(a["jnt_dofadr"][j]) for j in range(njnt) if a["jnt_type"][j] == mjcf.JNT_HINGE}
+    t["act_wrap_dadr"] = _i([q2d[int(q)] for q in wrap_q]) if wrap_q else Z(1, np.int32)
+    dofact_adr, dofact_u, dofact_coef = [0], [], []
+    for d in range(nv):
+        for u, cf in dofact[d]:
+            dofact_u.append(u); dofact_coef.append(cf)
+        dofact_adr.append(len(dofact_u))
+    t["dofact_adr"] = _i(dofact_adr)
+    t["dofact_u"] = _i(dofact_u) if dofact_u else Z(1, np.int32)
+    t["dofact_coef"] = _f(dofact_coef) if dofact_coef else Z(1, np.float32)
+    for k in ("dyntype", "gaintype", "biastype", "ctrllimited", "forcelimited", "actadr"):
+        t["actuator_" + k] = _i(a["actuator_" + k]) if nu else Z(1, np.int32)
+    for k in ("gear", "gainprm", "biasprm", "dynprm", "ctrlrange", "forcerange"):
+        t["actuator_" + k] = _f(a["actuator_" + k]) if nu else Z(3, np.float32)
+
+    # ------------------------------------------------------------------ options
+    S("cone", m.cone); S("iterations", m.iterations); S("ls_iterations", m.ls_iterations)
+    S("n_frames", cfg["n_frames"])
+    SF("timestep", m.timestep)
+    SF("grav_x", m.gravity[0]); SF("grav_y", m.gravity[1]); SF("grav_z", m.gravity[2])
+    SF("density", m.density); SF("viscosity", m.viscosity); SF("impratio", m.impratio)
+    SF("tolerance", m.tolerance); SF("ls_tolerance", m.ls_tolerance); SF("meaninertia", m.meaninertia)
+
+    # ------------------------------------------------------------------ env layer (fruitfly.py:405-447)
+    T = int(np.asarray(clip["joints"]).shape[0])
+    nj = int(np.asarray(clip["joints"]).shape[1])
+    S("free_jnt", int(cfg["free_jnt"])); S("seed_root_from_clip", int(cfg["seed_root_from_clip"]))
+    S("ref_len", cfg["ref_len"]); S("clip_len", T); S("clip_nj", nj)
+    jidx = _gather_idx(cfg["joint_idxs"], nj)
+    bidx = _gather_idx(cfg["body_idxs"], nbody)
+    eidx = _gather_idx(cfg["endeff_idxs"], nbody)
+    S("n_joint_idxs", len(jidx)); S("n_body_idxs", len(bidx)); S("n_endeff_idxs", len(eidx))
+    t["joint_idxs"] = jidx; t["body_idxs"] = bidx; t["endeff_idxs"] = eidx if len(eidx) else Z(1, np.int32)
+    S("torso_idx", int(cfg["torso_idx"]) % nbody)  # negative ids index from the end, as in JAX
+    S("terminate_when_unhealthy", int(cfg["terminate_when_unhealthy"]))
+    sfc = float(cfg["steps_for_cur_frame"])
+    # fruitfly.py:504-509 compares an int32 counter with this float; a non-integral value never matches
+    S("steps_for_cur_frame", int(sfc) if sfc == int(sfc) else -1)
+    S("episode_length", cfg["episode_length"]); S("start_frame_range", cfg.get("start_frame_range", 44))
+    for k in ("too_far_dist", "bad_pose_dist", "bad_quat_dist", "ctrl_cost_weight", "pos_reward_weight",
+              "quat_reward_weight", "joint_reward_weight", "angvel_reward_weight", "bodypos_reward_weight",
+              "endeff_reward_weight", "healthy_reward", "reset_noise_scale"):
+        SF(k, cfg[k])
+    SF("healthy_z_min", cfg["healthy_z_range"][0]); SF("healthy_z_max", cfg["healthy_z_range"][1])
+    L = int(cfg["ref_len"])
+    if cfg["free_jnt"]:
+        obs_size = nq + nv + 3 * L + 4 * L + len(jidx) * L + 3 * len(bidx) * L
+    else:
+        obs_size = nq + nv + len(jidx) * L + 3 * len(bidx) * L
+    S("obs_size", obs_size)
+    for k in CLIP_FIELDS:
+        t["clip_" + k] = _f(clip[k])
+    assert np.asarray(clip["body_positions"]).shape[1:] == (nbody, 3)
+    assert nj == (nq - 7 if cfg["free_jnt"] else nq), (nj, nq)
+
+    # ------------------------------------------------------------------ per-environment scratch layout (floats)
+    lay, off = {}, 0
+
+    def R(name, n):
+        nonlocal off
+        lay[name] = off
+        off += int(n)
+
+    R("qpos", nq); R("qvel", nv); R("act", max(na, 1)); R("ctrl", max(nu, 1)); R("warm", nv)
+    R("xpos", 3 * nbody); R("xquat", 4 * nbody); R("cdof", 6 * nv); R("crb", 10 * nbody)
+    # LD doubles as cvel/cacc storage during the forward tree pass
+    R("LD", max(m.nM, 12 * nbody)); R("Dinv", nv)
+    # T region: cfrc (forward/backward pass) -> buf (M assembly) -> contact geometry + wrenches (solver)
+    R("T", max(6 * nbody, 6 * nv, 12 * ncon + 6 * ncon + 6 * max(ncb, 1)))
+    R("ref", 3 * max(len(roots), 1))
+    R("aforce", max(nu, 1)); R("actdot", max(na, 1))
+    for v in ("qfrc_smooth", "qacc_smooth", "qacc", "x", "search", "qfrc_c"):
+        R(v, nv)
+    for k, v in lay.items():
+        S("o_" + k, v)
+    off = max(off, lay["crb"] + obs_size)  # the observation row is staged over crb/LD/T at the end of the step
+    S("smem_floats", off + (-off) % 4)
+    return t
+
+
+def model_dims(t: Dict[str, np.ndarray]) -> dict:
+    g = lambda k: int(t[k][0])
+    return dict(nq=g("nq"), nv=g("nv"), nu=g("nu"), na=g("na"), nbody=g("nbody"), ncon=g("ncon"),
+                obs_size=g("obs_size"), smem_floats=g("smem_floats"), n_frames=g("n_frames"), cone=g("cone"))

@@ -1,0 +1,183 @@
+"""ctypes binding of the C ABI (include/bt_api.h, libbt_b200.so).
+
+PyTorch is used only for device memory and streams: every call hands raw device pointers and the current
+CUDA stream to the library.  There is NO fallback: if the shared library is missing or a call fails, this
+module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libbt_b200.so")
+
+NUM_METRICS, NUM_INFO_F, NUM_INFO_I = 12, 5, 2
+METRIC_NAMES = ["pos_reward", "quat_reward", "joint_reward", "angvel_reward", "bodypos_reward", "endeff_reward",
+                "reward_quadctrl", "reward_alive", "too_far", "bad_pose", "bad_quat", "fall"]  # fruitfly.py:481-494
+INFO_F_NAMES = ["summed_pos_distance", "quat_distance", "joint_distance", "steps", "truncation"]
+INFO_I_NAMES = ["cur_frame", "steps_taken_cur_frame"]
+STATE_FIELDS = ("qpos", "qvel", "act", "qacc_warmstart", "time", "xpos")
+
+# exported symbols, exactly as declared in include/bt_api.h
+SYMBOLS = ["bt_model_create", "bt_model_destroy", "bt_model_dims", "bt_model_launch", "bt_reset", "bt_step",
+           "bt_physics_step", "bt_pipeline_init", "bt_reward_obs", "bt_forward_debug", "bt_last_error", "bt_launch_count"]
+
+
+class StatePtrs(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in STATE_FIELDS]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU or PyTorch fallback for the tracking step)")
+        l = C.CDLL(LIB_PATH)
+        l.bt_last_error.restype = C.c_char_p
+        l.bt_launch_count.restype = C.c_int64
+        for s in SYMBOLS:
+            getattr(l, s)
+        _lib = l
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise RuntimeError(f"libbt_b200: error {rc}: {lib().bt_last_error().decode()}")
+
+
+def launch_count() -> int:
+    return int(lib().bt_launch_count())
+
+
+class NativeModel:
+    """Owns a ``BtModel*`` (device copy of the packed tables)."""
+
+    def __init__(self, tables: Dict[str, np.ndarray], device: int = 0):
+        l = lib()
+        names = list(tables.keys())
+        arrs = [np.ascontiguousarray(tables[k]) for k in names]
+        for k, a in zip(names, arrs):
+            if a.dtype not in (np.float32, np.int32):
+                raise TypeError(f"table {k} has dtype {a.dtype}")
+        n = len(names)
+        c_names = (C.c_char_p * n)(*[k.encode() for k in names])
+        c_data = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+        c_counts = (C.c_int64 * n)(*[a.size for a in arrs])
+        c_isf = (C.c_int * n)(*[1 if a.dtype == np.float32 else 0 for a in arrs])
+        h = C.c_void_p()
+        _check(l.bt_model_create(n, c_names, c_data, c_counts, c_isf, int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+        self.tables = tables
+        d = (C.c_int * 8)()
+        _check(l.bt_model_dims(h, d))
+        self.nq, self.nv, self.nu, self.na, self.nbody, self.obs_size, self.smem_floats, self.ncon = [int(x) for x in d]
+        g = (C.c_int * 3)()
+        _check(l.bt_model_launch(h, g))
+        self.warps_per_cta, self.max_ctas, self.smem_bytes = int(g[0]), int(g[1]), int(g[2])
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and _lib is not None:
+            _lib.bt_model_destroy(h)
+            self._h = None
+
+    def offset(self, region: str) -> int:
+        return int(self.tables["o_" + region][0])
+
+    # ---- torch helpers -------------------------------------------------------------------------
+    def _torch(self):
+        import torch
+        return torch
+
+    def _dev(self):
+        return self._torch().device("cuda", self.device)
+
+    def new_state(self, n: int):
+        torch = self._torch()
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=self._dev())
+        return dict(qpos=z(n, self.nq), qvel=z(n, self.nv), act=z(n, self.na), qacc_warmstart=z(n, self.nv), time=z(n),
+                    xpos=z(n, 3 * self.nbody))
+
+    def new_outputs(self, n: int):
+        torch = self._torch()
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=self._dev())
+        return dict(obs=z(n, self.obs_size), reward=z(n), done=z(n), metrics=z(n, NUM_METRICS), info_f=z(n, NUM_INFO_F),
+                    info_i=torch.zeros(n, NUM_INFO_I, dtype=torch.int32, device=self._dev()))
+
+    def _sp(self, st, n) -> StatePtrs:
+        torch = self._torch()
+        shapes = dict(qpos=(n, self.nq), qvel=(n, self.nv), act=(n, self.na), qacc_warmstart=(n, self.nv), time=(n,),
+                      xpos=(n, 3 * self.nbody))
+        s = StatePtrs()
+        for k in STATE_FIELDS:
+            t = st[k]
+            if t.dtype != torch.float32 or not t.is_contiguous() or tuple(t.shape) != shapes[k] or t.device != self._dev():
+                raise ValueError(f"state['{k}'] must be a contiguous float32 {shapes[k]} tensor on cuda:{self.device}")
+            setattr(s, k, t.data_ptr() if t.numel() else None)
+        return s
+
+    def _p(self, t, shape, dtype=None):
+        torch = self._torch()
+        dtype = dtype or torch.float32
+        if t.dtype != dtype or not t.is_contiguous() or tuple(t.shape) != tuple(shape) or t.device != self._dev():
+            raise ValueError(f"expected a contiguous {dtype} tensor of shape {tuple(shape)} on cuda:{self.device}, got {t.dtype} {tuple(t.shape)}")
+        return C.c_void_p(t.data_ptr())
+
+    def _stream(self):
+        return C.c_void_p(self._torch().cuda.current_stream(self.device).cuda_stream)
+
+    # ---- entry points ----------------------------------------------------------------------------
+    def reset(self, keys, state, out):
+        torch = self._torch()
+        n = keys.shape[0]
+        _check(lib().bt_reset(self._h, n, self._p(keys, (n, 2), torch.uint32 if keys.dtype == torch.uint32 else torch.int32),
+                              self._sp(state, n), self._p(out["obs"], (n, self.obs_size)), self._p(out["reward"], (n,)),
+                              self._p(out["done"], (n,)), self._p(out["metrics"], (n, NUM_METRICS)),
+                              self._p(out["info_f"], (n, NUM_INFO_F)), self._p(out["info_i"], (n, NUM_INFO_I), torch.int32),
+                              self._stream()))
+
+    def step(self, action, state, first, first_obs, first_info_i, out):
+        torch = self._torch()
+        n = action.shape[0]
+        _check(lib().bt_step(self._h, n, self._p(action, (n, self.nu)), self._sp(state, n), self._sp(first, n),
+                             self._p(first_obs, (n, self.obs_size)), self._p(first_info_i, (n, NUM_INFO_I), torch.int32),
+                             self._p(out["obs"], (n, self.obs_size)), self._p(out["reward"], (n,)), self._p(out["done"], (n,)),
+                             self._p(out["metrics"], (n, NUM_METRICS)), self._p(out["info_f"], (n, NUM_INFO_F)),
+                             self._p(out["info_i"], (n, NUM_INFO_I), torch.int32), self._stream()))
+
+    def physics_step(self, ctrl, state, n_substeps: int):
+        n = state["qpos"].shape[0]
+        _check(lib().bt_physics_step(self._h, n, self._p(ctrl, (n, self.nu)), self._sp(state, n), int(n_substeps), self._stream()))
+
+    def pipeline_init(self, state):
+        n = state["qpos"].shape[0]
+        _check(lib().bt_pipeline_init(self._h, n, self._sp(state, n), self._stream()))
+
+    def reward_obs(self, action, state, out):
+        torch = self._torch()
+        n = action.shape[0]
+        _check(lib().bt_reward_obs(self._h, n, self._p(action, (n, self.nu)), self._sp(state, n),
+                                   self._p(out["info_i"], (n, NUM_INFO_I), torch.int32), self._p(out["obs"], (n, self.obs_size)),
+                                   self._p(out["reward"], (n,)), self._p(out["done"], (n,)), self._p(out["metrics"], (n, NUM_METRICS)),
+                                   self._p(out["info_f"], (n, NUM_INFO_F)), self._stream()))
+
+    def forward_debug(self, ctrl: Optional["object"], state, stop: int = 0):
+        torch = self._torch()
+        n = state["qpos"].shape[0]
+        scratch = torch.zeros(n, self.smem_floats, dtype=torch.float32, device=self._dev())
+        cdist = torch.zeros(n, max(self.ncon, 1), dtype=torch.float32, device=self._dev())
+        niter = torch.zeros(n, dtype=torch.int32, device=self._dev())
+        cp = self._p(ctrl, (n, self.nu)) if ctrl is not None else None
+        _check(lib().bt_forward_debug(self._h, n, cp, self._sp(state, n), int(stop), C.c_void_p(scratch.data_ptr()),
+                                      C.c_void_p(cdist.data_ptr()), C.c_void_p(niter.data_ptr()), self._stream()))
+        return scratch, cdist, niter

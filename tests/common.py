@@ -1,0 +1,49 @@
+"""Shared fixtures: compiled models, synthetic clips, packed tables, oracles (TEST INFRASTRUCTURE)."""
+from __future__ import annotations
+
+import functools
+
+import numpy as np
+
+import env_oracle
+import oracle
+from brax_tracking_b200 import assets, clips, configs, model
+
+ENV_ARGS = dict(rodent=configs.RODENT_ENV_ARGS, fly_free=configs.FLY_FREEJNT_ENV_ARGS, fly_tethered=configs.FLY_ENV_ARGS)
+
+
+@functools.lru_cache(maxsize=None)
+def setup(name: str):
+    """-> (mjcf.Model, cfg, clip dict, packed tables)"""
+    m = assets.load_model(name)
+    args = ENV_ARGS[name]
+    cfg = configs.resolve(m, args)
+    clip = clips.synthetic_clip(m, args["free_jnt"], z_stand=default_z(name)).as_dict()
+    return m, cfg, clip, model.pack(m, cfg, clip)
+
+
+def default_z(name):
+    # standing height of the synthetic clip's root (the models' qpos0 root height)
+    return None
+
+
+@functools.lru_cache(maxsize=None)
+def oracles(name: str, dtype=np.float64):
+    m, cfg, clip, _ = setup(name)
+    o = oracle.Oracle(m, dtype)
+    return o, env_oracle.EnvOracle(o, clip, cfg, dtype=np.float32)
+
+
+def jax_keys(n: int, seed: int = 0) -> np.ndarray:
+    """jax.random.split(jax.random.PRNGKey(seed), n) -> [n, 2] uint32 (custom_ppo.py:221)."""
+    return env_oracle.split((np.uint32(0), np.uint32(seed)), n)
+
+
+def actions(n_steps: int, n: int, nu: int, seed: int = 1, scale: float = 1.0) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    return (scale * np.tanh(rng.standard_normal((n_steps, n, nu)))).astype(np.float32)
+
+
+def region(tables, scratch, name, size):
+    o = int(tables["o_" + name][0])
+    return scratch[..., o:o + size]

@@ -1,0 +1,170 @@
+"""Backend-agnostic parity cases: the per-environment programs (CUDA through the C ABI, or the 1-lane host
+emulation) against the oracle on identical seeded inputs.  Tolerances are stated here, next to the assertions.
+
+Why the trajectory cases are *teacher forced*: the reference configuration (4 CG iterations, contact switching,
+milligram bodies) is chaotic in fp32 -- the oracle's own float32 build departs from its float64 build by ~1e-6 after
+one control step, ~1e-3 after two and O(1) after five (DESIGN.md "parity").  A free-running comparison after 10 or
+100 control steps therefore measures the Lyapunov exponent, not the implementation.  Instead every control step of a
+100-step trajectory is started from the ORACLE's state, the integer / flag outputs are required to be bit-exact, and
+the one-step float error distribution is required to be no worse than the float32 oracle's own."""
+from __future__ import annotations
+
+import numpy as np
+
+import common
+import oracle as oracle_mod
+from backends import state_from_oracle
+
+
+def random_states(m, N, seed=0):
+    rng = np.random.default_rng(seed)
+    st = dict(qpos=np.zeros((N, m.nq), np.float32), qvel=np.zeros((N, m.nv), np.float32), act=np.zeros((N, m.na), np.float32),
+              qacc_warmstart=np.zeros((N, m.nv), np.float32), time=np.zeros(N, np.float32), xpos=np.zeros((N, 3 * m.nbody), np.float32))
+    free = m.jnt_type[0] == 0
+    for e in range(N):
+        q = m.qpos0.copy()
+        hinge = slice(7, None) if free else slice(0, None)
+        q[hinge] += rng.uniform(-0.2, 0.2, q[hinge].shape)
+        if free:
+            q[2] += rng.uniform(-0.01, 0.02)
+            quat = np.array([1.0, 0, 0, 0]) + rng.uniform(-0.2, 0.2, 4)
+            q[3:7] = quat / np.linalg.norm(quat)
+        st["qpos"][e] = q
+        st["qvel"][e] = rng.uniform(-1, 1, m.nv)
+        st["act"][e] = rng.uniform(-0.5, 0.5, m.na)
+        st["qacc_warmstart"][e] = rng.uniform(-5, 5, m.nv)
+    ctrl = rng.uniform(-1, 1, (N, m.nu)).astype(np.float32)
+    return st, ctrl
+
+
+def check_forward_intermediates(backend, name, N=8):
+    """kinematics / smooth forces / tree-sparse factor+solve / collision / CG vs the dense float64 oracle."""
+    m, cfg, clip, tables = common.setup(name)
+    o, _ = common.oracles(name)
+    st, ctrl = random_states(m, N)
+    full, cdist, niter = backend.forward_debug(st, ctrl, 0)
+    at5, _, _ = backend.forward_debug(st, ctrl, 5)
+    R = lambda s, e, nm, size: common.region(tables, s[e], nm, size).astype(np.float64)
+    for e in range(N):
+        o.set_state(st["qpos"][e].astype(np.float64), st["qvel"][e].astype(np.float64), st["act"][e].astype(np.float64),
+                    st["qacc_warmstart"][e].astype(np.float64), ctrl[e].astype(np.float64))
+        o.forward()
+        d = o.d
+        np.testing.assert_allclose(R(full, e, "xpos", 3 * m.nbody), d.xpos, atol=2e-6)          # fp32 rounding over a 39-deep chain
+        np.testing.assert_allclose(R(full, e, "xquat", 4 * m.nbody), d.xquat, atol=2e-6)
+        sc = np.abs(d.qfrc_smooth).max()
+        np.testing.assert_allclose(R(at5, e, "qfrc_smooth", m.nv), d.qfrc_smooth, atol=2e-5 * sc)
+        sa = np.abs(d.qacc_smooth).max()
+        np.testing.assert_allclose(R(at5, e, "qacc_smooth", m.nv), d.qacc_smooth, atol=5e-4 * sa)  # cond(M) ~ 1e4..1e5
+        if m.a["pair_ncon"].sum():
+            np.testing.assert_allclose(cdist[e], d.con_dist, atol=2e-6)
+        np.testing.assert_allclose(R(full, e, "qacc", m.nv), d.qacc, atol=1e-3 * sa)
+        sf = max(np.abs(d.qfrc_constraint).max(), 1e-3)
+        np.testing.assert_allclose(R(full, e, "qfrc_c", m.nv), d.qfrc_constraint, atol=5e-2 * sf)   # 4 CG iterations, not converged
+
+
+def check_reset(backend, name, N=32, seed=3):
+    m, cfg, clip, tables = common.setup(name)
+    _, eo = common.oracles(name)
+    keys = common.jax_keys(N, seed=seed)
+    st, out = backend.reset(keys)
+    s0 = eo.reset(keys)
+    assert np.array_equal(out["info_i"][:, 0], s0["info"]["cur_frame"])               # threefry randint: bit exact
+    assert np.array_equal(out["info_i"][:, 1], s0["info"]["steps_taken_cur_frame"])
+    assert np.array_equal(st["qvel"], s0["pipeline_state"]["qvel"])                    # threefry uniform: bit exact
+    np.testing.assert_allclose(st["qpos"], s0["pipeline_state"]["qpos"], atol=1.2e-7)   # root quaternion renormalised (1 ulp)
+    np.testing.assert_allclose(out["obs"], s0["obs"], atol=2e-5)
+    sw = np.abs(s0["pipeline_state"]["qacc_warmstart"]).max()
+    np.testing.assert_allclose(st["qacc_warmstart"], s0["pipeline_state"]["qacc_warmstart"], atol=1e-3 * sw)
+    assert not out["done"].any() and not out["reward"].any() and not out["metrics"].any()
+    return st, out, s0
+
+
+def check_teacher_forced(backend, name, N=16, T=100, seed=5, act_scale=0.3):
+    m, cfg, clip, tables = common.setup(name)
+    o64, eo = common.oracles(name)
+    o32 = oracle_mod.Oracle(m, np.float32)
+    keys = common.jax_keys(N, seed=seed)
+    acts = common.actions(T, N, m.nu, seed=seed + 2, scale=act_scale)
+    s = eo.reset(keys)
+    first = state_from_oracle(s["info"]["first_pipeline_state"], N)
+    first_obs = np.array(s["info"]["first_obs"], np.float32)
+    first_ii = np.stack([s["info"]["first_cur_frame"], s["info"]["first_steps_taken_cur_frame"]], 1).astype(np.int32)
+    n_done = 0
+    eq, ev, oq, ov, er = [], [], [], [], []
+    for t in range(T):
+        st = state_from_oracle(s["pipeline_state"], N)
+        out = backend.new_outputs(N)
+        out["done"][:] = s["done"]
+        out["info_f"][:, 3] = s["info"]["steps"]
+        out["info_i"][:, 0] = s["info"]["cur_frame"]
+        out["info_i"][:, 1] = s["info"]["steps_taken_cur_frame"]
+        p32 = o32.pipeline_batch({k: np.array(v, np.float32) for k, v in s["pipeline_state"].items()}, acts[t], cfg["n_frames"])
+        backend.step(st, out, first, first_obs, first_ii, acts[t])
+        s = eo.step(s, acts[t])
+        # ---- bit-exact: done flags, frame counters, episode counters, reset selection
+        assert np.array_equal(out["done"], s["done"]), f"done flags differ at step {t}"
+        assert np.array_equal(out["info_i"][:, 0], s["info"]["cur_frame"]), f"cur_frame differs at step {t}"
+        assert np.array_equal(out["info_i"][:, 1], s["info"]["steps_taken_cur_frame"])
+        assert np.array_equal(out["info_f"][:, 3], s["info"]["steps"])
+        assert np.array_equal(out["info_f"][:, 4], s["info"]["truncation"])
+        for k in ("too_far", "bad_pose", "bad_quat", "fall"):
+            assert np.array_equal(out["metrics"][:, common_metric(k)], s["metrics"][k]), f"{k} differs at step {t}"
+        d = s["done"] > 0
+        n_done += int(d.sum())
+        if d.any():  # auto-reset restored the cached first state exactly
+            assert np.array_equal(st["qpos"][d], first["qpos"][d]) and np.array_equal(out["obs"][d], first_obs[d])
+        nd = ~d
+        ref = s["pipeline_state"]
+        eq.append(np.abs(st["qpos"] - ref["qpos"])[nd].max(1)); ev.append(np.abs(st["qvel"] - ref["qvel"])[nd].max(1))
+        oq.append(np.abs(p32["qpos"] - ref["qpos"])[nd].max(1)); ov.append(np.abs(p32["qvel"] - ref["qvel"])[nd].max(1))
+        er.append(np.abs(out["reward"] - s["reward"]))
+    assert n_done > 0, "the trajectory never exercised the auto-reset path"
+    eq, ev, oq, ov, er = (np.concatenate(x) for x in (eq, ev, oq, ov, er))
+    # ---- fp32 tolerance after ONE control step (n_frames substeps) from identical inputs:
+    #      absolute bounds on the bulk, and no worse than 3x the float32 oracle's own departure from float64 in the tails
+    assert np.median(eq) < 1e-4 and np.median(ev) < 2e-2, (np.median(eq), np.median(ev))
+    for p in (50, 90, 99, 100):
+        assert np.percentile(eq, p) <= 3 * np.percentile(oq, p) + 1e-5, (p, np.percentile(eq, p), np.percentile(oq, p))
+        assert np.percentile(ev, p) <= 3 * np.percentile(ov, p) + 1e-3, (p, np.percentile(ev, p), np.percentile(ov, p))
+    assert np.median(er) < 1e-4 and er.max() < 2e-2, (np.median(er), er.max())
+    return dict(n_done=n_done, qpos_med=float(np.median(eq)), qpos_max=float(eq.max()), qvel_med=float(np.median(ev)))
+
+
+def common_metric(name):
+    from brax_tracking_b200 import native
+    return native.METRIC_NAMES.index(name)
+
+
+def check_physics_1_10_100(backend, name, N=8, seed=11):
+    """Free-running qpos/qvel after 1, 10 and 100 control steps.  1 step: fp32 tolerance.  10 / 100 steps: the departure
+    from the float64 oracle must stay within 5x of the float32 oracle's own departure (same arithmetic precision, same
+    chaos), and the zero-action trajectory must settle to the same resting height."""
+    m, cfg, clip, tables = common.setup(name)
+    o64, eo = common.oracles(name)
+    o32 = oracle_mod.Oracle(m, np.float32)
+    keys = common.jax_keys(N, seed=seed)
+    s0 = eo.reset(keys)
+    res = {}
+    for label, scale in (("zero", 0.0), ("policy", 0.3)):
+        acts = common.actions(100, N, m.nu, seed=seed, scale=scale)
+        p64 = {k: np.asarray(v, np.float64) for k, v in s0["pipeline_state"].items()}
+        p32 = {k: np.array(v, np.float32) for k, v in s0["pipeline_state"].items()}
+        st = state_from_oracle(s0["pipeline_state"], N)
+        for t in range(1, 101):
+            p64 = o64.pipeline_batch(p64, acts[t - 1].astype(np.float64), cfg["n_frames"])
+            p32 = o32.pipeline_batch(p32, acts[t - 1], cfg["n_frames"])
+            backend.physics_step(st, acts[t - 1], cfg["n_frames"])
+            if t in (1, 10, 100):
+                e = np.abs(st["qpos"] - p64["qpos"]).max(); eo32 = np.abs(p32["qpos"] - p64["qpos"]).max()
+                ev = np.abs(st["qvel"] - p64["qvel"]).max(); ev32 = np.abs(p32["qvel"] - p64["qvel"]).max()
+                res[(label, t)] = (e, eo32, ev, ev32)
+                assert np.isfinite(st["qpos"]).all()
+                if t == 1:
+                    assert e < 5e-5 and ev < 2e-2, (label, t, e, ev)      # fp32 tolerance after 1 control step
+                else:
+                    assert e <= 5 * eo32 + 1e-3, (label, t, e, eo32)
+                    assert ev <= 5 * ev32 + 5e-2, (label, t, ev, ev32)
+        if label == "zero" and m.jnt_type[0] == 0:
+            np.testing.assert_allclose(st["qpos"][:, 2], p64["qpos"][:, 2], atol=5e-3)   # same resting height
+    return res

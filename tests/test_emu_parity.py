@@ -1,0 +1,30 @@
+"""CPU suite: the kernels' per-environment programs compiled for the host (one lane per environment) against the
+oracle.  This pins the table logic, tree-sparse factorisation, matrix-free Jacobian, CG solver and the env layer
+without a GPU; the warp-level build is checked by tests/test_gpu_parity.py on the B200."""
+import pytest
+
+import common
+import parity_cases as pc
+from backends import EmuBackend
+
+
+@pytest.fixture(scope="module")
+def rodent_emu():
+    return EmuBackend(common.setup("rodent")[3])
+
+
+def test_forward_intermediates(rodent_emu):
+    pc.check_forward_intermediates(rodent_emu, "rodent", N=4)
+
+
+def test_reset(rodent_emu):
+    pc.check_reset(rodent_emu, "rodent", N=16)
+
+
+def test_teacher_forced_wrapped_step(rodent_emu):
+    r = pc.check_teacher_forced(rodent_emu, "rodent", N=8, T=60)
+    assert r["n_done"] > 0
+
+
+def test_physics_1_10_100(rodent_emu):
+    pc.check_physics_1_10_100(rodent_emu, "rodent", N=4)
