@@ -71,6 +71,7 @@ struct BtEnv {
   BT_DEV float* xv() const { return s + m.o_x; }
   BT_DEV float* search() const { return s + m.o_search; }
   BT_DEV float* qfrc_c() const { return s + m.o_qfrc_c; }
+  BT_DEV float* tmpv() const { return s + m.o_tmpv; }
   // T-region views during the constraint phase
   BT_DEV float* congeo() const { return T(); }                          // [ncon][12] off(3) frame(9)
   BT_DEV float* wrench() const { return T() + 12 * m.ncon; }            // [ncon][6]
@@ -356,31 +357,30 @@ struct BtEnv {
     W::sync();
   }
 
-  // y = M v for lane-owned dofs (reads the *unfactored* M in LD; v in scratch)
-  BT_DEV void mul_M(const float* v, float y[DS]) {
-#pragma unroll
-    for (int sl = 0; sl < DS; sl++) {
-      const int i = lane + sl * G;
+  // y = M v (reads the *unfactored* M in LD; v, y in scratch)
+  BT_DEV void mul_M(const float* v, float* y) {
+    for (int i = lane; i < m.nv; i += G) {
+      const int ad = BT_LDG(m.dof_Madr + i), d = BT_LDG(m.dof_depth + i);
       float acc = 0.f;
-      if (i < m.nv) {
-        const int ad = BT_LDG(m.dof_Madr + i), d = BT_LDG(m.dof_depth + i);
-        for (int a = 0; a <= d; a++) acc += LD()[ad + a] * v[BT_LDG(m.M_col + ad + a)];
-        const int nd = BT_LDG(m.dof_subtreenum + i);
-        for (int i2 = i + 1; i2 < i + nd; i2++)
-          acc += LD()[BT_LDG(m.dof_Madr + i2) + BT_LDG(m.dof_depth + i2) - d] * v[i2];
-      }
-      y[sl] = acc;
+      for (int a = 0; a <= d; a++) acc += LD()[ad + a] * v[BT_LDG(m.M_col + ad + a)];
+      const int nd = BT_LDG(m.dof_subtreenum + i);
+      for (int i2 = i + 1; i2 < i + nd; i2++) acc += LD()[BT_LDG(m.dof_Madr + i2) + BT_LDG(m.dof_depth + i2) - d] * v[i2];
+      y[i] = acc;
     }
+    W::sync();
   }
 
-  // ================================================================== P6: in-place L'DL (MuJoCo mj_factorM order)
+  // ================================================================== P6: in-place L'DL, then in-place L -> L^-1
+  // After factor(): LD row k holds D[k] at a = 0 and the UNSCALED entries D[k] * L[k, anc_a] at a >= 1; Dinv[k] = 1 / D[k].
+  // (MuJoCo mj_factorM visiting order; one warp sync per dof: the row scaling is folded into invert().)
   BT_DEV void factor() {
     float* ld = LD();
     for (int k = m.nv - 1; k >= 0; k--) {
-      const int ad = BT_LDG(m.dof_Madr + k), d = BT_LDG(m.dof_depth + k);
+      const int md = BT_LDG(m.dof_md + k), ad = md & 0xffff, d = md >> 16;
       const float inv = 1.0f / ld[ad];
       if (lane == 0) Dinv()[k] = inv;
       if (d == 0) continue;
+      // the d (d + 1) / 2 updates (a <= b) of this row are independent: flat triangular enumeration over the lanes
       const int nt = d * (d + 1) / 2;
       for (int t = lane; t < nt; t += G) {
         const int ab = BT_LDG(m.tri_ab + t), a = ab & 255, b = ab >> 8;
@@ -388,34 +388,60 @@ struct BtEnv {
         ld[ia + b - a] -= ld[ad + a] * inv * ld[ad + b];
       }
       W::sync();
-      for (int a = 1 + lane; a <= d; a += G) ld[ad + a] *= inv;
-      W::sync();
     }
     W::sync();
   }
 
-  // x <- M^-1 x (in scratch), using the factor in LD / Dinv
+  // L^-1 has the same ancestor sparsity as L; computed level by level (dof depth ascending), in place:
+  //   Linv[i, a] = -L[i, a] - sum_{c < a} L[i, c] * Linv[anc_c(i), a - c],   L[i, c] = LD[i, c] * Dinv[i]
+  // items of a level are ordered by descending a inside a row, so a round never overwrites an entry that a later
+  // round of the same row still reads.
+  BT_DEV void invert() {
+    float* ld = LD();
+    for (int lv = 0; lv < m.nlevd; lv++) {
+      const int i0 = BT_LDG(m.inv_adr + lv), i1 = BT_LDG(m.inv_adr + lv + 1);
+      for (int base = i0; base < i1; base += G) {
+        const int it = base + lane;
+        float val = 0.f;
+        int dst = -1;
+        if (it < i1) {
+          const int pk = BT_LDG(m.inv_item + it), i = pk & 255, a = pk >> 8;
+          const int ad = BT_LDG(m.dof_Madr + i);
+          const float di = Dinv()[i];
+          float acc = ld[ad + a];
+          for (int c = 1; c < a; c++) acc += ld[ad + c] * ld[BT_LDG(m.M_colMadr + ad + c) + a - c];
+          val = -acc * di;
+          dst = ad + a;
+        }
+        W::sync();
+        if (dst >= 0) ld[dst] = val;
+        W::sync();
+      }
+    }
+  }
+
+  // x <- M^-1 x with M = L' D L:  M^-1 = Linv Dinv Linv'  -- two dependency-free tree-sparse mat-vecs
+  // (descendant gather with Linv', then ancestor gather with Linv); tmp = scratch vector `tmpv`
   BT_DEV void solve(float* x) {
     const float* ld = LD();
-    for (int i = m.nv - 1; i > 0; i--) {
-      const int d = BT_LDG(m.dof_depth + i);
-      if (d == 0) continue;
-      const int ad = BT_LDG(m.dof_Madr + i);
-      const float xi = x[i];
-      for (int a = 1 + lane; a <= d; a += G) x[BT_LDG(m.M_col + ad + a)] -= ld[ad + a] * xi;
-      W::sync();
+    float* y = tmpv();
+    for (int j = lane; j < m.nv; j += G) {
+      const int nd = BT_LDG(m.dof_subtreenum + j), dj = BT_LDG(m.dof_md + j) >> 16;
+      float acc = x[j];
+      for (int i2 = j + 1; i2 < j + nd; i2++) {
+        const int md = BT_LDG(m.dof_md + i2);
+        acc += ld[(md & 0xffff) + (md >> 16) - dj] * x[i2];
+      }
+      y[j] = acc * Dinv()[j];
     }
-    for (int i = lane; i < m.nv; i += G) x[i] *= Dinv()[i];
     W::sync();
-    for (int j = 0; j < m.nv - 1; j++) {
-      const int nd = BT_LDG(m.dof_subtreenum + j);
-      if (nd == 1) continue;
-      const int dj = BT_LDG(m.dof_depth + j);
-      const float xj = x[j];
-      for (int i2 = j + 1 + lane; i2 < j + nd; i2 += G)
-        x[i2] -= ld[BT_LDG(m.dof_Madr + i2) + BT_LDG(m.dof_depth + i2) - dj] * xj;
-      W::sync();
+    for (int i = lane; i < m.nv; i += G) {
+      const int md = BT_LDG(m.dof_md + i), ad = md & 0xffff, d = md >> 16;
+      float acc = y[i];
+      for (int a = 1; a <= d; a++) acc += ld[ad + a] * y[BT_LDG(m.M_col + ad + a)];
+      x[i] = acc;
     }
+    W::sync();
   }
 
   // ================================================================== P8: collision (static contact list)
@@ -599,9 +625,12 @@ struct BtEnv {
     if (sr0 <= 0.f) k = -sr0 / (dmax * dmax);
     if (sr1 <= 0.f) b = -sr1 / dmax;
     const float x = fabsf(pos) / width;
-    const float ia = (1.f / powf(mid, power - 1.f)) * powf(x, power);
-    const float ib = 1.f - (1.f / powf(1.f - mid, power - 1.f)) * powf(1.f - x, power);
-    const float y = x < mid ? ia : ib;
+    float y;
+    if (power == 2.f) {  // MuJoCo default; the general case goes through the out-of-line helper (code size)
+      y = x < mid ? x * x / mid : 1.f - (1.f - x) * (1.f - x) / (1.f - mid);
+    } else {
+      y = bt_impedance_pow(x, mid, power);
+    }
     float im = dmin + y * (dmax - dmin);
     im = bt_clampf(im, dmin, dmax);
     if (x > 1.f) im = dmax;
@@ -609,9 +638,7 @@ struct BtEnv {
   }
 
   // make_constraint: fills D / mu / limit rows and the row-wise aref (returned for the jar initialisation)
-  BT_DEV void make_rows(Efc& e, float aref[CS][4], float laref[DS]) {
-    float jv[CS][3];
-    jdot(qvel(), jv);
+  BT_DEV void make_rows(Efc& e, const float jv[CS][3], float aref[CS][4], float laref[DS]) {
 #pragma unroll
     for (int sl = 0; sl < CS; sl++) {
       const int c = lane + sl * G;
@@ -675,22 +702,6 @@ struct BtEnv {
     }
   }
 
-  // jar for a candidate qacc (scratch vector a)
-  BT_DEV void init_jar(Efc& e, const float aref[CS][4], const float laref[DS], const float* a) {
-    float jq[CS][3];
-    jdot(a, jq);
-#pragma unroll
-    for (int sl = 0; sl < CS; sl++) row_combine(e, sl, jq[sl], e.jar[sl]);
-#pragma unroll
-    for (int sl = 0; sl < CS; sl++)
-#pragma unroll
-      for (int r = 0; r < 4; r++) e.jar[sl][r] -= aref[sl][r];
-#pragma unroll
-    for (int sl = 0; sl < DS; sl++) {
-      const int i = lane + sl * G;
-      e.ljar[sl] = (i < m.nv ? e.lsg[sl] * a[i] : 0.f) - laref[sl];
-    }
-  }
   // base (normal, t1, t2) projections -> row values
   BT_DEV void row_combine(const Efc& e, int sl, const float base[3], float out[4]) const {
     if (m.cone == BT_CONE_PYRAMIDAL) {
@@ -716,7 +727,8 @@ struct BtEnv {
   }
 
   // cost of the constraint rows at jar; optionally the base-direction forces per contact and limit forces
-  BT_DEV float rows_cost(const Efc& e, float fbase[CS][3], float lforce[DS], bool want_force) const {
+  template <bool want_force>
+  BT_DEV float rows_cost(const Efc& e, float fbase[CS][3], float lforce[DS]) const {
     float cost = 0.f;
 #pragma unroll
     for (int sl = 0; sl < CS; sl++) {
@@ -760,7 +772,7 @@ struct BtEnv {
   }
 
   // qfrc_constraint = J^T f  (per-dof gather over the contacts whose chain contains the dof) -> scratch + regs
-  BT_DEV void jt_force(const Efc& e, const float fbase[CS][3], const float lforce[DS], float qc[DS]) {
+  BT_DEV void jt_force(const Efc& e, const float fbase[CS][3], const float lforce[DS]) {
 #pragma unroll
     for (int sl = 0; sl < CS; sl++) {
       const int c = lane + sl * G;
@@ -784,7 +796,6 @@ struct BtEnv {
           acc += BT_LDG(m.dofcon_sign + k) * bt_dot6(cdof() + 6 * i, wrench() + 6 * BT_LDG(m.dofcon_c + k));
         qfrc_c()[i] = acc;
       }
-      qc[sl] = acc;
     }
     W::sync();
   }
@@ -862,94 +873,133 @@ struct BtEnv {
   }
 
   // ================================================================== P9-P11: constraint solve (CG, primal in qacc)
-  // in: qfrc_smooth, qacc_smooth, warm (scratch), unfactored-M product Ma_warm (regs), factor in LD
+  // in: qfrc_smooth, qacc_smooth, warm (scratch), Ma_warm = M * warm in `qfrc_c` (scratch), L^-1 in LD
   // out: qacc, qfrc_c (scratch); warm <- qacc
-  BT_DEV void solve_constraints(const float Ma_warm[DS]) {
+  // Same algorithm as MJX solver.solve; the loop is rotated so that update_constraint /
+  // update_gradient / the M^-1 solve / the line search each have ONE call site (instruction-cache footprint).
+  BT_DEV void solve_constraints() {
     Efc e;
-    float qfs[DS], qas[DS];
+    float qfs[DS], qas[DS], Ma[DS];
 #pragma unroll
     for (int sl = 0; sl < DS; sl++) {
       const int i = lane + sl * G;
       qfs[sl] = i < m.nv ? qfrc_smooth()[i] : 0.f;
       qas[sl] = i < m.nv ? qacc_smooth()[i] : 0.f;
+      Ma[sl] = i < m.nv ? qfrc_c()[i] : 0.f;  // M * warm for now
     }
-    float Ma[DS], qc[DS];
-    float gauss, cost, prev_cost;
+    float gauss = 0.f;
     {
-      float aref[CS][4], laref[DS];
-      make_rows(e, aref, laref);
-      // warm-start selection (MJX solver.solve): keep the cheaper of qacc_warmstart / qacc_smooth
-      init_jar(e, aref, laref, warm());
-      float g = 0.f;
+      // candidate loop: c = 0 rows from qvel (make_constraint), c = 1 cost at qacc_warmstart, c = 2 cost at qacc_smooth
+      float aref[CS][4], laref[DS], jw[CS][4], ljw[DS];
+      float cost_w = 0.f, gauss_w = 0.f;
+      for (int c = 0; c < 3; c++) {
+        const float* vec = c == 0 ? qvel() : (c == 1 ? warm() : qacc_smooth());
+        float jb[CS][3];
+        jdot(vec, jb);
+        if (c == 0) {
+          make_rows(e, jb, aref, laref);
+          continue;
+        }
 #pragma unroll
-      for (int sl = 0; sl < DS; sl++) {
-        const int i = lane + sl * G;
-        if (i < m.nv) g += (Ma_warm[sl] - qfs[sl]) * (warm()[i] - qas[sl]);
+        for (int sl = 0; sl < CS; sl++) {
+          row_combine(e, sl, jb[sl], e.jar[sl]);
+#pragma unroll
+          for (int r = 0; r < 4; r++) e.jar[sl][r] -= aref[sl][r];
+        }
+        float g = 0.f;
+#pragma unroll
+        for (int sl = 0; sl < DS; sl++) {
+          const int i = lane + sl * G;
+          const float vi = i < m.nv ? vec[i] : 0.f;
+          e.ljar[sl] = e.lsg[sl] * vi - laref[sl];
+          if (c == 1) g += (Ma[sl] - qfs[sl]) * (vi - qas[sl]);
+        }
+        const float rc = rows_cost<false>(e, nullptr, nullptr);
+        if (c == 1) {
+          gauss_w = 0.5f * W::allsum(g);
+          cost_w = rc + gauss_w;
+#pragma unroll
+          for (int sl = 0; sl < CS; sl++)
+#pragma unroll
+            for (int r = 0; r < 4; r++) jw[sl][r] = e.jar[sl][r];
+#pragma unroll
+          for (int sl = 0; sl < DS; sl++) ljw[sl] = e.ljar[sl];
+        } else {
+          // warm-start selection (MJX solver.solve): keep the cheaper of qacc_warmstart / qacc_smooth
+          const bool use_warm = cost_w < rc;
+          if (use_warm) {
+#pragma unroll
+            for (int sl = 0; sl < CS; sl++)
+#pragma unroll
+              for (int r = 0; r < 4; r++) e.jar[sl][r] = jw[sl][r];
+#pragma unroll
+            for (int sl = 0; sl < DS; sl++) e.ljar[sl] = ljw[sl];
+          }
+#pragma unroll
+          for (int sl = 0; sl < DS; sl++) {
+            const int i = lane + sl * G;
+            if (!use_warm) Ma[sl] = qfs[sl];  // M * qacc_smooth = qfrc_smooth
+            if (i < m.nv) qacc()[i] = use_warm ? warm()[i] : qas[sl];
+          }
+          gauss = use_warm ? gauss_w : 0.f;
+        }
       }
-      const float gauss_w = 0.5f * W::allsum(g);
-      const float cost_w = rows_cost(e, nullptr, nullptr, false) + gauss_w;
-      float jw[CS][4], ljw[DS];
-#pragma unroll
-      for (int sl = 0; sl < CS; sl++)
-#pragma unroll
-        for (int r = 0; r < 4; r++) jw[sl][r] = e.jar[sl][r];
-#pragma unroll
-      for (int sl = 0; sl < DS; sl++) ljw[sl] = e.ljar[sl];
-      init_jar(e, aref, laref, qacc_smooth());
-      const float cost_s = rows_cost(e, nullptr, nullptr, false);
-      const bool use_warm = cost_w < cost_s;
-      if (use_warm) {
-#pragma unroll
-        for (int sl = 0; sl < CS; sl++)
-#pragma unroll
-          for (int r = 0; r < 4; r++) e.jar[sl][r] = jw[sl][r];
-#pragma unroll
-        for (int sl = 0; sl < DS; sl++) e.ljar[sl] = ljw[sl];
-      }
-#pragma unroll
-      for (int sl = 0; sl < DS; sl++) {
-        const int i = lane + sl * G;
-        Ma[sl] = use_warm ? Ma_warm[sl] : qfs[sl];
-        if (i < m.nv) qacc()[i] = use_warm ? warm()[i] : qas[sl];
-      }
-      gauss = use_warm ? gauss_w : 0.f;
       W::sync();
     }
     float grad[DS], Mgrad[DS], mv[DS];
-    // update_constraint + update_gradient
-    {
-      float fbase[CS][3], lforce[DS];
-      const float c = rows_cost(e, fbase, lforce, true);
-      jt_force(e, fbase, lforce, qc);
-      prev_cost = INFINITY;
-      cost = c + gauss;
-    }
-    float gnorm2 = 0.f;
 #pragma unroll
-    for (int sl = 0; sl < DS; sl++) {
-      const int i = lane + sl * G;
-      grad[sl] = Ma[sl] - qfs[sl] - qc[sl];
-      if (i < m.nv) { xv()[i] = grad[sl]; gnorm2 += grad[sl] * grad[sl]; }
-    }
-    gnorm2 = W::allsum(gnorm2);
-    W::sync();
-    solve(xv());
-#pragma unroll
-    for (int sl = 0; sl < DS; sl++) {
-      const int i = lane + sl * G;
-      Mgrad[sl] = i < m.nv ? xv()[i] : 0.f;
-      mv[sl] = -grad[sl];  // M * search with search = -Mgrad
-      if (i < m.nv) search()[i] = -Mgrad[sl];
-    }
-    W::sync();
+    for (int sl = 0; sl < DS; sl++) grad[sl] = Mgrad[sl] = mv[sl] = 0.f;
+    float cost = INFINITY, prev_cost = 0.f;
     const float nvf = (float)(m.nv > 1 ? m.nv : 1);
     const float scale = 1.0f / (m.meaninertia * nvf);
     int it = 0;
     while (true) {
+      // ---- update_constraint: cost + forces + qfrc_constraint = J' f
+      {
+        float fbase[CS][3], lforce[DS];
+        const float c = rows_cost<true>(e, fbase, lforce);
+        jt_force(e, fbase, lforce);
+        prev_cost = cost;
+        cost = c + gauss;
+      }
+      // ---- update_gradient: grad = M a - qfrc_smooth - qfrc_constraint; Mgrad = M^-1 grad; Polak-Ribiere direction
+      float pg_pMg = 0.f, g_pMg = 0.f, gnorm2 = 0.f;
+#pragma unroll
+      for (int sl = 0; sl < DS; sl++) {
+        const int i = lane + sl * G;
+        pg_pMg += grad[sl] * Mgrad[sl];
+        grad[sl] = i < m.nv ? Ma[sl] - qfs[sl] - qfrc_c()[i] : 0.f;
+        g_pMg += grad[sl] * Mgrad[sl];
+        gnorm2 += grad[sl] * grad[sl];
+        if (i < m.nv) xv()[i] = grad[sl];
+      }
+      W::sync();
+      solve(xv());
+      float g_Mg = 0.f;
+#pragma unroll
+      for (int sl = 0; sl < DS; sl++) {
+        const int i = lane + sl * G;
+        Mgrad[sl] = i < m.nv ? xv()[i] : 0.f;
+        g_Mg += grad[sl] * Mgrad[sl];
+      }
+      pg_pMg = W::allsum(pg_pMg); g_pMg = W::allsum(g_pMg); g_Mg = W::allsum(g_Mg); gnorm2 = W::allsum(gnorm2);
+      float beta = 0.f;
+      if (it > 0) {
+        beta = (g_Mg - g_pMg) / (pg_pMg > BT_MINVAL ? pg_pMg : BT_MINVAL);
+        beta = beta < 0.f ? 0.f : beta;
+      }
+#pragma unroll
+      for (int sl = 0; sl < DS; sl++) {
+        const int i = lane + sl * G;
+        mv[sl] = -grad[sl] + beta * mv[sl];  // M * search without a product: M * Mgrad = grad
+        if (i < m.nv) search()[i] = -Mgrad[sl] + (it > 0 ? beta * search()[i] : 0.f);
+      }
+      W::sync();
+      // ---- termination test (MJX solve.cond)
       const float improvement = (prev_cost - cost) * scale;
       const float gradient = sqrtf(gnorm2) * scale;
       if (it >= m.iterations || improvement < m.tolerance || gradient < m.tolerance) break;
-      // ---- line search along `search`
+      // ---- exact line search along `search` (MJX solver._linesearch)
       float jv[CS][4], ljv[DS];
       {
         float sb[CS][3];
@@ -971,20 +1021,29 @@ struct BtEnv {
       const float qg[3] = {gauss, g1, g2};
       const float gtol = m.tolerance * m.ls_tolerance * sqrtf(sn) * m.meaninertia * nvf;
       LsPt p0, lo, hi;
-      { const float a0 = 0.f; ls_eval<1>(e, jv, ljv, qg, &a0, &p0); }
-      { const float a1 = p0.alpha - p0.d0 / p0.d1; ls_eval<1>(e, jv, ljv, qg, &a1, &lo); }
-      if (lo.d0 < p0.d0) { hi = p0; } else { hi = lo; lo = p0; }
+      p0.alpha = p0.cost = p0.d0 = p0.d1 = 0.f;
+      lo = hi = p0;
+      // stage 0: p0 = point(0); stage 1: lo = point(newton step from p0); stage >= 2: bracketing iterations
       bool swap = true;
-      int li = 0;
-      while (true) {
-        bool done = li >= m.ls_iterations;
-        done |= !swap;
-        done |= (lo.d0 < 0.f) && (lo.d0 > -gtol);
-        done |= (hi.d0 > 0.f) && (hi.d0 < gtol);
-        if (done) break;
-        const float al[3] = {lo.alpha - lo.d0 / lo.d1, hi.alpha - hi.d0 / hi.d1, 0.5f * (lo.alpha + hi.alpha)};
+      for (int stage = 0;; stage++) {
+        float al[3];
+        if (stage == 0) { al[0] = al[1] = al[2] = 0.f; }
+        else if (stage == 1) { al[0] = al[1] = al[2] = p0.alpha - p0.d0 / p0.d1; }
+        else {
+          bool done = stage - 2 >= m.ls_iterations;
+          done |= !swap;
+          done |= (lo.d0 < 0.f) && (lo.d0 > -gtol);
+          done |= (hi.d0 > 0.f) && (hi.d0 < gtol);
+          if (done) break;
+          al[0] = lo.alpha - lo.d0 / lo.d1; al[1] = hi.alpha - hi.d0 / hi.d1; al[2] = 0.5f * (lo.alpha + hi.alpha);
+        }
         LsPt pt[3];
         ls_eval<3>(e, jv, ljv, qg, al, pt);
+        if (stage == 0) { p0 = pt[0]; continue; }
+        if (stage == 1) {
+          if (pt[0].d0 < p0.d0) { lo = pt[0]; hi = p0; } else { lo = p0; hi = pt[0]; }
+          continue;
+        }
         const bool s_lo_next = (lo.d0 > 0.f) || (lo.d0 < pt[0].d0);
         if (s_lo_next) lo = pt[0];
         const bool s_lo_mid = (pt[2].d0 < 0.f) && (lo.d0 < pt[2].d0);
@@ -994,7 +1053,6 @@ struct BtEnv {
         const bool s_hi_mid = (pt[2].d0 > 0.f) && (hi.d0 > pt[2].d0);
         if (s_hi_mid) hi = pt[2];
         swap = s_lo_next || s_lo_mid || s_hi_next || s_hi_mid;
-        li++;
       }
       const bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
       const float alpha = lo.cost < hi.cost ? lo.alpha : hi.alpha;
@@ -1012,7 +1070,6 @@ struct BtEnv {
           for (int r = 0; r < 4; r++) e.jar[sl][r] += jv[sl][r] * alpha;
       }
       W::sync();
-      // ---- update_constraint
       float g = 0.f;
 #pragma unroll
       for (int sl = 0; sl < DS; sl++) {
@@ -1020,43 +1077,6 @@ struct BtEnv {
         if (i < m.nv) g += (Ma[sl] - qfs[sl]) * (qacc()[i] - qas[sl]);
       }
       gauss = 0.5f * W::allsum(g);
-      {
-        float fbase[CS][3], lforce[DS];
-        const float c = rows_cost(e, fbase, lforce, true);
-        jt_force(e, fbase, lforce, qc);
-        prev_cost = cost;
-        cost = c + gauss;
-      }
-      // ---- update_gradient + Polak-Ribiere direction
-      float pg_pMg = 0.f, g_pMg = 0.f;
-      gnorm2 = 0.f;
-#pragma unroll
-      for (int sl = 0; sl < DS; sl++) {
-        const int i = lane + sl * G;
-        pg_pMg += grad[sl] * Mgrad[sl];
-        grad[sl] = Ma[sl] - qfs[sl] - qc[sl];
-        g_pMg += grad[sl] * Mgrad[sl];
-        if (i < m.nv) { xv()[i] = grad[sl]; gnorm2 += grad[sl] * grad[sl]; }
-      }
-      W::sync();
-      solve(xv());
-      float g_Mg = 0.f;
-#pragma unroll
-      for (int sl = 0; sl < DS; sl++) {
-        const int i = lane + sl * G;
-        Mgrad[sl] = i < m.nv ? xv()[i] : 0.f;
-        g_Mg += grad[sl] * Mgrad[sl];
-      }
-      pg_pMg = W::allsum(pg_pMg); g_pMg = W::allsum(g_pMg); g_Mg = W::allsum(g_Mg); gnorm2 = W::allsum(gnorm2);
-      float beta = (g_Mg - g_pMg) / (pg_pMg > BT_MINVAL ? pg_pMg : BT_MINVAL);
-      beta = beta < 0.f ? 0.f : beta;
-#pragma unroll
-      for (int sl = 0; sl < DS; sl++) {
-        const int i = lane + sl * G;
-        mv[sl] = -grad[sl] + beta * mv[sl];
-        if (i < m.nv) search()[i] = -Mgrad[sl] + beta * search()[i];
-      }
-      W::sync();
       it++;
     }
     niter = it;
@@ -1064,39 +1084,45 @@ struct BtEnv {
     W::sync();
   }
 
-  // ================================================================== mjx.forward
-  // returns false when stopped early by a debug stop point
-  BT_DEV bool forward(int stop = BT_STOP_NONE) {
+  // ================================================================== mjx.step = forward (phase 0) + euler (phase 1)
+  // Both phases share ONE call site of build_M / factor / invert / solve: phase 0 factors M, phase 1 factors
+  // M + h * diag(damping) (MJX euler with implicit joint damping).
+  // returns false when stopped early by a debug stop point.
+  BT_DEV bool substep(bool do_euler, int stop = BT_STOP_NONE) {
     tree_forward();
     tree_backward();
     if (stop == BT_STOP_TREE) return false;
     smooth_forces();
     if (stop == BT_STOP_SMOOTH) return false;
-    build_M(0.f);
-    if (stop == BT_STOP_M) return false;
-    float Ma_warm[DS];
-    mul_M(warm(), Ma_warm);
-    W::sync();
-    factor();
-    if (stop == BT_STOP_FACTOR) return false;
-    for (int i = lane; i < m.nv; i += G) qacc_smooth()[i] = qfrc_smooth()[i];
-    W::sync();
-    solve(qacc_smooth());
-    if (stop == BT_STOP_QACC_SMOOTH) return false;
-    collide();
-    if (stop == BT_STOP_COLLISION) return false;
-    solve_constraints(Ma_warm);
+    const float h = m.timestep;
+    for (int phase = 0; phase < (do_euler ? 2 : 1); phase++) {
+      build_M(phase ? h : 0.f);
+      if (stop == BT_STOP_M) return false;
+      if (phase == 0) mul_M(warm(), qfrc_c());  // M * qacc_warmstart, consumed by the solver's warm-start test
+      factor();
+      if (stop == BT_STOP_FACTOR) return false;
+      invert();
+      for (int i = lane; i < m.nv; i += G) xv()[i] = qfrc_smooth()[i] + (phase ? qfrc_c()[i] : 0.f);
+      W::sync();
+      solve(xv());
+      if (phase == 0) {
+        for (int i = lane; i < m.nv; i += G) qacc_smooth()[i] = xv()[i];
+        W::sync();
+        if (stop == BT_STOP_QACC_SMOOTH) return false;
+        collide();
+        if (stop == BT_STOP_COLLISION) return false;
+        solve_constraints();
+      }
+    }
+    if (do_euler) integrate();
     return true;
   }
+  BT_DEV bool forward(int stop = BT_STOP_NONE) { return substep(false, stop); }
+  BT_DEV void step() { substep(true); }
 
-  // ================================================================== mjx.euler (implicit joint damping) + _advance
-  BT_DEV void euler() {
+  // mjx _advance with qacc = xv (the implicitly damped acceleration)
+  BT_DEV void integrate() {
     const float h = m.timestep;
-    build_M(h);
-    factor();
-    for (int i = lane; i < m.nv; i += G) xv()[i] = qfrc_smooth()[i] + qfrc_c()[i];
-    W::sync();
-    solve(xv());
     for (int u = lane; u < m.na; u += G) act()[u] += h * actdot()[u];
     for (int i = lane; i < m.nv; i += G) {
       const float v = qvel()[i] + h * xv()[i];
@@ -1123,11 +1149,6 @@ struct BtEnv {
       q[3] = q2[0]; q[4] = q2[1]; q[5] = q2[2]; q[6] = q2[3];
     }
     W::sync();
-  }
-
-  BT_DEV void step() {
-    forward();
-    euler();
   }
 
   // ================================================================== state I/O ([n_envs, dim] rows, coalesced per env)

@@ -4,9 +4,11 @@
 
 #ifdef __CUDACC__
 #define BT_DEV __device__ __forceinline__
+#define BT_NOINLINE __device__ __noinline__
 #define BT_LDG(p) __ldg(p)
 #else
 #define BT_DEV inline
+#define BT_NOINLINE inline
 #define BT_LDG(p) (*(p))
 #endif
 
@@ -99,6 +101,17 @@ BT_DEV float bt_nan_to_num(float x) {
   if (x > 3.4028234664e38f) return 3.4028234664e38f;
   if (x < -3.4028234664e38f) return -3.4028234664e38f;
   return x;
+}
+
+// solimp sigmoid for power != 2 (mj_makeImpedance); out of line: powf is ~500 instructions when inlined
+#ifdef __CUDACC__
+static __device__ __noinline__ float bt_impedance_pow(float x, float mid, float power) {
+#else
+static inline float bt_impedance_pow(float x, float mid, float power) {
+#endif
+  const float ia = (1.f / powf(mid, power - 1.f)) * powf(x, power);
+  const float ib = 1.f - (1.f / powf(1.f - mid, power - 1.f)) * powf(1.f - x, power);
+  return x < mid ? ia : ib;
 }
 
 // ---- JAX threefry2x32 ----

@@ -123,6 +123,8 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
             dof_margin[i] = a["jnt_margin"][j]
     t["dof_bodyid"] = _i(a["dof_bodyid"]); t["dof_parentid"] = _i(a["dof_parentid"])
     t["dof_Madr"] = _i(a["dof_Madr"]); t["dof_depth"] = _i(a["dof_depth"]); t["dof_subtreenum"] = _i(a["dof_subtreenum"])
+    t["dof_md"] = _i(a["dof_Madr"].astype(np.int64) | (a["dof_depth"].astype(np.int64) << 16))  # packed (Madr, depth)
+    assert m.nM < 65536
     t["dof_qposadr"] = dof_qadr; t["dof_limited"] = dof_lim
     t["dof_stiffness"] = _f(dof_stiff); t["dof_springref"] = _f(dof_spring)
     t["dof_armature"] = _f(a["dof_armature"]); t["dof_damping"] = _f(a["dof_damping"])
@@ -138,11 +140,22 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
             j = a["dof_parentid"][j]
     t["M_row"] = M_row; t["M_col"] = M_col
     t["M_colMadr"] = _i(a["dof_Madr"][M_col])
-    # triangular decode table t -> (a, b), 1 <= a <= b, ordered by b (valid prefix for every depth)
+    # work list of the in-place inversion L -> L^-1: entries (i, a >= 1) grouped by dof depth (ascending), rows in dof
+    # order, descending a inside a row (csrc/bt_impl.h::invert)
     dmax = int(a["dof_depth"].max()) if nv else 0
+    inv_adr, inv_item = [0], []
+    for d in range(1, dmax + 1):
+        for i in range(nv):
+            if a["dof_depth"][i] == d:
+                inv_item.extend([i | (aa << 8) for aa in range(d, 0, -1)])
+        inv_adr.append(len(inv_item))
+    # triangular decode table t -> (a, b), 1 <= a <= b, ordered by b (a valid prefix for every row depth)
     tri = [(aa, bb) for bb in range(1, dmax + 1) for aa in range(1, bb + 1)]
-    S("ntri", len(tri))
     t["tri_ab"] = _i([aa | (bb << 8) for aa, bb in tri]) if tri else np.zeros(1, np.int32)
+    S("nlevd", dmax)
+    t["inv_adr"] = _i(inv_adr)
+    t["inv_item"] = _i(inv_item) if inv_item else np.zeros(1, np.int32)
+    assert nv < 256 and dmax < 256
 
     def chain(body):
         out, d = [], a["body_lastdof"][body]
@@ -339,10 +352,10 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
     # LD doubles as cvel/cacc storage during the forward tree pass
     R("LD", max(m.nM, 12 * nbody)); R("Dinv", nv)
     # T region: cfrc (forward/backward pass) -> buf (M assembly) -> contact geometry + wrenches (solver)
-    R("T", max(6 * nbody, 6 * nv, 12 * ncon + 6 * ncon + 6 * max(ncb, 1)))
+    R("T", max(6 * nbody, 6 * nv, 18 * ncon + 6 * max(ncb, 1)))
     R("ref", 3 * max(len(roots), 1))
     R("aforce", max(nu, 1)); R("actdot", max(na, 1))
-    for v in ("qfrc_smooth", "qacc_smooth", "qacc", "x", "search", "qfrc_c"):
+    for v in ("qfrc_smooth", "qacc_smooth", "qacc", "x", "search", "qfrc_c", "tmpv"):
         R(v, nv)
     for k, v in lay.items():
         S("o_" + k, v)
