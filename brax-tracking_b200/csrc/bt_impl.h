@@ -377,11 +377,12 @@ struct BtEnv {
     float* ld = LD();
     for (int k = m.nv - 1; k >= 0; k--) {
       const int md = BT_LDG(m.dof_md + k), ad = md & 0xffff, d = md >> 16;
-      const float inv = 1.0f / ld[ad];
+      const float inv = bt_rcp(ld[ad]);
       if (lane == 0) Dinv()[k] = inv;
       if (d == 0) continue;
       // the d (d + 1) / 2 updates (a <= b) of this row are independent: flat triangular enumeration over the lanes
       const int nt = d * (d + 1) / 2;
+#pragma unroll 2
       for (int t = lane; t < nt; t += G) {
         const int ab = BT_LDG(m.tri_ab + t), a = ab & 255, b = ab >> 8;
         const int ia = BT_LDG(m.M_colMadr + ad + a);
@@ -409,6 +410,7 @@ struct BtEnv {
           const int ad = BT_LDG(m.dof_Madr + i);
           const float di = Dinv()[i];
           float acc = ld[ad + a];
+#pragma unroll 4
           for (int c = 1; c < a; c++) acc += ld[ad + c] * ld[BT_LDG(m.M_colMadr + ad + c) + a - c];
           val = -acc * di;
           dst = ad + a;
@@ -428,6 +430,7 @@ struct BtEnv {
     for (int j = lane; j < m.nv; j += G) {
       const int nd = BT_LDG(m.dof_subtreenum + j), dj = BT_LDG(m.dof_md + j) >> 16;
       float acc = x[j];
+#pragma unroll 4
       for (int i2 = j + 1; i2 < j + nd; i2++) {
         const int md = BT_LDG(m.dof_md + i2);
         acc += ld[(md & 0xffff) + (md >> 16) - dj] * x[i2];
@@ -438,6 +441,7 @@ struct BtEnv {
     for (int i = lane; i < m.nv; i += G) {
       const int md = BT_LDG(m.dof_md + i), ad = md & 0xffff, d = md >> 16;
       float acc = y[i];
+#pragma unroll 4
       for (int a = 1; a <= d; a++) acc += ld[ad + a] * y[BT_LDG(m.M_col + ad + a)];
       x[i] = acc;
     }
@@ -576,6 +580,7 @@ struct BtEnv {
     for (int it = lane; it < nitem; it += G) {
       const int cb = it / 6, k = it - cb * 6;
       float acc = 0.f;
+#pragma unroll 4
       for (int e = BT_LDG(m.cb_adr + cb); e < BT_LDG(m.cb_adr + cb + 1); e++) {
         const int d = BT_LDG(m.cb_dof + e);
         acc += cdof()[6 * d + k] * v[d];

@@ -94,6 +94,13 @@ BT_DEV void bt_motion_cross_force(const float* v, const float* f, float* o) {
 BT_DEV float bt_dot6(const float* a, const float* b) {
   return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
 }
+BT_DEV float bt_rcp(float x) {
+#ifdef __CUDACC__
+  return __frcp_rn(x);
+#else
+  return 1.0f / x;
+#endif
+}
 BT_DEV float bt_clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
 // jnp.nan_to_num (fruitfly.py:569-570)
 BT_DEV float bt_nan_to_num(float x) {

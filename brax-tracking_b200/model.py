@@ -354,9 +354,12 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
     # T region: cfrc (forward/backward pass) -> buf (M assembly) -> contact geometry + wrenches (solver)
     R("T", max(6 * nbody, 6 * nv, 18 * ncon + 6 * max(ncb, 1)))
     R("ref", 3 * max(len(roots), 1))
-    R("aforce", max(nu, 1)); R("actdot", max(na, 1))
-    for v in ("qfrc_smooth", "qacc_smooth", "qacc", "x", "search", "qfrc_c", "tmpv"):
+    R("actdot", max(na, 1))
+    for v in ("qfrc_smooth", "qacc_smooth", "qacc", "search", "qfrc_c"):
         R(v, nv)
+    R("x", max(nv, nu))
+    lay["aforce"] = lay["x"]            # actuator forces live only inside smooth_forces()
+    lay["tmpv"] = lay["qacc_smooth"]    # solve() temp: qacc_smooth is consumed (into registers) before the first CG solve
     for k, v in lay.items():
         S("o_" + k, v)
     off = max(off, lay["crb"] + obs_size)  # the observation row is staged over crb/LD/T at the end of the step
