@@ -13,11 +13,13 @@ ENV_ARGS = dict(rodent=configs.RODENT_ENV_ARGS, fly_free=configs.FLY_FREEJNT_ENV
 
 
 @functools.lru_cache(maxsize=None)
-def setup(name: str):
-    """-> (mjcf.Model, cfg, clip dict, packed tables)"""
+def setup(name: str, episode_length: int = None):
+    """-> (mjcf.Model, cfg, clip dict, packed tables); `episode_length` overrides main.py:86 (tests of the truncation path)"""
     m = assets.load_model(name)
     args = ENV_ARGS[name]
     cfg = configs.resolve(m, args)
+    if episode_length is not None:
+        cfg["episode_length"] = int(episode_length)
     clip = clips.synthetic_clip(m, args["free_jnt"], z_stand=default_z(name)).as_dict()
     return m, cfg, clip, model.pack(m, cfg, clip)
 
@@ -28,8 +30,8 @@ def default_z(name):
 
 
 @functools.lru_cache(maxsize=None)
-def oracles(name: str, dtype=np.float64):
-    m, cfg, clip, _ = setup(name)
+def oracles(name: str, dtype=np.float64, episode_length: int = None):
+    m, cfg, clip, _ = setup(name, episode_length)
     o = oracle.Oracle(m, dtype)
     return o, env_oracle.EnvOracle(o, clip, cfg, dtype=np.float32)
 

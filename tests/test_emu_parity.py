@@ -7,6 +7,10 @@ import common
 import parity_cases as pc
 from backends import EmuBackend
 
+# the fly never terminates within a short test (tethered: it cannot fall); a short episode forces the truncation /
+# auto-reset path instead
+FLY_EPISODE = 12
+
 
 @pytest.fixture(scope="module")
 def rodent_emu():
@@ -28,3 +32,15 @@ def test_teacher_forced_wrapped_step(rodent_emu):
 
 def test_physics_1_10_100(rodent_emu):
     pc.check_physics_1_10_100(rodent_emu, "rodent", N=4)
+
+
+@pytest.mark.parametrize("name", ["fly_free", "fly_tethered"])
+def test_fly_elliptic_cone(name):
+    """configs[2]: fruit-fly imitation env (elliptic cones, fluid forces, claw-claw capsule contacts)."""
+    b = EmuBackend(common.setup(name)[3])
+    pc.check_forward_intermediates(b, name, N=4)
+    pc.check_reset(b, name, N=8)
+    pc.check_physics_1_10_100(b, name, N=4)
+    bt = EmuBackend(common.setup(name, FLY_EPISODE)[3])
+    r = pc.check_teacher_forced(bt, name, N=8, T=30, episode_length=FLY_EPISODE)
+    assert r["n_done"] > 0

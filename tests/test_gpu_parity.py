@@ -30,6 +30,25 @@ def test_physics_1_10_100(rodent_cuda):
     print(pc.check_physics_1_10_100(rodent_cuda, "rodent", N=8))
 
 
+@pytest.mark.parametrize("name", ["fly_free", "fly_tethered"])
+def test_fly_elliptic_cone(name):
+    """configs[2]: fruit-fly imitation env, 8192-env kernel variant (2 dof slots, 1 contact slot per lane)."""
+    from backends import CudaBackend
+    b = CudaBackend(common.setup(name)[3])
+    pc.check_forward_intermediates(b, name, N=16)
+    pc.check_reset(b, name, N=64)
+    pc.check_physics_1_10_100(b, name, N=8)
+    bt = CudaBackend(common.setup(name, 12)[3])
+    print(pc.check_teacher_forced(bt, name, N=16, T=40, episode_length=12))
+
+
+@pytest.mark.parametrize("name", ["rodent", "fly_free", "fly_tethered"])
+def test_cuda_matches_golden(name):
+    from backends import CudaBackend
+    from test_golden import run_against_golden
+    run_against_golden(CudaBackend, name)
+
+
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()
