@@ -282,6 +282,7 @@ struct BtEnv {
         const int c0 = BT_LDG(m.child_adr + b), c1 = BT_LDG(m.child_adr + b + 1);
         if (k < 10) {
           float acc = crb()[10 * b + k];
+#pragma unroll 2
           for (int c = c0; c < c1; c++) acc += crb()[10 * BT_LDG(m.child_id + c) + k];
           crb()[10 * b + k] = acc;
         } else {
@@ -362,8 +363,10 @@ struct BtEnv {
     for (int i = lane; i < m.nv; i += G) {
       const int ad = BT_LDG(m.dof_Madr + i), d = BT_LDG(m.dof_depth + i);
       float acc = 0.f;
+#pragma unroll 4
       for (int a = 0; a <= d; a++) acc += LD()[ad + a] * v[BT_LDG(m.M_col + ad + a)];
       const int nd = BT_LDG(m.dof_subtreenum + i);
+#pragma unroll 4
       for (int i2 = i + 1; i2 < i + nd; i2++) acc += LD()[BT_LDG(m.dof_Madr + i2) + BT_LDG(m.dof_depth + i2) - d] * v[i2];
       y[i] = acc;
     }
@@ -382,7 +385,7 @@ struct BtEnv {
       if (d == 0) continue;
       // the d (d + 1) / 2 updates (a <= b) of this row are independent: flat triangular enumeration over the lanes
       const int nt = d * (d + 1) / 2;
-#pragma unroll 2
+#pragma unroll 4
       for (int t = lane; t < nt; t += G) {
         const int ab = BT_LDG(m.tri_ab + t), a = ab & 255, b = ab >> 8;
         const int ia = BT_LDG(m.M_colMadr + ad + a);
@@ -797,6 +800,7 @@ struct BtEnv {
       float acc = 0.f;
       if (i < m.nv) {
         acc = e.lsg[sl] * lforce[sl];
+#pragma unroll 2
         for (int k = BT_LDG(m.dofcon_adr + i); k < BT_LDG(m.dofcon_adr + i + 1); k++)
           acc += BT_LDG(m.dofcon_sign + k) * bt_dot6(cdof() + 6 * i, wrench() + 6 * BT_LDG(m.dofcon_c + k));
         qfrc_c()[i] = acc;

@@ -1,0 +1,307 @@
+"""PPO rollout + learner loop around the fused step.
+
+Mirrors ``train()`` of /root/reference/custom_brax/custom_ppo.py:65-506 (a copy of Brax PPO that swaps in
+``custom_wrappers.wrap``) and the Brax pieces it calls: ``acting.generate_unroll``,
+``running_statistics``, ``NormalTanhDistribution``, ``compute_gae`` / ``compute_ppo_loss``, ``optax.adam``.
+Same argument names and meaning as the reference; differences that come with the platform:
+
+  * one process per GPU (torchrun) instead of ``jax.pmap``; the env shard of a rank is
+    ``split(key_env, num_envs)[rank * n : (rank + 1) * n]`` (custom_ppo.py:213-223);
+  * ``lax.pmean`` of the gradients (custom_ppo.py:246-248) = ONE NCCL all-reduce of a flat, pre-packed gradient buffer
+    per minibatch; the running-statistics sums (custom_ppo.py:323-327) are all-reduced once per training step;
+  * the policy / value MLPs run in PyTorch (cuBLAS) -- the north star keeps them out of the hand-written kernels.
+"""
+from __future__ import annotations
+
+import math
+import time
+from dataclasses import dataclass
+from typing import Callable, Dict, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import envs as envs_mod, parallel, prng
+
+
+# ---------------------------------------------------------------------------------------------- networks
+class MLP(nn.Module):
+    """brax.training.networks.MLP: swish activations, LeCun-uniform kernels, zero biases, linear output layer."""
+
+    def __init__(self, sizes: Sequence[int]):
+        super().__init__()
+        self.layers = nn.ModuleList([nn.Linear(a, b) for a, b in zip(sizes[:-1], sizes[1:])])
+        for l in self.layers:
+            bound = math.sqrt(3.0 / l.in_features)
+            nn.init.uniform_(l.weight, -bound, bound)
+            nn.init.zeros_(l.bias)
+
+    def forward(self, x):
+        for i, l in enumerate(self.layers):
+            x = l(x)
+            if i + 1 < len(self.layers):
+                x = F.silu(x)
+        return x
+
+
+class RunningStatistics:
+    """brax.training.acme.running_statistics: count / mean / summed_variance / std (clipped to [1e-6, 1e6])."""
+
+    def __init__(self, size: int, device):
+        self.count = torch.zeros((), dtype=torch.float64, device=device)
+        self.mean = torch.zeros(size, dtype=torch.float32, device=device)
+        self.summed_variance = torch.zeros(size, dtype=torch.float32, device=device)
+        self.std = torch.ones(size, dtype=torch.float32, device=device)
+
+    def update(self, batch: torch.Tensor, world: int = 1):
+        """Parallel (Chan) update with the batch of every rank (pmap_axis_name='i' in the reference)."""
+        b = batch.reshape(-1, batch.shape[-1]).to(torch.float32)
+        n = torch.tensor(float(b.shape[0]), dtype=torch.float64, device=b.device)
+        if world > 1:
+            dist.all_reduce(n)
+        new_count = self.count + n
+        diff = b - self.mean
+        upd = diff.sum(0)
+        if world > 1:
+            dist.all_reduce(upd)
+        mean = self.mean + (upd / new_count).to(torch.float32)
+        var_upd = (diff * (b - mean)).sum(0)
+        if world > 1:
+            dist.all_reduce(var_upd)
+        self.summed_variance = self.summed_variance + var_upd
+        self.mean, self.count = mean, new_count
+        self.std = torch.sqrt(torch.clamp(self.summed_variance / new_count.to(torch.float32), min=0.0)).clamp(1e-6, 1e6)
+
+    def normalize(self, x):
+        return (x - self.mean) / self.std
+
+    def state_dict(self):
+        return dict(count=self.count, mean=self.mean, summed_variance=self.summed_variance, std=self.std)
+
+    def load_state_dict(self, d):
+        self.count, self.mean, self.summed_variance, self.std = d["count"], d["mean"], d["summed_variance"], d["std"]
+
+
+class NormalTanh:
+    """brax NormalTanhDistribution (min_std = 0.001): logits -> (loc, softplus(scale) + min_std), tanh bijector."""
+    MIN_STD = 0.001
+
+    @staticmethod
+    def params(logits):
+        loc, scale = torch.chunk(logits, 2, dim=-1)
+        return loc, F.softplus(scale) + NormalTanh.MIN_STD
+
+    @staticmethod
+    def log_det_jac(x):
+        return 2.0 * (math.log(2.0) - x - F.softplus(-2.0 * x))
+
+    @staticmethod
+    def sample_raw(logits, noise):
+        loc, scale = NormalTanh.params(logits)
+        return loc + scale * noise
+
+    @staticmethod
+    def log_prob(logits, raw):
+        loc, scale = NormalTanh.params(logits)
+        lp = -0.5 * ((raw - loc) / scale) ** 2 - torch.log(scale) - 0.5 * math.log(2.0 * math.pi)
+        return (lp - NormalTanh.log_det_jac(raw)).sum(-1)
+
+    @staticmethod
+    def entropy(logits, noise):
+        loc, scale = NormalTanh.params(logits)
+        ent = 0.5 + 0.5 * math.log(2.0 * math.pi) + torch.log(scale)
+        return (ent + NormalTanh.log_det_jac(loc + scale * noise)).sum(-1)
+
+
+# ---------------------------------------------------------------------------------------------- losses
+def compute_gae(truncation, termination, rewards, values, bootstrap_value, lambda_: float, discount: float):
+    """brax.training.agents.ppo.losses.compute_gae; time-major [T, B]."""
+    trunc_mask = 1.0 - truncation
+    values_tp1 = torch.cat([values[1:], bootstrap_value[None]], 0)
+    deltas = (rewards + discount * (1.0 - termination) * values_tp1 - values) * trunc_mask
+    acc = torch.zeros_like(bootstrap_value)
+    out = []
+    for t in range(values.shape[0] - 1, -1, -1):
+        acc = deltas[t] + discount * (1.0 - termination[t]) * trunc_mask[t] * lambda_ * acc
+        out.append(acc)
+    vs = torch.stack(out[::-1], 0) + values
+    vs_tp1 = torch.cat([vs[1:], bootstrap_value[None]], 0)
+    adv = (rewards + discount * (1.0 - termination) * vs_tp1 - values) * trunc_mask
+    return vs.detach(), adv.detach()
+
+
+def compute_ppo_loss(policy, value, normalizer, data: Dict[str, torch.Tensor], noise, entropy_cost=1e-4, discounting=0.9,
+                     reward_scaling=1.0, gae_lambda=0.95, clipping_epsilon=0.3, normalize_advantage=True):
+    """brax compute_ppo_loss; ``data`` is batch-major [B, T, ...] as stored by the rollout."""
+    tm = {k: v.transpose(0, 1) for k, v in data.items()}  # time first
+    obs = normalizer(tm["observation"])
+    logits = policy(obs)
+    baseline = value(obs).squeeze(-1)
+    bootstrap = value(normalizer(tm["next_observation"][-1])).squeeze(-1)
+    rewards = tm["reward"] * reward_scaling
+    truncation = tm["truncation"]
+    termination = (1.0 - tm["discount"]) * (1.0 - truncation)
+    target_lp = NormalTanh.log_prob(logits, tm["raw_action"])
+    vs, adv = compute_gae(truncation, termination, rewards, baseline, bootstrap, gae_lambda, discounting)
+    if normalize_advantage:
+        adv = (adv - adv.mean()) / (adv.std(unbiased=False) + 1e-8)
+    rho = torch.exp(target_lp - tm["log_prob"])
+    policy_loss = -torch.minimum(rho * adv, rho.clamp(1 - clipping_epsilon, 1 + clipping_epsilon) * adv).mean()
+    v_err = vs - baseline
+    v_loss = (v_err * v_err).mean() * 0.5 * 0.5
+    entropy = NormalTanh.entropy(logits, noise).mean()
+    total = policy_loss + v_loss - entropy_cost * entropy
+    return total, dict(total_loss=total.detach(), policy_loss=policy_loss.detach(), v_loss=v_loss.detach(), entropy_loss=(-entropy_cost * entropy).detach())
+
+
+# ---------------------------------------------------------------------------------------------- training
+@dataclass
+class TrainingState:
+    """custom_ppo.py:41-48"""
+    policy: MLP
+    value: MLP
+    optimizer: torch.optim.Optimizer
+    normalizer: RunningStatistics
+    env_steps: int = 0
+
+
+def _flat_allreduce_mean(params, world):
+    """lax.pmean(grads, 'i'): one NCCL all-reduce on a flat buffer."""
+    grads = [p.grad for p in params]
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat)
+    flat /= world
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+
+
+def train(environment, num_timesteps: int, episode_length: int, action_repeat: int = 1, num_envs: int = 1,
+          learning_rate: float = 1e-4, entropy_cost: float = 1e-4, discounting: float = 0.9, seed: int = 0, unroll_length: int = 10,
+          batch_size: int = 32, num_minibatches: int = 16, num_updates_per_batch: int = 2, num_evals: int = 1,
+          normalize_observations: bool = False, reward_scaling: float = 1.0, clipping_epsilon: float = 0.3, gae_lambda: float = 0.95,
+          policy_hidden_layer_sizes: Sequence[int] = (256, 256), value_hidden_layer_sizes: Sequence[int] = (256, 256),
+          progress_fn: Callable[[int, Dict], None] = lambda *a: None, normalize_advantage: bool = True,
+          policy_params_fn: Callable[..., None] = lambda *a: None, restore_checkpoint_path: Optional[str] = None):
+    """PPO training on the fused B200 step.  Returns (make_policy, params, metrics) like the reference."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    assert batch_size * num_minibatches % num_envs == 0                      # custom_ppo.py:152
+    assert num_envs % world == 0                                             # custom_ppo.py:199
+    env_step_per_training_step = batch_size * unroll_length * num_minibatches * action_repeat
+    num_evals_after_init = max(num_evals - 1, 1)
+    num_training_steps_per_epoch = int(np.ceil(num_timesteps / (num_evals_after_init * env_step_per_training_step)))
+
+    env = envs_mod.wrap(environment, episode_length=episode_length, action_repeat=action_repeat)
+    device = environment._native._dev()
+    n_local = num_envs // world
+    # keys: PRNGKey(seed) -> (global, local); local -> (local, key_env, eval_key)   (custom_ppo.py:189-196)
+    key = prng.PRNGKey(seed)
+    global_key, local_key = prng.split(key, 2)
+    _, key_env, _ = prng.split(local_key, 3)
+    state = env.reset(parallel.shard_keys(key_env, num_envs, rank, world))
+    gen = torch.Generator(device=device)
+    gen.manual_seed(int(global_key[1]) + 7919 * rank)
+
+    obs_size, nu = env.observation_size, env.action_size
+    torch.manual_seed(int(global_key[0]) % (2 ** 31))                        # networks identical on every rank
+    policy = MLP([obs_size, *policy_hidden_layer_sizes, 2 * nu]).to(device)
+    value = MLP([obs_size, *value_hidden_layer_sizes, 1]).to(device)
+    params = list(policy.parameters()) + list(value.parameters())
+    opt = torch.optim.Adam(params, lr=learning_rate, eps=1e-8)
+    ts = TrainingState(policy, value, opt, RunningStatistics(obs_size, device))
+    if restore_checkpoint_path is not None:
+        load_checkpoint(ts, restore_checkpoint_path)
+    norm = ts.normalizer.normalize if normalize_observations else (lambda x: x)
+
+    def make_policy(deterministic: bool = False):
+        def act(obs):
+            with torch.no_grad():
+                logits = policy(norm(obs))
+                loc, scale = NormalTanh.params(logits)
+                raw = loc if deterministic else loc + scale * torch.randn(loc.shape, device=loc.device, generator=gen)
+                return torch.tanh(raw), raw, logits
+        return act
+
+    n_unrolls = batch_size * num_minibatches // num_envs
+    T = unroll_length
+    buf = dict(observation=torch.empty(n_unrolls, T, n_local, obs_size, device=device),
+               next_observation=torch.empty(n_unrolls, T, n_local, obs_size, device=device),
+               raw_action=torch.empty(n_unrolls, T, n_local, nu, device=device),
+               log_prob=torch.empty(n_unrolls, T, n_local, device=device), reward=torch.empty(n_unrolls, T, n_local, device=device),
+               discount=torch.empty(n_unrolls, T, n_local, device=device), truncation=torch.empty(n_unrolls, T, n_local, device=device))
+    metrics: Dict[str, float] = {}
+    t_start = time.time()
+    for it in range(num_evals_after_init):
+        t0 = time.time()
+        ep_reward = 0.0
+        for _ in range(num_training_steps_per_epoch):
+            # ---- rollout: acting.generate_unroll x n_unrolls (custom_ppo.py:296-314)
+            act = make_policy()
+            for u in range(n_unrolls):
+                for t in range(T):
+                    buf["observation"][u, t].copy_(state.obs)
+                    action, raw, logits = act(state.obs)
+                    buf["raw_action"][u, t].copy_(raw)
+                    buf["log_prob"][u, t].copy_(NormalTanh.log_prob(logits, raw))
+                    state = env.step(state, action.contiguous())
+                    buf["next_observation"][u, t].copy_(state.obs)
+                    buf["reward"][u, t].copy_(state.reward)
+                    buf["discount"][u, t].copy_(1.0 - state.done)
+                    buf["truncation"][u, t].copy_(state.info["truncation"])
+            ep_reward = float(buf["reward"].mean())
+            # [n_unrolls, T, n, ...] -> [n_unrolls * n, T, ...]  (custom_ppo.py:316-320)
+            data = {k: v.transpose(1, 2).reshape(n_unrolls * n_local, T, *v.shape[3:]) for k, v in buf.items()}
+            if normalize_observations:
+                ts.normalizer.update(data["observation"], world)             # custom_ppo.py:323-327
+            # ---- SGD: num_updates_per_batch x num_minibatches (custom_ppo.py:250-284,329-334)
+            B = data["reward"].shape[0]
+            for _ in range(num_updates_per_batch):
+                perm = torch.randperm(B, device=device, generator=gen)
+                for mb in perm.reshape(num_minibatches, -1):
+                    mbd = {k: v[mb] for k, v in data.items()}
+                    noise = torch.randn(T, mb.shape[0], nu, device=device, generator=gen)
+                    loss, lm = compute_ppo_loss(policy, value, norm, mbd, noise, entropy_cost, discounting, reward_scaling, gae_lambda,
+                                                clipping_epsilon, normalize_advantage)
+                    opt.zero_grad(set_to_none=False)
+                    loss.backward()
+                    if world > 1:
+                        _flat_allreduce_mean(params, world)                  # lax.pmean(grads, 'i')
+                    opt.step()
+            ts.env_steps += env_step_per_training_step
+        torch.cuda.synchronize(device)
+        dt = time.time() - t0
+        sps = num_training_steps_per_epoch * env_step_per_training_step / dt  # custom_ppo.py:373-377
+        metrics = {"training/sps": sps, "training/walltime": time.time() - t_start, "training/mean_step_reward": ep_reward,
+                   **{f"training/{k}": float(v) for k, v in lm.items()}}
+        if rank == 0:
+            progress_fn(ts.env_steps, metrics)
+            policy_params_fn(ts.env_steps, make_policy, (ts.normalizer.state_dict(), policy.state_dict()))
+    return make_policy, (ts.normalizer.state_dict(), policy.state_dict()), metrics
+
+
+# ---------------------------------------------------------------------------------------------- checkpoints
+def save_checkpoint(ts: TrainingState, path: str, env_state=None) -> None:
+    """Symmetric save/restore of (normalizer, policy, value, optimizer, env_steps[, env state]) -- the reference saves only
+    (normalizer, policy) and restores through a different format."""
+    blob = dict(normalizer=ts.normalizer.state_dict(), policy=ts.policy.state_dict(), value=ts.value.state_dict(),
+                optimizer=ts.optimizer.state_dict(), env_steps=ts.env_steps)
+    if env_state is not None:
+        blob["env_state"] = {k: v.clone() for k, v in env_state.pipeline_state.items()}
+        blob["env_raw"] = {k: (v.clone() if torch.is_tensor(v) else {kk: vv.clone() for kk, vv in v.items()}) for k, v in env_state._raw.items()}
+    torch.save(blob, path)
+
+
+def load_checkpoint(ts: TrainingState, path: str) -> dict:
+    blob = torch.load(path, map_location=ts.normalizer.mean.device, weights_only=False)
+    ts.normalizer.load_state_dict(blob["normalizer"])
+    ts.policy.load_state_dict(blob["policy"])
+    ts.value.load_state_dict(blob["value"])
+    ts.optimizer.load_state_dict(blob["optimizer"])
+    ts.env_steps = int(blob["env_steps"])
+    return blob

