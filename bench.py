@@ -29,12 +29,20 @@ import numpy as np  # noqa: E402
 
 METRIC = "rodent-imitation env-steps/sec at 8192 envs per GPU"
 UNIT = "env-steps/s"
-# algorithmic HBM bytes per env-step (SURVEY.md section 8d / BASELINE.md section 2)
-ALGO_BYTES = dict(rodent=4776, fly_free=6472, fly_tethered=6128)
+# algorithmic HBM bytes per env-step (SURVEY.md section 8d / BASELINE.md section 2):
+#   read  qpos + qvel + act + qacc_warmstart + time + action + 2 ints
+#   write qpos + qvel + act + qacc_warmstart + time + obs + reward, done + 12 metrics + 3 info floats + 2 info ints
+ALGO_BYTES = dict(rodent=4776, fly_free=6472, fly_tethered=6128, rodent_pair=7580)
+MODEL_XML = dict(rodent="rodent", fly_free="fruitfly_force_fast (free root)", fly_tethered="fruitfly_force_fast (tethered)",
+                 rodent_pair="2 x rodent in one world")
+
+
+def algo_bytes(nq, nv, na, nu, obs):
+    return 4 * ((nq + 2 * nv + na + 1 + nu + 2) + (nq + 2 * nv + na + 1 + obs + 2 + 12 + 3 + 2))
 
 
 def workload_name(model, envs):
-    return f"{model}.xml imitation rollout, {envs} envs/GPU, n_frames=5 substeps, CG 4x4, step-only"
+    return f"{MODEL_XML[model]}.xml imitation rollout, {envs} envs/GPU, n_frames=5 substeps, CG 4x4, step-only"
 
 
 class ClockSampler(threading.Thread):
@@ -142,8 +150,7 @@ def run_reference(args):
 def run_gpu(args):
     import torch
     import torch.distributed as dist
-    import common
-    from brax_tracking_b200 import envs, native
+    from brax_tracking_b200 import envs, native, parallel, presets, prng
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -153,11 +160,12 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n, K, Wm = args.envs, args.steps, args.warmup
-    m, cfg, clip, _ = common.setup(args.model)
-    make = dict(rodent=envs.RodentSingleClip, fly_free=envs.Fruitfly_Tethered_Free, fly_tethered=envs.Fruitfly_Tethered)[args.model]
-    env = envs.wrap(make(clip, mj_model=m, device=local), episode_length=cfg["episode_length"])
+    base = presets.make_env(args.model, device=local)
+    m = base.sys
+    env = envs.wrap(base, episode_length=base.episode_length)
+    assert algo_bytes(m.nq, m.nv, m.na, m.nu, env.observation_size) == ALGO_BYTES[args.model]
     # per-rank env shard: keys = split(PRNGKey(0), world*n)[rank*n:(rank+1)*n]  (custom_ppo.py:220-223)
-    keys = common.jax_keys(world * n)[rank * n:(rank + 1) * n]
+    keys = parallel.shard_keys(prng.PRNGKey(0), world * n, rank, world)
     state = env.reset(keys)
     rng = np.random.default_rng(1 + rank)
     n_act = 8

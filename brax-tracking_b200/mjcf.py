@@ -385,9 +385,41 @@ def _expand_replicate(elem: ET.Element):
                 break
 
 
+def _duplicate_animal(root: ET.Element, count: int, offset) -> None:
+    """Stress-model helper (variant ii): `count` copies of every top-level moving body of the
+    worldbody in ONE world, names suffixed `-k`, copy k translated by k * offset; excludes / tendons / actuators are
+    duplicated with the suffixed references.  Copy 0 keeps the original names (so the env's name lists still resolve)."""
+    wb = root.find("worldbody")
+    tops = [b for b in wb if b.tag == "body"]
+
+    def suffixed(elem, k, attrs=("name", "joint", "tendon", "body1", "body2", "joint1", "joint2", "site", "objname")):
+        c = copy.deepcopy(elem)
+        for e in c.iter():
+            for a in attrs:
+                if e.get(a) is not None:
+                    e.set(a, f"{e.get(a)}-{k}")
+        return c
+
+    for k in range(1, count):
+        for b in tops:
+            c = suffixed(b, k)
+            pos = _vec(c.get("pos"), default=[0, 0, 0]) + np.asarray(offset, dtype=np.float64) * k
+            c.set("pos", " ".join(repr(float(x)) for x in pos))
+            wb.append(c)
+        for sec in ("contact", "tendon", "actuator"):
+            node = root.find(sec)
+            if node is not None:
+                for e in list(node):
+                    node.append(suffixed(e, k))
+    sens = root.find("sensor")
+    if sens is not None:
+        root.remove(sens)
+
+
 def compile_mjcf(
     path: str,
     scale_factor: Optional[float] = None,
+    duplicate: Optional[tuple] = None,
     delete_free_joint_of: Optional[str] = None,
     overrides: Optional[dict] = None,
     missing_mesh: str = "error",
@@ -409,6 +441,8 @@ def compile_mjcf(
     _expand_replicate(root)
     if scale_factor is not None:
         _rescale_subtree(root, scale_factor, scale_factor)
+    if duplicate is not None:
+        _duplicate_animal(root, int(duplicate[0]), duplicate[1])
 
     comp = {}
     for c in root.findall("compiler"):

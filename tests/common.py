@@ -7,26 +7,19 @@ import numpy as np
 
 import env_oracle
 import oracle
-from brax_tracking_b200 import assets, clips, configs, model
+from brax_tracking_b200 import configs, model, presets
 
-ENV_ARGS = dict(rodent=configs.RODENT_ENV_ARGS, fly_free=configs.FLY_FREEJNT_ENV_ARGS, fly_tethered=configs.FLY_ENV_ARGS)
+ENV_ARGS = presets.ENV_ARGS
 
 
 @functools.lru_cache(maxsize=None)
 def setup(name: str, episode_length: int = None):
     """-> (mjcf.Model, cfg, clip dict, packed tables); `episode_length` overrides main.py:86 (tests of the truncation path)"""
-    m = assets.load_model(name)
-    args = ENV_ARGS[name]
+    m, args, clip = presets.load(name)
     cfg = configs.resolve(m, args)
     if episode_length is not None:
         cfg["episode_length"] = int(episode_length)
-    clip = clips.synthetic_clip(m, args["free_jnt"], z_stand=default_z(name)).as_dict()
     return m, cfg, clip, model.pack(m, cfg, clip)
-
-
-def default_z(name):
-    # standing height of the synthetic clip's root (the models' qpos0 root height)
-    return None
 
 
 @functools.lru_cache(maxsize=None)

@@ -44,3 +44,15 @@ def test_fly_elliptic_cone(name):
     bt = EmuBackend(common.setup(name, FLY_EPISODE)[3])
     r = pc.check_teacher_forced(bt, name, N=8, T=30, episode_length=FLY_EPISODE)
     assert r["n_done"] > 0
+
+
+def test_two_rodent_stress_model():
+    """configs[3]: two rodents in one world (nv 146, 60 floor contacts, two kinematic trees); SURVEY Appendix C.3 (ii)."""
+    name = "rodent_pair"
+    b = EmuBackend(common.setup(name)[3])
+    pc.check_forward_intermediates(b, name, N=2)
+    pc.check_reset(b, name, N=4)
+    pc.check_physics_1_10_100(b, name, N=2)
+    bt = EmuBackend(common.setup(name, FLY_EPISODE)[3])
+    r = pc.check_teacher_forced(bt, name, N=4, T=20, episode_length=FLY_EPISODE)
+    assert r["n_done"] > 0

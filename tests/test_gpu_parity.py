@@ -1,4 +1,5 @@
 """GPU parity tests proper: the sm_100a kernels, called through the C ABI, against the oracle on identical inputs."""
+import numpy as np
 import pytest
 
 import common
@@ -47,6 +48,18 @@ def test_cuda_matches_golden(name):
     from backends import CudaBackend
     from test_golden import run_against_golden
     run_against_golden(CudaBackend, name)
+
+
+def test_two_rodent_stress_model():
+    """configs[3]: 4096-env kernel variant (5 dof slots, 4 contact slots per lane)."""
+    from backends import CudaBackend
+    name = "rodent_pair"
+    b = CudaBackend(common.setup(name)[3])
+    pc.check_forward_intermediates(b, name, N=8)
+    pc.check_reset(b, name, N=32)
+    pc.check_physics_1_10_100(b, name, N=4)
+    bt = CudaBackend(common.setup(name, 12)[3])
+    print(pc.check_teacher_forced(bt, name, N=8, T=30, episode_length=12))
 
 
 def test_ppo_loop_runs_on_the_fused_step(tmp_path):

@@ -18,7 +18,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
-from brax_tracking_b200 import assets, clips, configs, envs, ppo  # noqa: E402
+from brax_tracking_b200 import ppo, presets  # noqa: E402
 
 
 def main():
@@ -39,10 +39,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    m = assets.load_model(a.model)
-    args = dict(rodent=configs.RODENT_ENV_ARGS, fly_free=configs.FLY_FREEJNT_ENV_ARGS, fly_tethered=configs.FLY_ENV_ARGS)[a.model]
-    clip = clips.synthetic_clip(m, args["free_jnt"])
-    env = envs.TrackingEnv(m, clip, args, device=local)
+    env = presets.make_env(a.model, device=local)
 
     def progress(step, metrics):
         print(json.dumps({"env_steps": step, **{k: round(v, 5) for k, v in metrics.items()}}), flush=True)
