@@ -166,12 +166,13 @@ static int check_state(const BtModel* m, const BtStatePtrs& s, bool need_xpos) {
   return 0;
 }
 
-int bt_reset(BtModel* m, int n_envs, const uint32_t* keys, BtStatePtrs state, float* obs, float* reward, float* done,
+int bt_reset(BtModel* m, int n_envs, const uint32_t* keys, int fixed_start_frame, BtStatePtrs state, float* obs, float* reward, float* done,
              float* metrics, float* info_f, int32_t* info_i, void* stream) {
   if (!m || n_envs < 0 || !keys || !obs || !reward || !done || !metrics || !info_f || !info_i) { snprintf(g_err, sizeof(g_err), "bad argument"); return BT_E_ARG; }
   if (check_state(m, state, true)) return BT_E_ARG;
   if (n_envs == 0) return BT_OK;
-  BtResetArgs a = {keys, state, obs, reward, done, metrics, info_f, info_i};
+  if (fixed_start_frame >= m->dev.clip_len) { snprintf(g_err, sizeof(g_err), "fixed_start_frame beyond the clip"); return BT_E_ARG; }
+  BtResetArgs a = {keys, fixed_start_frame, state, obs, reward, done, metrics, info_f, info_i};
   m->ops->reset(cfg_for(m, n_envs, stream), m->dev, n_envs, m->warps, a);
   BT_LAUNCHED();
   return BT_OK;

@@ -84,6 +84,7 @@ BT_DEV void bt_prog_step(const BtDev& m, float* s, int lane, int env, const BtSt
 
 struct BtResetArgs {
   const uint32_t* keys;  // [n, 2]
+  int fixed_start_frame; // < 0: training reset (fruitfly.py:449-495); >= 0: RenderRolloutWrapperTracking.reset (custom_wrappers.py:85-125)
   BtState state;
   float *obs, *reward, *done, *metrics, *info_f;
   int32_t* info_i;
@@ -95,10 +96,11 @@ BT_DEV void bt_prog_reset(const BtDev& m, float* s, int lane, int env, const BtR
   typedef BtLanes<G> W;
   BtEnv<G, DS, CS> E(m, s, lane);
   const unsigned k0 = a.keys[2 * (size_t)env], k1 = a.keys[2 * (size_t)env + 1];
-  // rng, rng1, rng2, rng_pos = split(rng, 4)
+  // training: rng, rng1, rng2, rng_pos = split(rng, 4);  render rollout: rng, rng1, rng2 = split(rng, 3)
+  const int nsplit = a.fixed_start_frame < 0 ? 8 : 6;
   unsigned sk[8];
 #pragma unroll
-  for (int i = 0; i < 8; i++) sk[i] = bt_random_bits(k0, k1, i, 8);
+  for (int i = 0; i < 8; i++) sk[i] = i < nsplit ? bt_random_bits(k0, k1, i, nsplit) : 0u;
   // start_frame = randint(rng, (), 0, range): k1_, k2_ = split(rng); bits of each; span arithmetic in uint32
   const unsigned r0 = sk[0], r1 = sk[1];
   unsigned ss[4];
@@ -110,11 +112,11 @@ BT_DEV void bt_prog_reset(const BtDev& m, float* s, int lane, int env, const BtR
   unsigned mult = 65536u % span;
   mult = (mult * mult) % span;
   const unsigned off = (hi_bits % span) * mult + (lo_bits % span);
-  const int start = (int)(off % span);
+  const int start = a.fixed_start_frame < 0 ? (int)(off % span) : a.fixed_start_frame;
   const float lo = -m.reset_noise_scale, hi = m.reset_noise_scale;
   for (int i = lane; i < m.nq; i += G) {
     float q0 = BT_LDG(m.qpos0 + i);
-    if (m.seed_root_from_clip) {
+    if (m.seed_root_from_clip && a.fixed_start_frame < 0) {  // the render-rollout reset starts from qpos0 (custom_wrappers.py:99-103)
       if (i < 2) q0 = BT_LDG(m.clip_position + 3 * start + i);
       else if (i >= 3 && i < 7) q0 = BT_LDG(m.clip_quaternion + 4 * start + i - 3);
     }

@@ -179,6 +179,30 @@ class AutoResetWrapperTracking:
         return state
 
 
+class RenderRolloutWrapperTracking:
+    """custom_brax/custom_wrappers.py:82-125: "always resets to 0" -- deterministic start frame for evaluation / rendering
+    rollouts (main.py:131-151); steps are the bare env's (no episode wrapper, no auto-reset)."""
+
+    def __init__(self, env: TrackingEnv):
+        self.env = env
+
+    def __getattr__(self, name):
+        return getattr(self.env, name)
+
+    def reset(self, rng) -> State:
+        env = self.env
+        keys = env._keys(rng)
+        n = keys.shape[0]
+        st, out = env._native.new_state(n), env._native.new_outputs(n)
+        env._native.reset(keys, st, out, fixed_start_frame=0)
+        metrics, info = _views(out)
+        info.pop("steps"); info.pop("truncation")
+        return State(st, out["obs"], out["reward"], out["done"], metrics, info, _raw=out)
+
+    def step(self, state: State, action) -> State:
+        return self.env.step(state, action)
+
+
 def wrap(env: TrackingEnv, episode_length: int = 1000, action_repeat: int = 1, randomization_fn=None) -> AutoResetWrapperTracking:
     """custom_brax/custom_wrappers.py:14-40."""
     if randomization_fn is not None:

@@ -137,11 +137,11 @@ class NativeModel:
         return C.c_void_p(self._torch().cuda.current_stream(self.device).cuda_stream)
 
     # ---- entry points ----------------------------------------------------------------------------
-    def reset(self, keys, state, out):
+    def reset(self, keys, state, out, fixed_start_frame: int = -1):
         torch = self._torch()
         n = keys.shape[0]
         _check(lib().bt_reset(self._h, n, self._p(keys, (n, 2), torch.uint32 if keys.dtype == torch.uint32 else torch.int32),
-                              self._sp(state, n), self._p(out["obs"], (n, self.obs_size)), self._p(out["reward"], (n,)),
+                              int(fixed_start_frame), self._sp(state, n), self._p(out["obs"], (n, self.obs_size)), self._p(out["reward"], (n,)),
                               self._p(out["done"], (n,)), self._p(out["metrics"], (n, NUM_METRICS)),
                               self._p(out["info_f"], (n, NUM_INFO_F)), self._p(out["info_i"], (n, NUM_INFO_I), torch.int32),
                               self._stream()))
@@ -170,6 +170,17 @@ class NativeModel:
                                    self._p(out["info_i"], (n, NUM_INFO_I), torch.int32), self._p(out["obs"], (n, self.obs_size)),
                                    self._p(out["reward"], (n,)), self._p(out["done"], (n,)), self._p(out["metrics"], (n, NUM_METRICS)),
                                    self._p(out["info_f"], (n, NUM_INFO_F)), self._stream()))
+
+    def kinematics(self, qpos):
+        """Batched forward kinematics (mjx smooth.kinematics; preprocessing/preprocess.py:144-204): qpos [n, nq] ->
+        (xpos [n, nbody, 3], xquat [n, nbody, 4]) through the tree pass of the step kernel."""
+        n = qpos.shape[0]
+        st = self.new_state(n)
+        st["qpos"].copy_(qpos)
+        scratch, _, _ = self.forward_debug(None, st, stop=1)
+        ox, oq = self.offset("xpos"), self.offset("xquat")
+        return (scratch[:, ox:ox + 3 * self.nbody].reshape(n, self.nbody, 3).clone(),
+                scratch[:, oq:oq + 4 * self.nbody].reshape(n, self.nbody, 4).clone())
 
     def forward_debug(self, ctrl: Optional["object"], state, stop: int = 0):
         torch = self._torch()

@@ -305,3 +305,30 @@ def load_checkpoint(ts: TrainingState, path: str) -> dict:
     ts.optimizer.load_state_dict(blob["optimizer"])
     ts.env_steps = int(blob["env_steps"])
     return blob
+
+
+# ---------------------------------------------------------------------------------------------- evaluation rollout
+def evaluate_rollout(environment, policy_fn, rng_keys, num_steps: Optional[int] = None) -> Dict[str, np.ndarray]:
+    """The authors' de-facto regression signal (/root/reference/main.py:136-258): a deterministic-policy rollout of
+    ``clip_length`` frames from frame 0 through ``RenderRolloutWrapperTracking`` with per-step traces of the reward terms,
+    the tracking distances and the torso height.  ``policy_fn(obs) -> (action, ...)`` as returned by ``make_policy``.
+    Returns {name: [num_steps, n_envs]} on the host (rendering itself is out of scope: it needs MuJoCo's GL renderer)."""
+    env = envs_mod.RenderRolloutWrapperTracking(environment)
+    state = env.reset(rng_keys)
+    if num_steps is None:
+        num_steps = int(250 * environment._steps_for_cur_frame)              # main.py:147
+    names = ["pos_reward", "quat_reward", "joint_reward", "bodypos_reward", "endeff_reward"]
+    trace = {k: [] for k in names + ["reward", "summed_pos_distance", "joint_distance", "torso_height", "done", "cur_frame"]}
+    tz = 3 * (environment._thorax_idx % environment.sys.nbody) + 2
+    for _ in range(num_steps):
+        action = policy_fn(state.obs)[0]
+        state = env.step(state, action.contiguous())
+        for k in names:
+            trace[k].append(state.metrics[k].clone())
+        trace["reward"].append(state.reward.clone())
+        trace["summed_pos_distance"].append(state.info["summed_pos_distance"].clone())
+        trace["joint_distance"].append(state.info["joint_distance"].clone())
+        trace["torso_height"].append(state.pipeline_state["xpos"][:, tz].clone())
+        trace["done"].append(state.done.clone())
+        trace["cur_frame"].append(state.info["cur_frame"].clone())
+    return {k: torch.stack(v).cpu().numpy() for k, v in trace.items()}

@@ -60,8 +60,10 @@ int bt_model_dims(const BtModel* m, int* dims);
 /* launch geometry chosen for this model: out[0] = warps (= envs) per CTA, out[1] = max CTAs, out[2] = dynamic smem bytes */
 int bt_model_launch(const BtModel* m, int* out);
 
-int bt_reset(BtModel* m, int n_envs, const uint32_t* keys /*[n,2]*/, BtStatePtrs state, float* obs /*[n,O]*/,
-             float* reward, float* done, float* metrics /*[n,12]*/, float* info_f /*[n,5]*/,
+/* fixed_start_frame < 0: training reset (random start frame in [0, 44), split(rng, 4));
+   fixed_start_frame >= 0: RenderRolloutWrapperTracking.reset (custom_brax/custom_wrappers.py:85-125: that frame, split(rng, 3)) */
+int bt_reset(BtModel* m, int n_envs, const uint32_t* keys /*[n,2]*/, int fixed_start_frame, BtStatePtrs state,
+             float* obs /*[n,O]*/, float* reward, float* done, float* metrics /*[n,12]*/, float* info_f /*[n,5]*/,
              int32_t* info_i /*[n,2]*/, void* stream);
 
 int bt_step(BtModel* m, int n_envs, const float* action /*[n,nu]*/, BtStatePtrs state /*in-out*/,

@@ -167,8 +167,9 @@ class EnvOracle:
         return 0.5 * np.arccos(dist)
 
     # -- reset: fruitfly.py:449-495 (+ rodent.py:154-159), EpisodeWrapper.reset, AutoReset.reset -----
-    def reset(self, keys):
-        """keys: [N,2] uint32 (one JAX key per env, as jax.random.split(key_env, num_envs))."""
+    def reset(self, keys, fixed_start_frame=-1):
+        """keys: [N,2] uint32 (one JAX key per env, as jax.random.split(key_env, num_envs)).
+        fixed_start_frame >= 0: RenderRolloutWrapperTracking.reset (custom_wrappers.py:85-125): split(rng, 3), that frame."""
         c, dt, m = self.c, self.dt, self.m
         N = keys.shape[0]
         qpos = np.zeros((N, m.nq), dtype=dt)
@@ -176,11 +177,11 @@ class EnvOracle:
         start = np.zeros(N, dtype=np.int32)
         lo, hi = -c["reset_noise_scale"], c["reset_noise_scale"]
         for e in range(N):
-            k = split((keys[e, 0], keys[e, 1]), 4)
+            k = split((keys[e, 0], keys[e, 1]), 4 if fixed_start_frame < 0 else 3)
             rng, rng1, rng2 = (k[0, 0], k[0, 1]), (k[1, 0], k[1, 1]), (k[2, 0], k[2, 1])
-            start[e] = randint(rng, 0, 44)
+            start[e] = randint(rng, 0, 44) if fixed_start_frame < 0 else fixed_start_frame
             q0 = m.qpos0.astype(dt).copy()
-            if c["seed_root_from_clip"]:
+            if c["seed_root_from_clip"] and fixed_start_frame < 0:
                 q0[:2] = self.clip["position"][start[e], :2]
                 q0[3:7] = self.clip["quaternion"][start[e]]
             qpos[e] = q0 + uniform(rng1, m.nq, lo, hi).astype(dt)

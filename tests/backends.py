@@ -26,8 +26,8 @@ class EmuBackend:
     def new_outputs(self, N):
         return self.e.new_outputs(N)
 
-    def reset(self, keys):
-        return self.e.reset(keys)
+    def reset(self, keys, fixed_start_frame=-1):
+        return self.e.reset(keys, fixed_start_frame)
 
     def step(self, st, out, first, first_obs, first_ii, action):
         self.e.step(st, out, first, first_obs, first_ii, action)
@@ -70,10 +70,10 @@ class CudaBackend:
     def new_outputs(self, N):
         return {k: v.cpu().numpy() for k, v in self.nm.new_outputs(N).items()}
 
-    def reset(self, keys):
+    def reset(self, keys, fixed_start_frame=-1):
         N = keys.shape[0]
         st, out = self.nm.new_state(N), self.nm.new_outputs(N)
-        self.nm.reset(self._d(np.ascontiguousarray(keys, dtype=np.uint32).view(np.int32)), st, out)
+        self.nm.reset(self._d(np.ascontiguousarray(keys, dtype=np.uint32).view(np.int32)), st, out, fixed_start_frame)
         return {k: v.cpu().numpy() for k, v in st.items()}, {k: v.cpu().numpy() for k, v in out.items()}
 
     def step(self, st, out, first, first_obs, first_ii, action):

@@ -81,11 +81,11 @@ class Emu:
         return dict(obs=np.zeros((N, self.obs_size), np.float32), reward=np.zeros(N, np.float32), done=np.zeros(N, np.float32),
                     metrics=np.zeros((N, 12), np.float32), info_f=np.zeros((N, 5), np.float32), info_i=np.zeros((N, 2), np.int32))
 
-    def reset(self, keys):
+    def reset(self, keys, fixed_start_frame=-1):
         keys = np.ascontiguousarray(keys, dtype=np.uint32)
         N = keys.shape[0]
         st, out = self.new_state(N), self.new_outputs(N)
-        self.lib.emu_reset(self.h, N, _ptr(keys), self.sp(st), _ptr(out["obs"]), _ptr(out["reward"]), _ptr(out["done"]),
+        self.lib.emu_reset(self.h, N, _ptr(keys), int(fixed_start_frame), self.sp(st), _ptr(out["obs"]), _ptr(out["reward"]), _ptr(out["done"]),
                            _ptr(out["metrics"]), _ptr(out["info_f"]), _ptr(out["info_i"]))
         return st, out
 

@@ -38,10 +38,10 @@ int emu_model_create(int n, const char* const* names, const void* const* data, c
 }
 void emu_model_destroy(EmuModel* m) { delete m; }
 
-int emu_reset(EmuModel* m, int n, const uint32_t* keys, BtStatePtrs st, float* obs, float* reward, float* done, float* metrics,
-              float* info_f, int32_t* info_i) {
+int emu_reset(EmuModel* m, int n, const uint32_t* keys, int fixed_start_frame, BtStatePtrs st, float* obs, float* reward, float* done,
+              float* metrics, float* info_f, int32_t* info_i) {
   std::vector<float> s(m->dev.smem_floats);
-  BtResetArgs a = {keys, st, obs, reward, done, metrics, info_f, info_i};
+  BtResetArgs a = {keys, fixed_start_frame, st, obs, reward, done, metrics, info_f, info_i};
   for (int e = 0; e < n; e++) bt_prog_reset<1, EMU_DS, EMU_CS>(m->dev, s.data(), 0, e, a);
   return 0;
 }

@@ -79,6 +79,15 @@ def test_ppo_loop_runs_on_the_fused_step(tmp_path):
     a, raw, logits = act(torch.zeros(3, env.observation_size, device="cuda"))
     assert a.shape == (3, env.action_size) and torch.isfinite(a).all() and float(a.abs().max()) <= 1.0
     assert float(params[0]["count"]) == 2 * 256 * 4 * 4
+    # evaluation rollout from frame 0 (main.py:136-258) + device FK for clip preprocessing (preprocess.py:144-204)
+    tr = ppo.evaluate_rollout(env, act, common.jax_keys(4, seed=2), num_steps=10)
+    assert tr["reward"].shape == (10, 4) and np.isfinite(tr["reward"]).all()
+    assert (tr["cur_frame"][1] == 1).all() and (tr["cur_frame"][-1] == 5).all()      # two control steps per mocap frame
+    from brax_tracking_b200 import mjcf, preprocess
+    q = np.tile(m.qpos0, (6, 1)) + 0.05 * np.random.default_rng(0).standard_normal((6, m.nq))
+    c_dev = preprocess.process_clip(q, m, kinematics=preprocess.device_kinematics(env._native))
+    c_host = preprocess.process_clip(q, m)
+    np.testing.assert_allclose(c_dev.body_positions, c_host.body_positions, atol=2e-6)
 
 
 def test_smoke_entry():
