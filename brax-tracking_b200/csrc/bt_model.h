@@ -9,14 +9,14 @@
 
 // ---- scalar ints (1-element int tables, by name) ----
 #define BT_INT_SCALARS(X) \
-  X(nq) X(nv) X(nu) X(na) X(nbody) X(njnt) X(nM) X(nlevel) X(nlevd) X(nroot) X(ncon) X(ncgeom) X(ncb)           \
+  X(nq) X(nv) X(nu) X(na) X(nbody) X(njnt) X(nlevel) X(nchain) X(nclev) X(nroot) X(ncon) X(ncgeom) X(ncb)           \
   X(cone) X(iterations) X(ls_iterations) X(n_frames)                                                            \
   /* env layer */                                                                                               \
   X(free_jnt) X(seed_root_from_clip) X(ref_len) X(clip_len) X(clip_nj) X(n_joint_idxs) X(n_body_idxs)           \
   X(n_endeff_idxs) X(torso_idx) X(terminate_when_unhealthy) X(steps_for_cur_frame) X(episode_length)            \
   X(start_frame_range) X(obs_size)                                                                              \
   /* per-environment scratch layout (offsets in floats) */                                                      \
-  X(o_qpos) X(o_qvel) X(o_act) X(o_ctrl) X(o_warm) X(o_xpos) X(o_xquat) X(o_cdof) X(o_crb) X(o_LD) X(o_Dinv)    \
+  X(o_qpos) X(o_qvel) X(o_act) X(o_ctrl) X(o_warm) X(o_xpos) X(o_xquat) X(o_cdof) X(o_crb) X(o_U) X(o_pvec) X(o_Dinv)    \
   X(o_T) X(o_ref) X(o_aforce) X(o_actdot) X(o_qfrc_smooth) X(o_qacc_smooth) X(o_qacc) X(o_x) X(o_search)        \
   X(o_qfrc_c) X(o_tmpv) X(smem_floats)
 
@@ -32,8 +32,8 @@
 #define BT_INT_TABLES(X) \
   X(body_parentid) X(body_jntadr) X(body_jntnum) X(body_ref) X(level_adr) X(level_body) X(child_adr) X(child_id)\
   X(jnt_type) X(jnt_qposadr) X(jnt_dofadr)                                                                      \
-  X(dof_bodyid) X(dof_parentid) X(dof_Madr) X(dof_depth) X(dof_md) X(dof_subtreenum) X(dof_qposadr) X(dof_limited)        \
-  X(M_row) X(M_col) X(M_colMadr) X(inv_adr) X(inv_item) X(tri_ab)                                                                      \
+  X(dof_bodyid) X(dof_parentid) X(dof_qposadr) X(dof_limited)                                                   \
+  X(chain_k0) X(chain_len) X(clev_adr) X(clev_chain) X(dof_chain) X(dchild_adr) X(dchild_id) X(dofbody_adr) X(dofbody_id)                                                                      \
   X(cgeom_bodyid) X(cb_adr) X(cb_dof) X(cb_ref)                                                                 \
   X(con_g1) X(con_g2) X(con_cb1) X(con_cb2) X(con_ref) X(con_fn) X(con_sub) X(con_dim)                          \
   X(dofcon_adr) X(dofcon_c)                                                                                     \

@@ -20,25 +20,31 @@ BT_DEV void bt_write_obs(BtEnv<G, DS, CS>& E, float* obs_row, const float* src) 
 
 // wrap(env).step  (custom_wrappers.py:54-80 o EpisodeWrapper.step o fruitfly.py:497-596)
 template <int G, int DS, int CS>
-BT_DEV void bt_prog_step(const BtDev& m, float* s, int lane, int env, const BtStepArgs& a) {
+// `live` = false: this lane group has no environment in this round and only takes part in the CTA barriers of substep()
+BT_DEV void bt_prog_step(const BtDev& m, float* s, int lane, int env, bool live, const BtStepArgs& a) {
   typedef BtLanes<G> W;
-  BtEnv<G, DS, CS> E(m, s, lane);
-  // AutoResetWrapperTracking.step: steps <- 0 where the previous step was done (custom_wrappers.py:55-58)
-  const float prev_done = a.done[env];
-  float steps = a.info_f[(size_t)env * BT_NINFOF + BT_IF_STEPS];
-  if (prev_done > 0.f) steps = 0.f;
-  const int cur_in = a.info_i[(size_t)env * BT_NINFOI + BT_II_CUR_FRAME];
-  const int stc_in = a.info_i[(size_t)env * BT_NINFOI + BT_II_STEPS_TAKEN];
-  float time = a.state.time[env];
-  W::sync();  // all lanes have read done / info before lane 0 overwrites them below
-  E.load_state(a.state, env);
-  const float* act_row = a.action + (size_t)env * m.nu;
-  for (int u = lane; u < m.nu; u += G) E.ctrl()[u] = act_row[u];
-  W::sync();
+  BtEnv<G, DS, CS> E(m, s, lane, live);
+  float steps = 0.f, time = 0.f;
+  int cur_in = 0, stc_in = 0;
+  if (live) {
+    // AutoResetWrapperTracking.step: steps <- 0 where the previous step was done (custom_wrappers.py:55-58)
+    const float prev_done = a.done[env];
+    steps = a.info_f[(size_t)env * BT_NINFOF + BT_IF_STEPS];
+    if (prev_done > 0.f) steps = 0.f;
+    cur_in = a.info_i[(size_t)env * BT_NINFOI + BT_II_CUR_FRAME];
+    stc_in = a.info_i[(size_t)env * BT_NINFOI + BT_II_STEPS_TAKEN];
+    time = a.state.time[env];
+    W::sync();  // all lanes have read done / info before lane 0 overwrites them below
+    E.load_state(a.state, env);
+    const float* act_row = a.action + (size_t)env * m.nu;
+    for (int u = lane; u < m.nu; u += G) E.ctrl()[u] = act_row[u];
+    W::sync();
+  }
   for (int f = 0; f < m.n_frames; f++) {
     E.step();
     time += m.timestep;
   }
+  if (!live) return;
   typename BtEnv<G, DS, CS>::StepOut r;
   E.reward_terms(E.ctrl(), cur_in, stc_in, r);
   E.build_obs(r.cur_frame);
@@ -92,9 +98,10 @@ struct BtResetArgs {
 
 // wrap(env).reset  (fruitfly.py:449-495, rodent.py:154-159; JAX threefry per SURVEY Appendix D)
 template <int G, int DS, int CS>
-BT_DEV void bt_prog_reset(const BtDev& m, float* s, int lane, int env, const BtResetArgs& a) {
+BT_DEV void bt_prog_reset(const BtDev& m, float* s, int lane, int env, bool live, const BtResetArgs& a) {
   typedef BtLanes<G> W;
-  BtEnv<G, DS, CS> E(m, s, lane);
+  BtEnv<G, DS, CS> E(m, s, lane, live);
+  if (!live) { E.forward(); return; }
   const unsigned k0 = a.keys[2 * (size_t)env], k1 = a.keys[2 * (size_t)env + 1];
   // training: rng, rng1, rng2, rng_pos = split(rng, 4);  render rollout: rng, rng1, rng2 = split(rng, 3)
   const int nsplit = a.fixed_start_frame < 0 ? 8 : 6;
@@ -146,20 +153,24 @@ BT_DEV void bt_prog_reset(const BtDev& m, float* s, int lane, int env, const BtR
 
 // PipelineEnv.pipeline_step (n_substeps > 0) or pipeline_init (n_substeps == 0: one mjx.forward)
 template <int G, int DS, int CS>
-BT_DEV void bt_prog_physics(const BtDev& m, float* s, int lane, int env, const float* ctrl, const BtState& st, int n_substeps) {
+BT_DEV void bt_prog_physics(const BtDev& m, float* s, int lane, int env, bool live, const float* ctrl, const BtState& st,
+                            int n_substeps) {
   typedef BtLanes<G> W;
-  BtEnv<G, DS, CS> E(m, s, lane);
-  float time = st.time[env];
-  W::sync();
-  E.load_state(st, env);
-  for (int u = lane; u < m.nu; u += G) E.ctrl()[u] = ctrl ? ctrl[(size_t)env * m.nu + u] : 0.f;
-  W::sync();
+  BtEnv<G, DS, CS> E(m, s, lane, live);
+  float time = 0.f;
+  if (live) {
+    time = st.time[env];
+    W::sync();
+    E.load_state(st, env);
+    for (int u = lane; u < m.nu; u += G) E.ctrl()[u] = ctrl ? ctrl[(size_t)env * m.nu + u] : 0.f;
+    W::sync();
+  }
   if (n_substeps == 0) E.forward();
   for (int f = 0; f < n_substeps; f++) {
     E.step();
     time += m.timestep;
   }
-  E.store_state(st, env, time);
+  if (live) E.store_state(st, env, time);
   W::sync();
 }
 
@@ -172,8 +183,9 @@ struct BtRewardArgs {
 
 // env.step after pipeline_step (fruitfly.py:502-596), no wrappers
 template <int G, int DS, int CS>
-BT_DEV void bt_prog_reward(const BtDev& m, float* s, int lane, int env, const BtRewardArgs& a) {
+BT_DEV void bt_prog_reward(const BtDev& m, float* s, int lane, int env, bool live, const BtRewardArgs& a) {
   typedef BtLanes<G> W;
+  if (!live) return;
   BtEnv<G, DS, CS> E(m, s, lane);
   const int cur_in = a.info_i[(size_t)env * BT_NINFOI + BT_II_CUR_FRAME];
   const int stc_in = a.info_i[(size_t)env * BT_NINFOI + BT_II_STEPS_TAKEN];
@@ -200,10 +212,11 @@ BT_DEV void bt_prog_reward(const BtDev& m, float* s, int lane, int env, const Bt
 
 // mjx.forward up to a stop point, then dump the scratch block (parity tests of intermediates)
 template <int G, int DS, int CS>
-BT_DEV void bt_prog_debug(const BtDev& m, float* s, int lane, int env, const float* ctrl, const BtState& st, int stop,
+BT_DEV void bt_prog_debug(const BtDev& m, float* s, int lane, int env, bool live, const float* ctrl, const BtState& st, int stop,
                           float* scratch, float* cdist, int32_t* niter) {
   typedef BtLanes<G> W;
-  BtEnv<G, DS, CS> E(m, s, lane);
+  BtEnv<G, DS, CS> E(m, s, lane, live);
+  if (!live) { E.forward(stop); return; }
   for (int i = lane; i < m.smem_floats; i += G) s[i] = 0.f;
   W::sync();
   E.load_state(st, env);

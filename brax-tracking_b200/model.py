@@ -77,7 +77,7 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
     body_ref = np.array([0] + [root_slot[a["body_rootid"][b]] for b in range(1, nbody)], dtype=np.int32)
 
     S("nq", nq); S("nv", nv); S("nu", nu); S("na", na); S("nbody", nbody); S("njnt", njnt)
-    S("nM", m.nM); S("nlevel", nlevel); S("nroot", len(roots))
+    S("nlevel", nlevel); S("nroot", len(roots))
     t["body_parentid"] = _i(parent)
     t["body_jntadr"] = _i(a["body_jntadr"])
     t["body_jntnum"] = _i(a["body_jntnum"])
@@ -122,40 +122,54 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
             dof_solimp[i] = a["jnt_solimp"][j]
             dof_margin[i] = a["jnt_margin"][j]
     t["dof_bodyid"] = _i(a["dof_bodyid"]); t["dof_parentid"] = _i(a["dof_parentid"])
-    t["dof_Madr"] = _i(a["dof_Madr"]); t["dof_depth"] = _i(a["dof_depth"]); t["dof_subtreenum"] = _i(a["dof_subtreenum"])
-    t["dof_md"] = _i(a["dof_Madr"].astype(np.int64) | (a["dof_depth"].astype(np.int64) << 16))  # packed (Madr, depth)
-    assert m.nM < 65536
     t["dof_qposadr"] = dof_qadr; t["dof_limited"] = dof_lim
     t["dof_stiffness"] = _f(dof_stiff); t["dof_springref"] = _f(dof_spring)
     t["dof_armature"] = _f(a["dof_armature"]); t["dof_damping"] = _f(a["dof_damping"])
     t["dof_range"] = _f(dof_range); t["dof_solref"] = _f(dof_solref); t["dof_solimp"] = _f(dof_solimp)
     t["dof_margin"] = _f(dof_margin); t["dof_invweight0"] = _f(a["dof_invweight0"])
-    # tree-sparse M: entry e of row i (a = e - Madr[i]) is M[i, anc_a(i)]
-    M_row = np.zeros(m.nM, dtype=np.int32); M_col = np.zeros(m.nM, dtype=np.int32)
+    # dof tree cut into chains (maximal single-child paths: consecutive dof ids by DFS numbering), scheduled by the depth
+    # of the chain in the chain tree (articulated-body sweeps, csrc/bt_impl.h::aba_factor / solve / mul_M)
+    dchild = [[] for _ in range(nv)]
     for i in range(nv):
-        j, e = i, a["dof_Madr"][i]
-        while j >= 0:
-            M_row[e], M_col[e] = i, j
-            e += 1
-            j = a["dof_parentid"][j]
-    t["M_row"] = M_row; t["M_col"] = M_col
-    t["M_colMadr"] = _i(a["dof_Madr"][M_col])
-    # work list of the in-place inversion L -> L^-1: entries (i, a >= 1) grouped by dof depth (ascending), rows in dof
-    # order, descending a inside a row (csrc/bt_impl.h::invert)
-    dmax = int(a["dof_depth"].max()) if nv else 0
-    inv_adr, inv_item = [0], []
-    for d in range(1, dmax + 1):
-        for i in range(nv):
-            if a["dof_depth"][i] == d:
-                inv_item.extend([i | (aa << 8) for aa in range(d, 0, -1)])
-        inv_adr.append(len(inv_item))
-    # triangular decode table t -> (a, b), 1 <= a <= b, ordered by b (a valid prefix for every row depth)
-    tri = [(aa, bb) for bb in range(1, dmax + 1) for aa in range(1, bb + 1)]
-    t["tri_ab"] = _i([aa | (bb << 8) for aa, bb in tri]) if tri else np.zeros(1, np.int32)
-    S("nlevd", dmax)
-    t["inv_adr"] = _i(inv_adr)
-    t["inv_item"] = _i(inv_item) if inv_item else np.zeros(1, np.int32)
-    assert nv < 256 and dmax < 256
+        if a["dof_parentid"][i] >= 0:
+            dchild[a["dof_parentid"][i]].append(i)
+    dchild_adr, dchild_id = [0], []
+    for i in range(nv):
+        dchild_id.extend(dchild[i])
+        dchild_adr.append(len(dchild_id))
+    # bodies carried by a dof: every body whose last dof on the chain root -> body is that dof (jointless bodies ride
+    # on their ancestor's last dof; bodies of the static world group carry no dof and drop out of the dynamics)
+    dofbody = [[] for _ in range(nv)]
+    for b in range(1, nbody):
+        if a["body_lastdof"][b] >= 0:
+            dofbody[a["body_lastdof"][b]].append(b)
+    dofbody_adr, dofbody_id = [0], []
+    for i in range(nv):
+        dofbody_id.extend(dofbody[i])
+        dofbody_adr.append(len(dofbody_id))
+    chain_k0, chain_len, dof_chain = [], [], np.zeros(nv, dtype=np.int32)
+    for i in range(nv):
+        par = a["dof_parentid"][i]
+        if par >= 0 and len(dchild[par]) == 1:
+            assert par == i - 1, "single-child dofs must be consecutive (DFS numbering)"
+            dof_chain[i] = dof_chain[par]
+            chain_len[dof_chain[i]] += 1
+        else:
+            dof_chain[i] = len(chain_k0)
+            chain_k0.append(i); chain_len.append(1)
+    nchain = len(chain_k0)
+    clevel = np.zeros(nchain, dtype=np.int32)
+    for c in range(nchain):
+        par = a["dof_parentid"][chain_k0[c]]
+        clevel[c] = 0 if par < 0 else clevel[dof_chain[par]] + 1
+    nclev = int(clevel.max()) + 1 if nchain else 1
+    corder = sorted(range(nchain), key=lambda c: (clevel[c], c))
+    clev_adr = np.concatenate([[0], np.cumsum([int(np.sum(clevel == L)) for L in range(nclev)])]).astype(np.int32)
+    S("nchain", nchain); S("nclev", nclev)
+    t["chain_k0"] = _i(chain_k0); t["chain_len"] = _i(chain_len); t["clev_adr"] = clev_adr; t["clev_chain"] = _i(corder)
+    t["dof_chain"] = dof_chain
+    t["dchild_adr"] = _i(dchild_adr); t["dchild_id"] = _i(dchild_id) if dchild_id else np.zeros(1, np.int32)
+    t["dofbody_adr"] = _i(dofbody_adr); t["dofbody_id"] = _i(dofbody_id) if dofbody_id else np.zeros(1, np.int32)
 
     def chain(body):
         out, d = [], a["body_lastdof"][body]
@@ -349,17 +363,18 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
 
     R("qpos", nq); R("qvel", nv); R("act", max(na, 1)); R("ctrl", max(nu, 1)); R("warm", nv)
     R("xpos", 3 * nbody); R("xquat", 4 * nbody); R("cdof", 6 * nv); R("crb", 10 * nbody)
-    # LD doubles as cvel/cacc storage during the forward tree pass
-    R("LD", max(m.nM, 12 * nbody)); R("Dinv", nv)
-    # T region: cfrc (forward/backward pass) -> buf (M assembly) -> contact geometry + wrenches (solver)
-    R("T", max(6 * nbody, 6 * nv, 18 * ncon + 6 * max(ncb, 1)))
+    # U (6/dof) and pvec (6/dof) are contiguous: together they hold cvel/cacc (12/body) during the forward tree pass
+    R("U", 6 * nv); R("pvec", max(6 * nv, 12 * nbody - 6 * nv)); R("Dinv", nv)
+    # T region: cfrc (tree passes) -> one 6x6 reduced articulated inertia per chain (aba_factor) -> contact geometry +
+    # wrenches + chain sums (solver)
+    R("T", max(6 * nbody, 36 * nchain, 18 * ncon + 6 * max(ncb, 1)))
     R("ref", 3 * max(len(roots), 1))
     R("actdot", max(na, 1))
     for v in ("qfrc_smooth", "qacc_smooth", "qacc", "search", "qfrc_c"):
         R(v, nv)
     R("x", max(nv, nu))
     lay["aforce"] = lay["x"]            # actuator forces live only inside smooth_forces()
-    lay["tmpv"] = lay["qacc_smooth"]    # solve() temp: qacc_smooth is consumed (into registers) before the first CG solve
+    lay["tmpv"] = lay["qacc_smooth"]    # solve() temp (u_k): qacc_smooth is consumed (into registers) before the first CG solve
     for k, v in lay.items():
         S("o_" + k, v)
     off = max(off, lay["crb"] + obs_size)  # the observation row is staged over crb/LD/T at the end of the step

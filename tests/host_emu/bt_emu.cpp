@@ -42,31 +42,31 @@ int emu_reset(EmuModel* m, int n, const uint32_t* keys, int fixed_start_frame, B
               float* metrics, float* info_f, int32_t* info_i) {
   std::vector<float> s(m->dev.smem_floats);
   BtResetArgs a = {keys, fixed_start_frame, st, obs, reward, done, metrics, info_f, info_i};
-  for (int e = 0; e < n; e++) bt_prog_reset<1, EMU_DS, EMU_CS>(m->dev, s.data(), 0, e, a);
+  for (int e = 0; e < n; e++) bt_prog_reset<1, EMU_DS, EMU_CS>(m->dev, s.data(), 0, e, true, a);
   return 0;
 }
 int emu_step(EmuModel* m, int n, const float* action, BtStatePtrs st, BtStatePtrs first, const float* first_obs,
              const int32_t* first_info_i, float* obs, float* reward, float* done, float* metrics, float* info_f, int32_t* info_i) {
   std::vector<float> s(m->dev.smem_floats);
   BtStepArgs a = {action, st, first, first_obs, first_info_i, obs, reward, done, metrics, info_f, info_i};
-  for (int e = 0; e < n; e++) bt_prog_step<1, EMU_DS, EMU_CS>(m->dev, s.data(), 0, e, a);
+  for (int e = 0; e < n; e++) bt_prog_step<1, EMU_DS, EMU_CS>(m->dev, s.data(), 0, e, true, a);
   return 0;
 }
 int emu_physics_step(EmuModel* m, int n, const float* ctrl, BtStatePtrs st, int n_substeps) {
   std::vector<float> s(m->dev.smem_floats);
-  for (int e = 0; e < n; e++) bt_prog_physics<1, EMU_DS, EMU_CS>(m->dev, s.data(), 0, e, ctrl, st, n_substeps);
+  for (int e = 0; e < n; e++) bt_prog_physics<1, EMU_DS, EMU_CS>(m->dev, s.data(), 0, e, true, ctrl, st, n_substeps);
   return 0;
 }
 int emu_reward_obs(EmuModel* m, int n, const float* action, BtStatePtrs st, int32_t* info_i, float* obs, float* reward,
                    float* done, float* metrics, float* info_f) {
   std::vector<float> s(m->dev.smem_floats);
   BtRewardArgs a = {action, st, info_i, obs, reward, done, metrics, info_f};
-  for (int e = 0; e < n; e++) bt_prog_reward<1, EMU_DS, EMU_CS>(m->dev, s.data(), 0, e, a);
+  for (int e = 0; e < n; e++) bt_prog_reward<1, EMU_DS, EMU_CS>(m->dev, s.data(), 0, e, true, a);
   return 0;
 }
 int emu_forward_debug(EmuModel* m, int n, const float* ctrl, BtStatePtrs st, int stop, float* scratch, float* cdist, int32_t* niter) {
   std::vector<float> s(m->dev.smem_floats);
-  for (int e = 0; e < n; e++) bt_prog_debug<1, EMU_DS, EMU_CS>(m->dev, s.data(), 0, e, ctrl, st, stop, scratch, cdist, niter);
+  for (int e = 0; e < n; e++) bt_prog_debug<1, EMU_DS, EMU_CS>(m->dev, s.data(), 0, e, true, ctrl, st, stop, scratch, cdist, niter);
   return 0;
 }
 }
