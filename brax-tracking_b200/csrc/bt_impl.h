@@ -98,11 +98,14 @@ struct BtEnv {
   BT_DEV float* cbA() const { return T() + 18 * m.ncon; }               // [ncb][6]
 
   // ================================================================== P1: forward tree pass
-  // kinematics + cdof + cinert + cvel/cdof_dot/cacc + body-local cfrc in ONE root->leaves sweep
-  // (MJX: smooth.kinematics, com_pos, com_vel, rne forward half, passive fluid).
-  BT_DEV void body_forward(int b) {
+  // (MJX: smooth.kinematics, com_pos, com_vel, rne forward half, passive fluid), in two parts:
+  //  * body_pose: the recursion proper -- pose, cdof, cvel / cdof_dot / cacc -- walked chain by chain (maximal single-child
+  //    body paths, consecutive body ids) by ONE lane per chain with the parent state carried in registers;
+  //  * body_local: everything that only needs the body's own pose and velocity (inertia about the reference point, RNE
+  //    body force, fluid forces), one lane per body, all bodies in parallel.
+  // `first`: the body starts a chain -> (pos, quat, cvel, cacc, rp) are loaded from the parent's stored state.
+  BT_DEV void body_pose(int b, bool first, float pos[3], float quat[4], float cvel[6], float cacc[6], float rp[3]) {
     const int p = BT_LDG(m.body_parentid + b);
-    float pos[3], quat[4], cvel[6], cacc[6];
     float* cv = Uv();  // cvel at 12*b, cacc at 12*b+6 (U and pvec are contiguous and not live during this pass)
     if (p == 0) {
       pos[0] = pos[1] = pos[2] = 0.f;
@@ -111,7 +114,7 @@ struct BtEnv {
       for (int k = 0; k < 6; k++) cvel[k] = 0.f;
       cacc[0] = cacc[1] = cacc[2] = 0.f;
       cacc[3] = -m.grav_x; cacc[4] = -m.grav_y; cacc[5] = -m.grav_z;
-    } else {
+    } else if (first) {
 #pragma unroll
       for (int k = 0; k < 3; k++) pos[k] = xpos()[3 * p + k];
 #pragma unroll
@@ -131,7 +134,6 @@ struct BtEnv {
     }
     const int jadr = BT_LDG(m.body_jntadr + b), jnum = BT_LDG(m.body_jntnum + b);
     const int rs = BT_LDG(m.body_ref + b);
-    float rp[3];
     if (p == 0) {
       if (jnum > 0 && BT_LDG(m.jnt_type + jadr) == BT_JNT_FREE) {
         const int qa = BT_LDG(m.jnt_qposadr + jadr);
@@ -140,7 +142,7 @@ struct BtEnv {
         rp[0] = pos[0]; rp[1] = pos[1]; rp[2] = pos[2];
       }
       ref()[3 * rs] = rp[0]; ref()[3 * rs + 1] = rp[1]; ref()[3 * rs + 2] = rp[2];
-    } else {
+    } else if (first) {
       rp[0] = ref()[3 * rs]; rp[1] = ref()[3 * rs + 1]; rp[2] = ref()[3 * rs + 2];
     }
     for (int jj = 0; jj < jnum; jj++) {
@@ -212,6 +214,18 @@ struct BtEnv {
     for (int k = 0; k < 4; k++) xquat()[4 * b + k] = quat[k];
 #pragma unroll
     for (int k = 0; k < 6; k++) { cv[12 * b + k] = cvel[k]; cv[12 * b + 6 + k] = cacc[k]; }
+  }
+
+  BT_DEV void body_local(int b) {
+    const float* cv = Uv();
+    float pos[3], quat[4], cvel[6], cacc[6], rp[3];
+    const int rs = BT_LDG(m.body_ref + b);
+#pragma unroll
+    for (int k = 0; k < 3; k++) { pos[k] = xpos()[3 * b + k]; rp[k] = ref()[3 * rs + k]; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) quat[k] = xquat()[4 * b + k];
+#pragma unroll
+    for (int k = 0; k < 6; k++) { cvel[k] = cv[12 * b + k]; cacc[k] = cv[12 * b + 6 + k]; }
     // body inertia about the tree reference point, world axes
     const float mass = BT_LDG(m.body_mass + b);
     float ci[10], cf[6];
@@ -285,27 +299,17 @@ struct BtEnv {
       xpos()[0] = xpos()[1] = xpos()[2] = 0.f;
       xquat()[0] = 1.f; xquat()[1] = xquat()[2] = xquat()[3] = 0.f;
     }
-    for (int L = 0; L < m.nlevel; L++) {
-      const int a0 = BT_LDG(m.level_adr + L), a1 = BT_LDG(m.level_adr + L + 1);
-      for (int idx = a0 + lane; idx < a1; idx += G) body_forward(BT_LDG(m.level_body + idx));
-      W::sync();
-    }
-  }
-
-  // ================================================================== P2: backward tree pass (crb + cfrc)
-  BT_DEV void tree_backward() {
-    for (int L = m.nlevel - 2; L >= 0; L--) {
-      const int a0 = BT_LDG(m.level_adr + L), a1 = BT_LDG(m.level_adr + L + 1);
-      const int nitem = (a1 - a0) * 6;
-      for (int it = lane; it < nitem; it += G) {
-        const int bi = it / 6, k = it - bi * 6, b = BT_LDG(m.level_body + a0 + bi);
-        const int c0 = BT_LDG(m.child_adr + b), c1 = BT_LDG(m.child_adr + b + 1);
-        float acc = T()[6 * b + k];
-        for (int c = c0; c < c1; c++) acc += T()[6 * BT_LDG(m.child_id + c) + k];
-        T()[6 * b + k] = acc;
+    for (int cl = 0; cl < m.nbclev; cl++) {
+      const int c0 = BT_LDG(m.bclev_adr + cl), c1 = BT_LDG(m.bclev_adr + cl + 1);
+      for (int ci = c0 + lane; ci < c1; ci += G) {
+        const int c = BT_LDG(m.bclev_chain + ci), b0 = BT_LDG(m.bchain_b0 + c), b1 = b0 + BT_LDG(m.bchain_len + c);
+        float pos[3], quat[4], cvel[6], cacc[6], rp[3];
+        for (int b = b0; b < b1; b++) body_pose(b, b == b0, pos, quat, cvel, cacc, rp);
       }
       W::sync();
     }
+    for (int b = 1 + lane; b < m.nbody; b += G) body_local(b);
+    W::sync();
   }
 
   // ================================================================== P3: actuation + smooth generalized forces
@@ -343,9 +347,35 @@ struct BtEnv {
         f = bt_clampf(f, BT_LDG(m.actuator_forcerange + 2 * u), BT_LDG(m.actuator_forcerange + 2 * u + 1));
       aforce()[u] = f;
     }
-    W::sync();
+    // RNE backward half on the dof chains: f_k = sum of the body forces carried by dof k and its subtree; bias_k = S_k . f_k
+    {
+      float* pv = pvec();
+      for (int cl = m.nclev - 1; cl >= 0; cl--) {
+        const int c0 = BT_LDG(m.clev_adr + cl), c1 = BT_LDG(m.clev_adr + cl + 1);
+        for (int ci = c0 + lane; ci < c1; ci += G) {
+          const int c = BT_LDG(m.clev_chain + ci), k0 = BT_LDG(m.chain_k0 + c), kb = k0 + BT_LDG(m.chain_len + c) - 1;
+          float f[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          for (int e = BT_LDG(m.dchild_adr + kb); e < BT_LDG(m.dchild_adr + kb + 1); e++) {
+            const float* fc = pv + 6 * BT_LDG(m.dchild_id + e);
+#pragma unroll
+            for (int j = 0; j < 6; j++) f[j] += fc[j];
+          }
+          for (int k = kb; k >= k0; k--) {
+            for (int e = BT_LDG(m.dofbody_adr + k); e < BT_LDG(m.dofbody_adr + k + 1); e++) {
+              const float* fb = T() + 6 * BT_LDG(m.dofbody_id + e);
+#pragma unroll
+              for (int j = 0; j < 6; j++) f[j] += fb[j];
+            }
+            qfrc_smooth()[k] = -bt_dot6(cdof() + 6 * k, f);
+          }
+#pragma unroll
+          for (int j = 0; j < 6; j++) pv[6 * k0 + j] = f[j];
+        }
+        W::sync();
+      }
+    }
     for (int i = lane; i < m.nv; i += G) {
-      const float bias = bt_dot6(cdof() + 6 * i, T() + 6 * BT_LDG(m.dof_bodyid + i));
+      const float bias = -qfrc_smooth()[i];
       float f = -BT_LDG(m.dof_damping + i) * qvel()[i];
       const int qa = BT_LDG(m.dof_qposadr + i);
       if (qa >= 0) f -= BT_LDG(m.dof_stiffness + i) * (qpos()[qa] - BT_LDG(m.dof_springref + i));
@@ -378,49 +408,53 @@ struct BtEnv {
       for (int j = 0; j < 10; j++) I10[j] += ci[j];
     }
   }
-  // row r of the 6x6 spatial inertia [[Ibar, [h]x], [-[h]x, m 1]] of a 10-number inertia
-  static BT_DEV void inertia_row(const float* I, int r, float* row) {
-    row[0] = r == 0 ? I[0] : r == 1 ? I[3] : r == 2 ? I[4] : r == 3 ? 0.f : r == 4 ? -I[8] : I[7];
-    row[1] = r == 0 ? I[3] : r == 1 ? I[1] : r == 2 ? I[5] : r == 3 ? I[8] : r == 4 ? 0.f : -I[6];
-    row[2] = r == 0 ? I[4] : r == 1 ? I[5] : r == 2 ? I[2] : r == 3 ? -I[7] : r == 4 ? I[6] : 0.f;
-    row[3] = r == 0 ? 0.f : r == 1 ? I[8] : r == 2 ? -I[7] : r == 3 ? I[9] : 0.f;
-    row[4] = r == 0 ? -I[8] : r == 1 ? 0.f : r == 2 ? I[6] : r == 4 ? I[9] : 0.f;
-    row[5] = r == 0 ? I[7] : r == 1 ? -I[6] : r == 5 ? I[9] : 0.f;
-  }
-
+  // The articulated inertia is kept split as A = Iacc + R: Iacc = plain sum of the link inertias outboard of the dof
+  // (10 numbers, applied with bt_inert_mul -- no 6x6 expansion) and R = the accumulated rank-1 downdates (6x6; lane r of
+  // the chain's 8-lane group owns row r).  Per chain the parent receives 36 + 10 floats.
   BT_DEV void aba_factor(float hdamp) {
     const int grp = lane / kGrp, rl = lane % kGrp;
-    float* Ab = T();  // 36 floats per chain: reduced articulated inertia of the chain top, handed to the parent chain
+    float* Ab = T();  // 46 floats per chain: R (36) and Iacc (10) of the chain top, handed to the parent chain
     for (int cl = m.nclev - 1; cl >= 0; cl--) {
       const int c0 = BT_LDG(m.clev_adr + cl), c1 = BT_LDG(m.clev_adr + cl + 1);
       for (int ci = c0 + grp; ci < c1; ci += G / kGrp) {
         const int c = BT_LDG(m.clev_chain + ci), k0 = BT_LDG(m.chain_k0 + c), kb = k0 + BT_LDG(m.chain_len + c) - 1;
         const bool on = rl < 6;
-        float a[kNR][6];
+        float R[kNR][6], Ia[10];
 #pragma unroll
         for (int i = 0; i < kNR; i++)
 #pragma unroll
-          for (int j = 0; j < 6; j++) a[i][j] = 0.f;
-        if (on)
-          for (int e = BT_LDG(m.dchild_adr + kb); e < BT_LDG(m.dchild_adr + kb + 1); e++) {
-            const float* cr = Ab + 36 * BT_LDG(m.dof_chain + BT_LDG(m.dchild_id + e));
+          for (int j = 0; j < 6; j++) R[i][j] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 10; j++) Ia[j] = 0.f;
+        for (int e = BT_LDG(m.dchild_adr + kb); e < BT_LDG(m.dchild_adr + kb + 1); e++) {
+          const float* cr = Ab + 46 * BT_LDG(m.dof_chain + BT_LDG(m.dchild_id + e));
+          if (on) {
 #pragma unroll
             for (int i = 0; i < kNR; i++)
 #pragma unroll
-              for (int j = 0; j < 6; j++) a[i][j] += cr[6 * (rl + i) + j];
+              for (int j = 0; j < 6; j++) R[i][j] += cr[6 * (rl + i) + j];
           }
+#pragma unroll
+          for (int j = 0; j < 10; j++) Ia[j] += cr[36 + j];
+        }
         for (int k = kb; k >= k0; k--) {
-          float I[10], S[6], u[kNR], U[6];
-          link_inertia(k, I);
+          float S[6], w[6], u[kNR], U[6];
+          for (int e = BT_LDG(m.dofbody_adr + k); e < BT_LDG(m.dofbody_adr + k + 1); e++) {
+            const float* ci_ = crb() + 10 * BT_LDG(m.dofbody_id + e);
+#pragma unroll
+            for (int j = 0; j < 10; j++) Ia[j] += ci_[j];
+          }
 #pragma unroll
           for (int j = 0; j < 6; j++) S[j] = cdof()[6 * k + j];
+          bt_inert_mul(Ia, S, w);
 #pragma unroll
           for (int i = 0; i < kNR; i++) {
-            float row[6];
-            inertia_row(I, rl + i, row);
-            u[i] = 0.f;
+            const int r = rl + i;
+            float wr = w[0];
+            wr = r == 1 ? w[1] : wr; wr = r == 2 ? w[2] : wr; wr = r == 3 ? w[3] : wr; wr = r == 4 ? w[4] : wr; wr = r == 5 ? w[5] : wr;
+            u[i] = wr;
 #pragma unroll
-            for (int j = 0; j < 6; j++) { a[i][j] += row[j]; u[i] += a[i][j] * S[j]; }
+            for (int j = 0; j < 6; j++) u[i] += R[i][j] * S[j];
           }
           W::template gather6<kNR>(u, U, lane);
           float D = BT_LDG(m.dof_armature + k) + hdamp * BT_LDG(m.dof_damping + k);
@@ -433,7 +467,7 @@ struct BtEnv {
               Uv()[6 * k + rl + i] = u[i];
               const float ui = u[i] * inv;
 #pragma unroll
-              for (int j = 0; j < 6; j++) a[i][j] -= ui * U[j];
+              for (int j = 0; j < 6; j++) R[i][j] -= ui * U[j];
             }
             if (rl == 0) Dinv()[k] = inv;
           }
@@ -442,7 +476,11 @@ struct BtEnv {
 #pragma unroll
           for (int i = 0; i < kNR; i++)
 #pragma unroll
-            for (int j = 0; j < 6; j++) Ab[36 * c + 6 * (rl + i) + j] = a[i][j];
+            for (int j = 0; j < 6; j++) Ab[46 * c + 6 * (rl + i) + j] = R[i][j];
+        }
+        if (rl == 0) {
+#pragma unroll
+          for (int j = 0; j < 10; j++) Ab[46 * c + 36 + j] = Ia[j];
         }
       }
       W::sync();
@@ -1225,7 +1263,6 @@ struct BtEnv {
     // `live` is warp-uniform and `stop` / `do_euler` are CTA-uniform, so every warp of the CTA reaches every barrier
     if (live) tree_forward();
     W::cta_sync();
-    if (live) tree_backward();
     if (stop == BT_STOP_TREE) return false;
     if (live) smooth_forces();
     if (stop == BT_STOP_SMOOTH) return false;

@@ -69,6 +69,27 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
         child_adr[b] = len(child_id)
         child_id.extend(children[b])
     child_adr[nbody] = len(child_id)
+    # body chains (maximal single-child body paths: consecutive ids by DFS numbering) for the pose recursion
+    bchain_b0, bchain_len, body_chain = [], [], np.zeros(nbody, dtype=np.int32)
+    for b in range(1, nbody):
+        pb = parent[b]
+        if pb > 0 and len(children[pb]) == 1:
+            assert pb == b - 1
+            body_chain[b] = body_chain[pb]
+            bchain_len[body_chain[b]] += 1
+        else:
+            body_chain[b] = len(bchain_b0)
+            bchain_b0.append(b); bchain_len.append(1)
+    nbchain = len(bchain_b0)
+    bclevel = np.zeros(nbchain, dtype=np.int32)
+    for c in range(nbchain):
+        pb = parent[bchain_b0[c]]
+        bclevel[c] = 0 if pb == 0 else bclevel[body_chain[pb]] + 1
+    nbclev = int(bclevel.max()) + 1
+    t["bchain_b0"] = _i(bchain_b0); t["bchain_len"] = _i(bchain_len)
+    t["bclev_adr"] = np.concatenate([[0], np.cumsum([int(np.sum(bclevel == L)) for L in range(nbclev)])]).astype(np.int32)
+    t["bclev_chain"] = _i(sorted(range(nbchain), key=lambda c: (bclevel[c], c)))
+    S("nbchain", nbchain); S("nbclev", nbclev)
     # reference point of every kinematic tree: the position of the tree's root body (a free root moves with
     # qpos[0:3]; a static root is a model constant).  MJX uses the subtree COM here; any fixed point gives the
     # same qM / qfrc_bias (DESIGN.md "reference point").
@@ -365,9 +386,9 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
     R("xpos", 3 * nbody); R("xquat", 4 * nbody); R("cdof", 6 * nv); R("crb", 10 * nbody)
     # U (6/dof) and pvec (6/dof) are contiguous: together they hold cvel/cacc (12/body) during the forward tree pass
     R("U", 6 * nv); R("pvec", max(6 * nv, 12 * nbody - 6 * nv)); R("Dinv", nv)
-    # T region: cfrc (tree passes) -> one 6x6 reduced articulated inertia per chain (aba_factor) -> contact geometry +
+    # T region: cfrc (tree passes) -> the reduced articulated inertia of every chain top, 36 + 10 floats (aba_factor) -> contact geometry +
     # wrenches + chain sums (solver)
-    R("T", max(6 * nbody, 36 * nchain, 18 * ncon + 6 * max(ncb, 1)))
+    R("T", max(6 * nbody, 46 * nchain, 18 * ncon + 6 * max(ncb, 1)))
     R("ref", 3 * max(len(roots), 1))
     R("actdot", max(na, 1))
     for v in ("qfrc_smooth", "qacc_smooth", "qacc", "search", "qfrc_c"):
