@@ -1248,7 +1248,7 @@ struct BtEnv {
       gauss = 0.5f * W::allsum(g);
       it++;
       }
-      if (!W::cta_any(active)) break;  // all warps of the CTA iterate together (done ones idle): see BtLanes::cta_sync
+      if (!active) break;  // no CTA barrier here: the warps share this loop's code whatever their iteration
     }
     niter = it;
     if (live) for (int i = lane; i < m.nv; i += G) warm()[i] = qacc()[i];
@@ -1261,24 +1261,21 @@ struct BtEnv {
   // returns false when stopped early by a debug stop point.
   BT_DEV bool substep(bool do_euler, int stop = BT_STOP_NONE) {
     // `live` is warp-uniform and `stop` / `do_euler` are CTA-uniform, so every warp of the CTA reaches every barrier
-    if (live) tree_forward();
     W::cta_sync();
+    if (live) tree_forward();
     if (stop == BT_STOP_TREE) return false;
     if (live) smooth_forces();
     if (stop == BT_STOP_SMOOTH) return false;
-    W::cta_sync();
     const float h = m.timestep;
     for (int phase = 0; phase < (do_euler ? 2 : 1); phase++) {
       if (live) aba_factor(phase ? h : 0.f);
       if (stop == BT_STOP_M || stop == BT_STOP_FACTOR) return false;
-      W::cta_sync();
       if (live) {
         if (phase == 0) mul_M(warm(), qfrc_c());  // qM * qacc_warmstart, consumed by the solver's warm-start test
         for (int i = lane; i < m.nv; i += G) xv()[i] = qfrc_smooth()[i] + (phase ? qfrc_c()[i] : 0.f);
         W::sync();
         solve(xv());
       }
-      W::cta_sync();
       if (phase == 0) {
         if (live) {
           for (int i = lane; i < m.nv; i += G) qacc_smooth()[i] = xv()[i];
@@ -1287,7 +1284,6 @@ struct BtEnv {
         if (stop == BT_STOP_QACC_SMOOTH) return false;
         if (live) collide();
         if (stop == BT_STOP_COLLISION) return false;
-        W::cta_sync();
         solve_constraints();
       }
     }
