@@ -1119,6 +1119,7 @@ struct BtEnv {
     const float scale = 1.0f / (m.meaninertia * nvf);
     int it = 0;
     bool active = live;
+    float pg_pMg = 0.f, g_pMg = 0.f;
     while (true) {
       if (active) {
       // ---- update_constraint: cost + forces + qfrc_constraint = J' f
@@ -1130,7 +1131,8 @@ struct BtEnv {
         cost = c + gauss;
       }
       // ---- update_gradient: grad = M a - qfrc_smooth - qfrc_constraint; Mgrad = M^-1 grad; Polak-Ribiere direction
-      float pg_pMg = 0.f, g_pMg = 0.f, gnorm2 = 0.f;
+      pg_pMg = 0.f; g_pMg = 0.f;
+      float gnorm2 = 0.f;
 #pragma unroll
       for (int sl = 0; sl < DS; sl++) {
         const int i = lane + sl * G;
@@ -1140,6 +1142,15 @@ struct BtEnv {
         gnorm2 += grad[sl] * grad[sl];
         if (i < m.nv) xv()[i] = grad[sl];
       }
+      gnorm2 = W::allsum(gnorm2);
+      // ---- termination test (MJX solve.cond); it does not involve Mgrad, so the M^-1 solve of the final pass is skipped
+      {
+        const float improvement = (prev_cost - cost) * scale;
+        const float gradient = sqrtf(gnorm2) * scale;
+        if (it >= m.iterations || improvement < m.tolerance || gradient < m.tolerance) active = false;
+      }
+      }
+      if (active) {
       W::sync();
       solve(xv());
       float g_Mg = 0.f;
@@ -1149,7 +1160,7 @@ struct BtEnv {
         Mgrad[sl] = i < m.nv ? xv()[i] : 0.f;
         g_Mg += grad[sl] * Mgrad[sl];
       }
-      pg_pMg = W::allsum(pg_pMg); g_pMg = W::allsum(g_pMg); g_Mg = W::allsum(g_Mg); gnorm2 = W::allsum(gnorm2);
+      pg_pMg = W::allsum(pg_pMg); g_pMg = W::allsum(g_pMg); g_Mg = W::allsum(g_Mg);
       float beta = 0.f;
       if (it > 0) {
         beta = (g_Mg - g_pMg) / (pg_pMg > BT_MINVAL ? pg_pMg : BT_MINVAL);
@@ -1162,12 +1173,6 @@ struct BtEnv {
         if (i < m.nv) search()[i] = -Mgrad[sl] + (it > 0 ? beta * search()[i] : 0.f);
       }
       W::sync();
-      // ---- termination test (MJX solve.cond)
-      const float improvement = (prev_cost - cost) * scale;
-      const float gradient = sqrtf(gnorm2) * scale;
-      if (it >= m.iterations || improvement < m.tolerance || gradient < m.tolerance) active = false;
-      }
-      if (active) {
       // ---- exact line search along `search` (MJX solver._linesearch)
       float jv[CS][4], ljv[DS];
       {
