@@ -76,11 +76,12 @@ struct BtEnv {
   BT_DEV float* warm() const { return s + m.o_warm; }
   BT_DEV float* xpos() const { return s + m.o_xpos; }
   BT_DEV float* xquat() const { return s + m.o_xquat; }
+  // one 12-float record per dof: S_k = cdof_k (6) then G_k = U_k / D_k (6); 16-byte aligned so the chain sweeps load it
+  // with three 128-bit shared-memory loads
   BT_DEV float* cdof() const { return s + m.o_cdof; }
   BT_DEV float* crb() const { return s + m.o_crb; }
-  BT_DEV float* Uv() const { return s + m.o_U; }      // U_k = A_k S_k (6 per dof); with pvec: cvel/cacc during the tree pass
-  BT_DEV float* pvec() const { return s + m.o_pvec; }  // 6 per dof: sweep state of solve() / mul_M()
   BT_DEV float* Dinv() const { return s + m.o_Dinv; }
+  BT_DEV float* pvec() const { return s + m.o_pvec; }  // 6 per dof: sweep state of solve() / mul_M(); with the vectors behind it: cvel/cacc in the tree pass
   BT_DEV float* T() const { return s + m.o_T; }
   BT_DEV float* ref() const { return s + m.o_ref; }
   BT_DEV float* aforce() const { return s + m.o_aforce; }
@@ -106,7 +107,7 @@ struct BtEnv {
   // `first`: the body starts a chain -> (pos, quat, cvel, cacc, rp) are loaded from the parent's stored state.
   BT_DEV void body_pose(int b, bool first, float pos[3], float quat[4], float cvel[6], float cacc[6], float rp[3]) {
     const int p = BT_LDG(m.body_parentid + b);
-    float* cv = Uv();  // cvel at 12*b, cacc at 12*b+6 (U and pvec are contiguous and not live during this pass)
+    float* cv = pvec();  // cvel at 12*b, cacc at 12*b+6 (pvec and the solver vectors behind it are not live during this pass)
     if (p == 0) {
       pos[0] = pos[1] = pos[2] = 0.f;
       quat[0] = 1.f; quat[1] = quat[2] = quat[3] = 0.f;
@@ -160,7 +161,7 @@ struct BtEnv {
         bt_quat_to_mat(quat, R);
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-          float* c = cdof() + 6 * (da + k);
+          float* c = cdof() + 12 * (da + k);
           c[0] = c[1] = c[2] = c[3] = c[4] = c[5] = 0.f;
           c[3 + k] = 1.f;
           cvel[3 + k] += qvel()[da + k];
@@ -171,7 +172,7 @@ struct BtEnv {
           float c[6], cd[6];
           c[0] = R[k]; c[1] = R[3 + k]; c[2] = R[6 + k];
           bt_cross(c, off, c + 3);
-          float* cs = cdof() + 6 * (da + 3 + k);
+          float* cs = cdof() + 12 * (da + 3 + k);
           const float qv = qvel()[da + 3 + k];
           bt_motion_cross(cvel, c, cd);
 #pragma unroll
@@ -202,7 +203,7 @@ struct BtEnv {
         bt_cross(c, off, c + 3);
         const float qv = qvel()[da];
         bt_motion_cross(cvel, c, cd);
-        float* cs = cdof() + 6 * da;
+        float* cs = cdof() + 12 * da;
 #pragma unroll
         for (int i = 0; i < 6; i++) { cs[i] = c[i]; cacc[i] += cd[i] * qv; cvel[i] += c[i] * qv; }
       }
@@ -217,7 +218,7 @@ struct BtEnv {
   }
 
   BT_DEV void body_local(int b) {
-    const float* cv = Uv();
+    const float* cv = pvec();
     float pos[3], quat[4], cvel[6], cacc[6], rp[3];
     const int rs = BT_LDG(m.body_ref + b);
 #pragma unroll
@@ -366,7 +367,7 @@ struct BtEnv {
 #pragma unroll
               for (int j = 0; j < 6; j++) f[j] += fb[j];
             }
-            qfrc_smooth()[k] = -bt_dot6(cdof() + 6 * k, f);
+            qfrc_smooth()[k] = -bt_dot6(cdof() + 12 * k, f);
           }
 #pragma unroll
           for (int j = 0; j < 6; j++) pv[6 * k0 + j] = f[j];
@@ -445,7 +446,7 @@ struct BtEnv {
             for (int j = 0; j < 10; j++) Ia[j] += ci_[j];
           }
 #pragma unroll
-          for (int j = 0; j < 6; j++) S[j] = cdof()[6 * k + j];
+          bt_ld6(cdof() + 12 * k, S);
           bt_inert_mul(Ia, S, w);
 #pragma unroll
           for (int i = 0; i < kNR; i++) {
@@ -464,12 +465,12 @@ struct BtEnv {
           if (on) {
 #pragma unroll
             for (int i = 0; i < kNR; i++) {
-              Uv()[6 * k + rl + i] = u[i];
               const float ui = u[i] * inv;
+              cdof()[12 * k + 6 + rl + i] = ui;  // G_k = U_k / D_k
+              if (rl + i == 0) Dinv()[k] = inv;
 #pragma unroll
               for (int j = 0; j < 6; j++) R[i][j] -= ui * U[j];
             }
-            if (rl == 0) Dinv()[k] = inv;
           }
         }
         if (on) {
@@ -488,8 +489,8 @@ struct BtEnv {
   }
 
   // x <- M^-1 x  (M = qM + diag(h * damping) of the last aba_factor): the articulated-body solve, two O(nv) sweeps
-  //   leaves->root:  p_k = sum_children pbar_c;  u_k = x_k - S_k . p_k;  pbar_k = p_k + U_k u_k / D_k
-  //   root->leaves:  a = a_parent;  x_k = (u_k - U_k . a) / D_k;  a_k = a + S_k x_k
+  //   leaves->root:  p_k = sum_children pbar_c;  u_k = x_k - S_k . p_k;  pbar_k = p_k + G_k u_k        (G_k = U_k / D_k)
+  //   root->leaves:  a = a_parent;  x_k = u_k / D_k - G_k . a;  a_k = a + S_k x_k
   // one lane per chain, p / a carried in registers along the chain
   BT_DEV void solve(float* x) {
     float* pv = pvec();
@@ -506,12 +507,12 @@ struct BtEnv {
         }
 #pragma unroll 2
         for (int k = kb; k >= k0; k--) {
-          const float u = x[k] - bt_dot6(cdof() + 6 * k, p);
-          uu[k] = u;
-          const float ud = u * Dinv()[k];
-          const float* U = Uv() + 6 * k;
+          float SG[12];
+          bt_ld12(cdof() + 12 * k, SG);
+          const float u = x[k] - bt_dot6(SG, p);
+          uu[k] = u * Dinv()[k];  // g_k = u_k / D_k, consumed by the root->leaves pass
 #pragma unroll
-          for (int j = 0; j < 6; j++) p[j] += U[j] * ud;
+          for (int j = 0; j < 6; j++) p[j] += SG[6 + j] * u;
         }
 #pragma unroll
         for (int j = 0; j < 6; j++) pv[6 * k0 + j] = p[j];
@@ -530,11 +531,13 @@ struct BtEnv {
         }
 #pragma unroll 2
         for (int k = k0; k <= kb; k++) {
-          const float xk = (uu[k] - bt_dot6(Uv() + 6 * k, a)) * Dinv()[k];
+          float SG[12];
+          bt_ld12(cdof() + 12 * k, SG);
+          // x_k = (u_k - U_k . a) / D_k = g_k - G_k . a
+          const float xk = uu[k] - bt_dot6(SG + 6, a);
           x[k] = xk;
-          const float* S = cdof() + 6 * k;
 #pragma unroll
-          for (int j = 0; j < 6; j++) a[j] += S[j] * xk;
+          for (int j = 0; j < 6; j++) a[j] += SG[j] * xk;
         }
 #pragma unroll
         for (int j = 0; j < 6; j++) pv[6 * kb + j] = a[j];
@@ -559,7 +562,7 @@ struct BtEnv {
         }
         for (int k = k0; k <= kb; k++) {
           const float vk = v[k];
-          const float* S = cdof() + 6 * k;
+          const float* S = cdof() + 12 * k;
 #pragma unroll
           for (int j = 0; j < 6; j++) { a[j] += S[j] * vk; pv[6 * k + j] = a[j]; }
         }
@@ -582,7 +585,7 @@ struct BtEnv {
           bt_inert_mul(I, pv + 6 * k, t);
 #pragma unroll
           for (int j = 0; j < 6; j++) f[j] += t[j];
-          y[k] = bt_dot6(cdof() + 6 * k, f) + BT_LDG(m.dof_armature + k) * v[k];
+          y[k] = bt_dot6(cdof() + 12 * k, f) + BT_LDG(m.dof_armature + k) * v[k];
         }
 #pragma unroll
         for (int j = 0; j < 6; j++) pv[6 * k0 + j] = f[j];
@@ -726,7 +729,7 @@ struct BtEnv {
 #pragma unroll 4
       for (int e = BT_LDG(m.cb_adr + cb); e < BT_LDG(m.cb_adr + cb + 1); e++) {
         const int d = BT_LDG(m.cb_dof + e);
-        acc += cdof()[6 * d + k] * v[d];
+        acc += cdof()[12 * d + k] * v[d];
       }
       cbA()[it] = acc;
     }
@@ -953,7 +956,7 @@ struct BtEnv {
         acc = e.lsg[sl] * lforce[sl];
 #pragma unroll 2
         for (int k = BT_LDG(m.dofcon_adr + i); k < BT_LDG(m.dofcon_adr + i + 1); k++)
-          acc += BT_LDG(m.dofcon_sign + k) * bt_dot6(cdof() + 6 * i, wrench() + 6 * BT_LDG(m.dofcon_c + k));
+          acc += BT_LDG(m.dofcon_sign + k) * bt_dot6(cdof() + 12 * i, wrench() + 6 * BT_LDG(m.dofcon_c + k));
         qfrc_c()[i] = acc;
       }
     }

@@ -104,6 +104,24 @@ BT_DEV float bt_rcp(float x) {
   return 1.0f / x;
 #endif
 }
+// 16-byte aligned 12-float record / its first 6 floats (shared memory): 128-bit loads on the device
+BT_DEV void bt_ld12(const float* p, float* o) {
+#ifdef __CUDACC__
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4), c = *reinterpret_cast<const float4*>(p + 8);
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w; o[8] = c.x; o[9] = c.y; o[10] = c.z; o[11] = c.w;
+#else
+  for (int j = 0; j < 12; j++) o[j] = p[j];
+#endif
+}
+BT_DEV void bt_ld6(const float* p, float* o) {
+#ifdef __CUDACC__
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float2 b = *reinterpret_cast<const float2*>(p + 4);
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y;
+#else
+  for (int j = 0; j < 6; j++) o[j] = p[j];
+#endif
+}
 BT_DEV float bt_clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
 // jnp.nan_to_num (fruitfly.py:569-570)
 BT_DEV float bt_nan_to_num(float x) {

@@ -16,7 +16,7 @@
   X(n_endeff_idxs) X(torso_idx) X(terminate_when_unhealthy) X(steps_for_cur_frame) X(episode_length)            \
   X(start_frame_range) X(obs_size)                                                                              \
   /* per-environment scratch layout (offsets in floats) */                                                      \
-  X(o_qpos) X(o_qvel) X(o_act) X(o_ctrl) X(o_warm) X(o_xpos) X(o_xquat) X(o_cdof) X(o_crb) X(o_U) X(o_pvec) X(o_Dinv)    \
+  X(o_qpos) X(o_qvel) X(o_act) X(o_ctrl) X(o_warm) X(o_xpos) X(o_xquat) X(o_cdof) X(o_crb) X(o_Dinv) X(o_pvec)    \
   X(o_T) X(o_ref) X(o_aforce) X(o_actdot) X(o_qfrc_smooth) X(o_qacc_smooth) X(o_qacc) X(o_x) X(o_search)        \
   X(o_qfrc_c) X(o_tmpv) X(smem_floats)
 

@@ -382,20 +382,31 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
         lay[name] = off
         off += int(n)
 
+    def ALIGN4():
+        nonlocal off
+        off += (-off) % 4
+
     R("qpos", nq); R("qvel", nv); R("act", max(na, 1)); R("ctrl", max(nu, 1)); R("warm", nv)
-    R("xpos", 3 * nbody); R("xquat", 4 * nbody); R("cdof", 6 * nv); R("crb", 10 * nbody)
-    # U (6/dof) and pvec (6/dof) are contiguous: together they hold cvel/cacc (12/body) during the forward tree pass
-    R("U", 6 * nv); R("pvec", max(6 * nv, 12 * nbody - 6 * nv)); R("Dinv", nv)
-    # T region: cfrc (tree passes) -> the reduced articulated inertia of every chain top, 36 + 10 floats (aba_factor) -> contact geometry +
-    # wrenches + chain sums (solver)
+    R("xpos", 3 * nbody); R("xquat", 4 * nbody)
+    ALIGN4()
+    R("cdof", 12 * nv)   # per dof: S_k = cdof_k (6) | G_k = U_k / D_k (6); 16-byte aligned records
+    R("crb", 10 * nbody); R("Dinv", nv)
+    # T region: cfrc (tree passes) -> the reduced articulated inertia of every chain top, 36 + 10 floats (aba_factor)
+    # -> contact geometry + wrenches + chain sums (solver)
     R("T", max(6 * nbody, 46 * nchain, 18 * ncon + 6 * max(ncb, 1)))
     R("ref", 3 * max(len(roots), 1))
     R("actdot", max(na, 1))
+    # pvec (sweep state, 6/dof) and the solver vectors behind it are contiguous: together they hold cvel/cacc (12/body)
+    # during the forward tree pass, when none of them is live
+    w12 = off
+    R("pvec", 6 * nv)
     for v in ("qfrc_smooth", "qacc_smooth", "qacc", "search", "qfrc_c"):
         R(v, nv)
     R("x", max(nv, nu))
+    if off - w12 < 12 * nbody:
+        off = w12 + 12 * nbody
     lay["aforce"] = lay["x"]            # actuator forces live only inside smooth_forces()
-    lay["tmpv"] = lay["qacc_smooth"]    # solve() temp (u_k): qacc_smooth is consumed (into registers) before the first CG solve
+    lay["tmpv"] = lay["qacc_smooth"]    # solve() temp (g_k): qacc_smooth is consumed (into registers) before the first CG solve
     for k, v in lay.items():
         S("o_" + k, v)
     off = max(off, lay["crb"] + obs_size)  # the observation row is staged over crb/LD/T at the end of the step

@@ -35,6 +35,7 @@ for l in dis.splitlines():
         locs.append(cur)
 agg = collections.defaultdict(lambda: [0, 0, 0])
 tot = [0, 0]
+last_key = "other"
 stall_cols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
 stalls = collections.defaultdict(lambda: collections.Counter())
 for k, r in enumerate(ins):
@@ -42,7 +43,10 @@ for k, r in enumerate(ins):
     # phases: outermost bt_impl.h frames, from the outside in
     impl_frames = [func_of(n) for f, n in chain if f == "bt_impl.h"]
     prog = [n for f, n in chain if f == "bt_programs.h"]
-    key = impl_frames[-1] if impl_frames else ("programs" if prog else "other")
+    key = impl_frames[-1] if impl_frames else ("programs" if prog else None)
+    if key is None:   # helper inlined from bt_math.h / intrinsics: attribute to the enclosing function in address order
+        key = last_key
+    last_key = key
     # a second-level key: e.g. solve called from solve_constraints
     n = int(r[ci["Instructions Executed"]] or 0); s = int(r[ci["# Samples"]] or 0); t = int(r[ci["Thread Instructions Executed"]] or 0)
     inner = impl_frames[0] if impl_frames else key
