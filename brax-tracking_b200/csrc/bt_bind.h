@@ -40,7 +40,7 @@ static inline int bt_bind(BtDev* d, int n, const char* const* names, const void*
       {"level_adr", d->nlevel + 1LL}, {"level_body", d->nbody - 1LL}, {"child_adr", d->nbody + 1LL},
       {"jnt_type", d->njnt}, {"qpos0", d->nq}, {"dof_bodyid", d->nv}, {"chain_k0", d->nchain}, {"chain_len", d->nchain},
       {"clev_adr", d->nclev + 1LL}, {"clev_chain", d->nchain}, {"dof_chain", d->nv}, {"dchild_adr", d->nv + 1LL}, {"dofbody_adr", d->nv + 1LL}, {"dof_range", 2LL * d->nv}, {"dof_solimp", 5LL * d->nv},
-      {"dofcon_adr", d->nv + 1LL}, {"dofact_adr", d->nv + 1LL}, {"act_wrap_adr", d->nu + 1LL}, {"cb_adr", d->ncb + 1LL},
+      {"dofcb_adr", d->nv + 1LL}, {"cbcon_adr", d->ncb + 1LL}, {"dofact_adr", d->nv + 1LL}, {"act_wrap_adr", d->nu + 1LL}, {"cb_adr", d->ncb + 1LL},
       {"clip_position", 3LL * d->clip_len}, {"clip_quaternion", 4LL * d->clip_len},
       {"clip_joints", (int64_t)d->clip_len * d->clip_nj}, {"clip_body_positions", 3LL * d->clip_len * d->nbody},
       {"clip_angular_velocity", 3LL * d->clip_len}, {"joint_idxs", d->n_joint_idxs}, {"body_idxs", d->n_body_idxs},

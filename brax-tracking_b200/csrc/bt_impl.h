@@ -130,8 +130,10 @@ struct BtEnv {
       float r[3], q2[4];
       bt_rotate(bp, quat, r);
       pos[0] += r[0]; pos[1] += r[1]; pos[2] += r[2];
-      bt_quat_mul(quat, bq, q2);
-      quat[0] = q2[0]; quat[1] = q2[1]; quat[2] = q2[2]; quat[3] = q2[3];
+      if (!(BT_LDG(m.body_flags + b) & 1)) {  // model-uniform branch: most body frames are only translated
+        bt_quat_mul(quat, bq, q2);
+        quat[0] = q2[0]; quat[1] = q2[1]; quat[2] = q2[2]; quat[3] = q2[3];
+      }
     }
     const int jadr = BT_LDG(m.body_jntadr + b), jnum = BT_LDG(m.body_jntnum + b);
     const int rs = BT_LDG(m.body_ref + b);
@@ -184,8 +186,12 @@ struct BtEnv {
         float jp[3] = {BT_LDG(m.jnt_pos + 3 * j), BT_LDG(m.jnt_pos + 3 * j + 1), BT_LDG(m.jnt_pos + 3 * j + 2)};
         float ja[3] = {BT_LDG(m.jnt_axis + 3 * j), BT_LDG(m.jnt_axis + 3 * j + 1), BT_LDG(m.jnt_axis + 3 * j + 2)};
         float anchor[3], c[6], r[3], ql[4], q2[4], cd[6];
-        bt_rotate(jp, quat, anchor);
-        anchor[0] += pos[0]; anchor[1] += pos[1]; anchor[2] += pos[2];
+        const bool at_origin = BT_LDG(m.jnt_flags + j) & 1;  // model-uniform branch
+        if (at_origin) { anchor[0] = pos[0]; anchor[1] = pos[1]; anchor[2] = pos[2]; }
+        else {
+          bt_rotate(jp, quat, anchor);
+          anchor[0] += pos[0]; anchor[1] += pos[1]; anchor[2] += pos[2];
+        }
         bt_rotate(ja, quat, c);
         const float ang = 0.5f * (qpos()[qa] - BT_LDG(m.qpos0 + qa));
         float sn, cs_;
@@ -197,8 +203,10 @@ struct BtEnv {
         ql[0] = cs_; ql[1] = ja[0] * sn; ql[2] = ja[1] * sn; ql[3] = ja[2] * sn;
         bt_quat_mul(quat, ql, q2);
         quat[0] = q2[0]; quat[1] = q2[1]; quat[2] = q2[2]; quat[3] = q2[3];
-        bt_rotate(jp, quat, r);
-        pos[0] = anchor[0] - r[0]; pos[1] = anchor[1] - r[1]; pos[2] = anchor[2] - r[2];
+        if (!at_origin) {
+          bt_rotate(jp, quat, r);
+          pos[0] = anchor[0] - r[0]; pos[1] = anchor[1] - r[1]; pos[2] = anchor[2] - r[2];
+        }
         float off[3] = {rp[0] - anchor[0], rp[1] - anchor[1], rp[2] - anchor[2]};
         bt_cross(c, off, c + 3);
         const float qv = qvel()[da];
@@ -948,15 +956,24 @@ struct BtEnv {
       w[0] = tq[0]; w[1] = tq[1]; w[2] = tq[2]; w[3] = F[0]; w[4] = F[1]; w[5] = F[2];
     }
     W::sync();
+    // wrench per contact BODY (8 for the rodent instead of 30 contacts), then one gather per dof over the contact bodies
+    // whose ancestor chain contains the dof
+    for (int it = lane; it < m.ncb * 6; it += G) {
+      const int cb = it / 6, j = it - cb * 6;
+      float acc = 0.f;
+      for (int k = BT_LDG(m.cbcon_adr + cb); k < BT_LDG(m.cbcon_adr + cb + 1); k++)
+        acc += BT_LDG(m.cbcon_sign + k) * wrench()[6 * BT_LDG(m.cbcon_c + k) + j];
+      cbA()[it] = acc;
+    }
+    W::sync();
 #pragma unroll
     for (int sl = 0; sl < DS; sl++) {
       const int i = lane + sl * G;
-      float acc = 0.f;
       if (i < m.nv) {
-        acc = e.lsg[sl] * lforce[sl];
-#pragma unroll 2
-        for (int k = BT_LDG(m.dofcon_adr + i); k < BT_LDG(m.dofcon_adr + i + 1); k++)
-          acc += BT_LDG(m.dofcon_sign + k) * bt_dot6(cdof() + 12 * i, wrench() + 6 * BT_LDG(m.dofcon_c + k));
+        float acc = e.lsg[sl] * lforce[sl];
+        float S[6];
+        bt_ld6(cdof() + 12 * i, S);
+        for (int k = BT_LDG(m.dofcb_adr + i); k < BT_LDG(m.dofcb_adr + i + 1); k++) acc += bt_dot6(S, cbA() + 6 * BT_LDG(m.dofcb_id + k));
         qfrc_c()[i] = acc;
       }
     }

@@ -30,14 +30,14 @@
 
 // ---- int tables ----
 #define BT_INT_TABLES(X) \
-  X(body_parentid) X(body_jntadr) X(body_jntnum) X(body_ref) X(level_adr) X(level_body) X(child_adr) X(child_id)\
+  X(body_parentid) X(body_jntadr) X(body_jntnum) X(body_ref) X(body_flags) X(level_adr) X(level_body) X(child_adr) X(child_id)\
   X(bchain_b0) X(bchain_len) X(bclev_adr) X(bclev_chain)                                                        \
-  X(jnt_type) X(jnt_qposadr) X(jnt_dofadr)                                                                      \
+  X(jnt_type) X(jnt_qposadr) X(jnt_dofadr) X(jnt_flags)                                                                      \
   X(dof_bodyid) X(dof_parentid) X(dof_qposadr) X(dof_limited)                                                   \
   X(chain_k0) X(chain_len) X(clev_adr) X(clev_chain) X(dof_chain) X(dchild_adr) X(dchild_id) X(dofbody_adr) X(dofbody_id)                                                                      \
   X(cgeom_bodyid) X(cb_adr) X(cb_dof) X(cb_ref)                                                                 \
   X(con_g1) X(con_g2) X(con_cb1) X(con_cb2) X(con_ref) X(con_fn) X(con_sub) X(con_dim)                          \
-  X(dofcon_adr) X(dofcon_c)                                                                                     \
+  X(cbcon_adr) X(cbcon_c) X(dofcb_adr) X(dofcb_id)                                                                                     \
   X(act_wrap_adr) X(act_wrap_qadr) X(act_wrap_dadr) X(dofact_adr) X(dofact_u)                                   \
   X(actuator_dyntype) X(actuator_gaintype) X(actuator_biastype) X(actuator_ctrllimited)                         \
   X(actuator_forcelimited) X(actuator_actadr)                                                                   \
@@ -50,7 +50,7 @@
   X(dof_stiffness) X(dof_springref) X(dof_armature) X(dof_damping) X(dof_range) X(dof_solref) X(dof_solimp)     \
   X(dof_margin) X(dof_invweight0)                                                                               \
   X(cgeom_pos) X(cgeom_quat) X(cgeom_size)                                                                      \
-  X(con_mu) X(con_solref) X(con_solimp) X(con_includemargin) X(con_invweight) X(dofcon_sign)                    \
+  X(con_mu) X(con_solref) X(con_solimp) X(con_includemargin) X(con_invweight) X(cbcon_sign)                    \
   X(act_wrap_coef) X(dofact_coef)                                                                               \
   X(actuator_gear) X(actuator_gainprm) X(actuator_biasprm) X(actuator_dynprm) X(actuator_ctrlrange)             \
   X(actuator_forcerange)                                                                                        \

@@ -103,6 +103,8 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
     t["body_jntadr"] = _i(a["body_jntadr"])
     t["body_jntnum"] = _i(a["body_jntnum"])
     t["body_ref"] = body_ref
+    # bit 0: body_quat is the identity (the frame composition with the parent is skipped)
+    t["body_flags"] = _i([int(np.abs(a["body_quat"][b] - np.array([1.0, 0, 0, 0])).max() == 0.0) for b in range(nbody)])
     t["level_adr"] = level_adr
     t["level_body"] = _i(order)
     t["child_adr"] = child_adr
@@ -123,6 +125,8 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
     # ------------------------------------------------------------------ joints / dofs
     t["jnt_type"] = _i(a["jnt_type"]); t["jnt_qposadr"] = _i(a["jnt_qposadr"]); t["jnt_dofadr"] = _i(a["jnt_dofadr"])
     t["jnt_pos"] = _f(a["jnt_pos"]); t["jnt_axis"] = _f(a["jnt_axis"])
+    # bit 0: the joint sits at the body origin (anchor = body position, no offset rotations)
+    t["jnt_flags"] = _i([int(np.abs(a["jnt_pos"][j]).max() == 0.0) for j in range(njnt)])
     t["qpos0"] = _f(a["qpos0"])
     dof_jnt = a["dof_jntid"]
     dof_qadr = np.full(nv, -1, dtype=np.int32)
@@ -280,22 +284,30 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
         m2 = a["body_lastdof"][c["b2"]] >= 0
         if m1 and m2 and body_ref[c["b1"]] != body_ref[c["b2"]]:
             raise NotImplementedError("contacts between two different kinematic trees need per-tree wrenches")
-    # per-dof gather list of contacts (sign +1 for body2's chain, -1 for body1's chain; common ancestors cancel)
-    dofcon = [[] for _ in range(nv)]
+    # J' f in two gathers: contact -> contact body (sign +1 when the body is geom2's, -1 when it is geom1's), then
+    # contact body -> every dof on its ancestor chain (common ancestors of a two-body contact cancel in the sum)
+    cbcon = [[] for _ in range(max(ncb, 1))]
     for ci, c in enumerate(con):
-        ch1 = set(chain(c["b1"])); ch2 = set(chain(c["b2"]))
-        for d in ch2 - ch1:
-            dofcon[d].append((ci, 1.0))
-        for d in ch1 - ch2:
-            dofcon[d].append((ci, -1.0))
-    dofcon_adr, dofcon_c, dofcon_s = [0], [], []
+        if c["b2"] in cb_slot:
+            cbcon[cb_slot[c["b2"]]].append((ci, 1.0))
+        if c["b1"] in cb_slot:
+            cbcon[cb_slot[c["b1"]]].append((ci, -1.0))
+    cbcon_adr, cbcon_c, cbcon_s = [0], [], []
+    for k in range(ncb):
+        for ci, sg in cbcon[k]:
+            cbcon_c.append(ci); cbcon_s.append(sg)
+        cbcon_adr.append(len(cbcon_c))
+    dofcb = [[] for _ in range(nv)]
+    for k, b in enumerate(cbs):
+        for d in chain(b):
+            dofcb[d].append(k)
+    dofcb_adr, dofcb_id = [0], []
     for d in range(nv):
-        for ci, s in sorted(dofcon[d]):
-            dofcon_c.append(ci); dofcon_s.append(s)
-        dofcon_adr.append(len(dofcon_c))
-    t["dofcon_adr"] = _i(dofcon_adr)
-    t["dofcon_c"] = _i(dofcon_c) if dofcon_c else Z(1, np.int32)
-    t["dofcon_sign"] = _f(dofcon_s) if dofcon_s else Z(1, np.float32)
+        dofcb_id.extend(dofcb[d])
+        dofcb_adr.append(len(dofcb_id))
+    t["cbcon_adr"] = _i(cbcon_adr); t["cbcon_c"] = _i(cbcon_c) if cbcon_c else Z(1, np.int32)
+    t["cbcon_sign"] = _f(cbcon_s) if cbcon_s else Z(1, np.float32)
+    t["dofcb_adr"] = _i(dofcb_adr); t["dofcb_id"] = _i(dofcb_id) if dofcb_id else Z(1, np.int32)
 
     # ------------------------------------------------------------------ actuators
     wrap_adr, wrap_q, wrap_coef = [0], [], []
