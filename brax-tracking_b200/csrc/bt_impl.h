@@ -417,58 +417,62 @@ struct BtEnv {
       for (int j = 0; j < 10; j++) I10[j] += ci[j];
     }
   }
-  // The articulated inertia is kept split as A = Iacc + R: Iacc = plain sum of the link inertias outboard of the dof
-  // (10 numbers, applied with bt_inert_mul -- no 6x6 expansion) and R = the accumulated rank-1 downdates (6x6; lane r of
-  // the chain's 8-lane group owns row r).  Per chain the parent receives 36 + 10 floats.
+  // Lane r of a chain's 8-lane group owns row r of the 6x6 articulated inertia A.  Row r of a link's spatial inertia
+  // [[Ibar, [h]x], [-[h]x, m 1]] is six signed picks out of its 10 numbers: the per-row index / sign tables below turn
+  // the 6x6 expansion into six lane-indexed shared-memory loads (no selects).
   BT_DEV void aba_factor(float hdamp) {
     const int grp = lane / kGrp, rl = lane % kGrp;
-    float* Ab = T();  // 46 floats per chain: R (36) and Iacc (10) of the chain top, handed to the parent chain
+    float* Ab = T();  // 36 floats per chain: reduced articulated inertia of the chain top, handed to the parent chain
+    // idx (4 bits each) and sign (2 bits each: 0 -> 0, 1 -> +1, 2 -> -1) of row r, packed
+    const unsigned kIdx[6] = {0x780430u, 0x608513u, 0x067254u, 0x009780u, 0x090608u, 0x900067u};
+    const unsigned kSgn[6] = {0x615u, 0x855u, 0x195u, 0x064u, 0x112u, 0x409u};
+    int ix[kNR][6];
+    float sg[kNR][6];
+#pragma unroll
+    for (int i = 0; i < kNR; i++) {
+      const int r = (rl + i) < 6 ? (rl + i) : 0;
+      unsigned pi = kIdx[0], ps = kSgn[0];
+#pragma unroll
+      for (int q = 1; q < 6; q++) { pi = r == q ? kIdx[q] : pi; ps = r == q ? kSgn[q] : ps; }
+#pragma unroll
+      for (int j = 0; j < 6; j++) {
+        ix[i][j] = (pi >> (4 * j)) & 15;
+        const unsigned c = (ps >> (2 * j)) & 3;
+        sg[i][j] = c == 0 ? 0.f : (c == 1 ? 1.f : -1.f);
+      }
+    }
     for (int cl = m.nclev - 1; cl >= 0; cl--) {
       const int c0 = BT_LDG(m.clev_adr + cl), c1 = BT_LDG(m.clev_adr + cl + 1);
       for (int ci = c0 + grp; ci < c1; ci += G / kGrp) {
         const int c = BT_LDG(m.clev_chain + ci), k0 = BT_LDG(m.chain_k0 + c), kb = k0 + BT_LDG(m.chain_len + c) - 1;
         const bool on = rl < 6;
-        float R[kNR][6], Ia[10];
+        float a[kNR][6];
 #pragma unroll
         for (int i = 0; i < kNR; i++)
 #pragma unroll
-          for (int j = 0; j < 6; j++) R[i][j] = 0.f;
-#pragma unroll
-        for (int j = 0; j < 10; j++) Ia[j] = 0.f;
-        for (int e = BT_LDG(m.dchild_adr + kb); e < BT_LDG(m.dchild_adr + kb + 1); e++) {
-          const float* cr = Ab + 46 * BT_LDG(m.dof_chain + BT_LDG(m.dchild_id + e));
-          if (on) {
+          for (int j = 0; j < 6; j++) a[i][j] = 0.f;
+        if (on)
+          for (int e = BT_LDG(m.dchild_adr + kb); e < BT_LDG(m.dchild_adr + kb + 1); e++) {
+            const float* cr = Ab + 36 * BT_LDG(m.dof_chain + BT_LDG(m.dchild_id + e));
 #pragma unroll
             for (int i = 0; i < kNR; i++)
 #pragma unroll
-              for (int j = 0; j < 6; j++) R[i][j] += cr[6 * (rl + i) + j];
+              for (int j = 0; j < 6; j++) a[i][j] += cr[6 * (rl + i) + j];
           }
-#pragma unroll
-          for (int j = 0; j < 10; j++) Ia[j] += cr[36 + j];
-        }
         for (int k = kb; k >= k0; k--) {
-          float S[6], w[6], u[kNR], U[6];
+          float S[6], u[kNR], U[6];
           for (int e = BT_LDG(m.dofbody_adr + k); e < BT_LDG(m.dofbody_adr + k + 1); e++) {
             const float* ci_ = crb() + 10 * BT_LDG(m.dofbody_id + e);
 #pragma unroll
-            for (int j = 0; j < 10; j++) Ia[j] += ci_[j];
-          }
+            for (int i = 0; i < kNR; i++)
 #pragma unroll
+              for (int j = 0; j < 6; j++) a[i][j] += sg[i][j] * ci_[ix[i][j]];
+          }
           bt_ld6(cdof() + 12 * k, S);
-          bt_inert_mul(Ia, S, w);
 #pragma unroll
-          for (int i = 0; i < kNR; i++) {
-            const int r = rl + i;
-            float wr = w[0];
-            wr = r == 1 ? w[1] : wr; wr = r == 2 ? w[2] : wr; wr = r == 3 ? w[3] : wr; wr = r == 4 ? w[4] : wr; wr = r == 5 ? w[5] : wr;
-            u[i] = wr;
-#pragma unroll
-            for (int j = 0; j < 6; j++) u[i] += R[i][j] * S[j];
-          }
+          for (int i = 0; i < kNR; i++) u[i] = bt_dot6(a[i], S);
           W::template gather6<kNR>(u, U, lane);
-          float D = BT_LDG(m.dof_armature + k) + hdamp * BT_LDG(m.dof_damping + k);
-#pragma unroll
-          for (int j = 0; j < 6; j++) D += S[j] * U[j];
+          const float D = BT_LDG(m.dof_armature + k) + hdamp * BT_LDG(m.dof_damping + k) + bt_dot6(S, U);
           const float inv = bt_rcp(D);
           if (on) {
 #pragma unroll
@@ -477,7 +481,7 @@ struct BtEnv {
               cdof()[12 * k + 6 + rl + i] = ui;  // G_k = U_k / D_k
               if (rl + i == 0) Dinv()[k] = inv;
 #pragma unroll
-              for (int j = 0; j < 6; j++) R[i][j] -= ui * U[j];
+              for (int j = 0; j < 6; j++) a[i][j] -= ui * U[j];
             }
           }
         }
@@ -485,11 +489,7 @@ struct BtEnv {
 #pragma unroll
           for (int i = 0; i < kNR; i++)
 #pragma unroll
-            for (int j = 0; j < 6; j++) Ab[46 * c + 6 * (rl + i) + j] = R[i][j];
-        }
-        if (rl == 0) {
-#pragma unroll
-          for (int j = 0; j < 10; j++) Ab[46 * c + 36 + j] = Ia[j];
+            for (int j = 0; j < 6; j++) Ab[36 * c + 6 * (rl + i) + j] = a[i][j];
         }
       }
       W::sync();

@@ -403,9 +403,9 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
     ALIGN4()
     R("cdof", 12 * nv)   # per dof: S_k = cdof_k (6) | G_k = U_k / D_k (6); 16-byte aligned records
     R("crb", 10 * nbody); R("Dinv", nv)
-    # T region: cfrc (tree passes) -> the reduced articulated inertia of every chain top, 36 + 10 floats (aba_factor)
+    # T region: cfrc (tree passes) -> the 6x6 reduced articulated inertia of every chain top (aba_factor)
     # -> contact geometry + wrenches + chain sums (solver)
-    R("T", max(6 * nbody, 46 * nchain, 18 * ncon + 6 * max(ncb, 1)))
+    R("T", max(6 * nbody, 36 * nchain, 18 * ncon + 6 * max(ncb, 1)))
     R("ref", 3 * max(len(roots), 1))
     R("actdot", max(na, 1))
     # pvec (sweep state, 6/dof) and the solver vectors behind it are contiguous: together they hold cvel/cacc (12/body)
