@@ -99,100 +99,41 @@ struct BtEnv {
   BT_DEV float* cbA() const { return T() + 18 * m.ncon; }               // [ncb][6]
 
   // ================================================================== P1: forward tree pass
-  // (MJX: smooth.kinematics, com_pos, com_vel, rne forward half, passive fluid), in two parts:
-  //  * body_pose: the recursion proper -- pose, cdof, cvel / cdof_dot / cacc -- walked chain by chain (maximal single-child
-  //    body paths, consecutive body ids) by ONE lane per chain with the parent state carried in registers;
-  //  * body_local: everything that only needs the body's own pose and velocity (inertia about the reference point, RNE
-  //    body force, fluid forces), one lane per body, all bodies in parallel.
-  // `first`: the body starts a chain -> (pos, quat, cvel, cacc, rp) are loaded from the parent's stored state.
-  BT_DEV void body_pose(int b, bool first, float pos[3], float quat[4], float cvel[6], float cacc[6], float rp[3]) {
-    const int p = BT_LDG(m.body_parentid + b);
-    float* cv = pvec();  // cvel at 12*b, cacc at 12*b+6 (pvec and the solver vectors behind it are not live during this pass)
-    if (p == 0) {
-      pos[0] = pos[1] = pos[2] = 0.f;
-      quat[0] = 1.f; quat[1] = quat[2] = quat[3] = 0.f;
-#pragma unroll
-      for (int k = 0; k < 6; k++) cvel[k] = 0.f;
-      cacc[0] = cacc[1] = cacc[2] = 0.f;
-      cacc[3] = -m.grav_x; cacc[4] = -m.grav_y; cacc[5] = -m.grav_z;
-    } else if (first) {
-#pragma unroll
-      for (int k = 0; k < 3; k++) pos[k] = xpos()[3 * p + k];
-#pragma unroll
-      for (int k = 0; k < 4; k++) quat[k] = xquat()[4 * p + k];
-#pragma unroll
-      for (int k = 0; k < 6; k++) { cvel[k] = cv[12 * p + k]; cacc[k] = cv[12 * p + 6 + k]; }
-    }
-    {
-      float bp[3] = {BT_LDG(m.body_pos + 3 * b), BT_LDG(m.body_pos + 3 * b + 1), BT_LDG(m.body_pos + 3 * b + 2)};
-      float bq[4] = {BT_LDG(m.body_quat + 4 * b), BT_LDG(m.body_quat + 4 * b + 1), BT_LDG(m.body_quat + 4 * b + 2),
-                     BT_LDG(m.body_quat + 4 * b + 3)};
-      float r[3], q2[4];
-      bt_rotate(bp, quat, r);
-      pos[0] += r[0]; pos[1] += r[1]; pos[2] += r[2];
-      if (!(BT_LDG(m.body_flags + b) & 1)) {  // model-uniform branch: most body frames are only translated
-        bt_quat_mul(quat, bq, q2);
-        quat[0] = q2[0]; quat[1] = q2[1]; quat[2] = q2[2]; quat[3] = q2[3];
-      }
-    }
+  // (MJX: smooth.kinematics, com_pos, com_vel, rne forward half, passive fluid), in five parts so that
+  // only a frame composition (pose) and a 12-float recursion (velocity) remain serial:
+  //  * body_frame  (lane per body)      the body's frame RELATIVE TO ITS PARENT after its own joints (sincos, local
+  //                                      quaternion products), local joint anchors / axes;
+  //  * compose     (lane per body chain) world pose = parent pose o local frame, carried in registers along the chain;
+  //  * joint_cdof  (lane per joint)      world anchor / axis -> cdof (the S half of the dof records);
+  //  * vel_sweep   (lane per dof chain)  cvel / cdof_dot / cacc, carried in registers along the chain;
+  //  * body_local  (lane per body)       inertia about the reference point, RNE body force, fluid forces.
+  BT_DEV void body_frame(int b) {
+    float p[3] = {BT_LDG(m.body_pos + 3 * b), BT_LDG(m.body_pos + 3 * b + 1), BT_LDG(m.body_pos + 3 * b + 2)};
+    float q[4] = {BT_LDG(m.body_quat + 4 * b), BT_LDG(m.body_quat + 4 * b + 1), BT_LDG(m.body_quat + 4 * b + 2),
+                  BT_LDG(m.body_quat + 4 * b + 3)};
     const int jadr = BT_LDG(m.body_jntadr + b), jnum = BT_LDG(m.body_jntnum + b);
-    const int rs = BT_LDG(m.body_ref + b);
-    if (p == 0) {
-      if (jnum > 0 && BT_LDG(m.jnt_type + jadr) == BT_JNT_FREE) {
-        const int qa = BT_LDG(m.jnt_qposadr + jadr);
-        rp[0] = qpos()[qa]; rp[1] = qpos()[qa + 1]; rp[2] = qpos()[qa + 2];
-      } else {
-        rp[0] = pos[0]; rp[1] = pos[1]; rp[2] = pos[2];
-      }
-      ref()[3 * rs] = rp[0]; ref()[3 * rs + 1] = rp[1]; ref()[3 * rs + 2] = rp[2];
-    } else if (first) {
-      rp[0] = ref()[3 * rs]; rp[1] = ref()[3 * rs + 1]; rp[2] = ref()[3 * rs + 2];
-    }
     for (int jj = 0; jj < jnum; jj++) {
       const int j = jadr + jj, qa = BT_LDG(m.jnt_qposadr + j), da = BT_LDG(m.jnt_dofadr + j);
       if (BT_LDG(m.jnt_type + j) == BT_JNT_FREE) {
-        pos[0] = qpos()[qa]; pos[1] = qpos()[qa + 1]; pos[2] = qpos()[qa + 2];
-        quat[0] = qpos()[qa + 3]; quat[1] = qpos()[qa + 4]; quat[2] = qpos()[qa + 5]; quat[3] = qpos()[qa + 6];
-        {  // x / norm(x), as mjx math.normalize
-          const float nrm = sqrtf(quat[0] * quat[0] + quat[1] * quat[1] + quat[2] * quat[2] + quat[3] * quat[3]);
-          quat[0] /= nrm; quat[1] /= nrm; quat[2] /= nrm; quat[3] /= nrm;
-        }
+        // a free joint hangs off the world: the "local" frame is the absolute pose
+        p[0] = qpos()[qa]; p[1] = qpos()[qa + 1]; p[2] = qpos()[qa + 2];
+        q[0] = qpos()[qa + 3]; q[1] = qpos()[qa + 4]; q[2] = qpos()[qa + 5]; q[3] = qpos()[qa + 6];
+        const float nrm = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);  // x / norm(x), as mjx math.normalize
+        q[0] /= nrm; q[1] /= nrm; q[2] /= nrm; q[3] /= nrm;
         // MJX kinematics stores the normalised quaternion back into qpos
-        qpos()[qa + 3] = quat[0]; qpos()[qa + 4] = quat[1]; qpos()[qa + 5] = quat[2]; qpos()[qa + 6] = quat[3];
-        float R[9], off[3] = {rp[0] - pos[0], rp[1] - pos[1], rp[2] - pos[2]};
-        bt_quat_to_mat(quat, R);
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          float* c = cdof() + 12 * (da + k);
-          c[0] = c[1] = c[2] = c[3] = c[4] = c[5] = 0.f;
-          c[3 + k] = 1.f;
-          cvel[3 + k] += qvel()[da + k];
-        }
-        float dv[6] = {0, 0, 0, 0, 0, 0};
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          float c[6], cd[6];
-          c[0] = R[k]; c[1] = R[3 + k]; c[2] = R[6 + k];
-          bt_cross(c, off, c + 3);
-          float* cs = cdof() + 12 * (da + 3 + k);
-          const float qv = qvel()[da + 3 + k];
-          bt_motion_cross(cvel, c, cd);
-#pragma unroll
-          for (int i = 0; i < 6; i++) { cs[i] = c[i]; cacc[i] += cd[i] * qv; dv[i] += c[i] * qv; }
-        }
-#pragma unroll
-        for (int i = 0; i < 6; i++) cvel[i] += dv[i];
+        qpos()[qa + 3] = q[0]; qpos()[qa + 4] = q[1]; qpos()[qa + 5] = q[2]; qpos()[qa + 6] = q[3];
       } else {
         float jp[3] = {BT_LDG(m.jnt_pos + 3 * j), BT_LDG(m.jnt_pos + 3 * j + 1), BT_LDG(m.jnt_pos + 3 * j + 2)};
         float ja[3] = {BT_LDG(m.jnt_axis + 3 * j), BT_LDG(m.jnt_axis + 3 * j + 1), BT_LDG(m.jnt_axis + 3 * j + 2)};
-        float anchor[3], c[6], r[3], ql[4], q2[4], cd[6];
         const bool at_origin = BT_LDG(m.jnt_flags + j) & 1;  // model-uniform branch
-        if (at_origin) { anchor[0] = pos[0]; anchor[1] = pos[1]; anchor[2] = pos[2]; }
-        else {
-          bt_rotate(jp, quat, anchor);
-          anchor[0] += pos[0]; anchor[1] += pos[1]; anchor[2] += pos[2];
+        float anchor[3] = {p[0], p[1], p[2]}, axis[3], r[3], ql[4], q2[4];
+        if (!at_origin) {
+          bt_rotate(jp, q, r);
+          anchor[0] += r[0]; anchor[1] += r[1]; anchor[2] += r[2];
         }
-        bt_rotate(ja, quat, c);
+        bt_rotate(ja, q, axis);
+        float* rec = cdof() + 12 * da;  // local axis / anchor, turned into cdof by joint_cdof()
+        rec[0] = axis[0]; rec[1] = axis[1]; rec[2] = axis[2]; rec[3] = anchor[0]; rec[4] = anchor[1]; rec[5] = anchor[2];
         const float ang = 0.5f * (qpos()[qa] - BT_LDG(m.qpos0 + qa));
         float sn, cs_;
 #ifdef __CUDACC__
@@ -201,28 +142,52 @@ struct BtEnv {
         sn = sinf(ang); cs_ = cosf(ang);
 #endif
         ql[0] = cs_; ql[1] = ja[0] * sn; ql[2] = ja[1] * sn; ql[3] = ja[2] * sn;
-        bt_quat_mul(quat, ql, q2);
-        quat[0] = q2[0]; quat[1] = q2[1]; quat[2] = q2[2]; quat[3] = q2[3];
+        bt_quat_mul(q, ql, q2);
+        q[0] = q2[0]; q[1] = q2[1]; q[2] = q2[2]; q[3] = q2[3];
         if (!at_origin) {
-          bt_rotate(jp, quat, r);
-          pos[0] = anchor[0] - r[0]; pos[1] = anchor[1] - r[1]; pos[2] = anchor[2] - r[2];
+          bt_rotate(jp, q, r);
+          p[0] = anchor[0] - r[0]; p[1] = anchor[1] - r[1]; p[2] = anchor[2] - r[2];
         }
-        float off[3] = {rp[0] - anchor[0], rp[1] - anchor[1], rp[2] - anchor[2]};
-        bt_cross(c, off, c + 3);
-        const float qv = qvel()[da];
-        bt_motion_cross(cvel, c, cd);
-        float* cs = cdof() + 12 * da;
-#pragma unroll
-        for (int i = 0; i < 6; i++) { cs[i] = c[i]; cacc[i] += cd[i] * qv; cvel[i] += c[i] * qv; }
       }
     }
-    bt_quat_normalize(quat);
 #pragma unroll
-    for (int k = 0; k < 3; k++) xpos()[3 * b + k] = pos[k];
+    for (int k = 0; k < 3; k++) xpos()[3 * b + k] = p[k];
 #pragma unroll
-    for (int k = 0; k < 4; k++) xquat()[4 * b + k] = quat[k];
+    for (int k = 0; k < 4; k++) xquat()[4 * b + k] = q[k];
+  }
+
+  BT_DEV void joint_cdof(int j) {
+    const int b = BT_LDG(m.jnt_bodyid + j), p = BT_LDG(m.body_parentid + b), da = BT_LDG(m.jnt_dofadr + j);
+    const int rs = BT_LDG(m.body_ref + b);
+    const float rp[3] = {ref()[3 * rs], ref()[3 * rs + 1], ref()[3 * rs + 2]};
+    if (BT_LDG(m.jnt_type + j) == BT_JNT_FREE) {
+      float R[9];
+      bt_quat_to_mat(xquat() + 4 * b, R);
+      const float off[3] = {rp[0] - xpos()[3 * b], rp[1] - xpos()[3 * b + 1], rp[2] - xpos()[3 * b + 2]};
 #pragma unroll
-    for (int k = 0; k < 6; k++) { cv[12 * b + k] = cvel[k]; cv[12 * b + 6 + k] = cacc[k]; }
+      for (int k = 0; k < 3; k++) {
+        float* c = cdof() + 12 * (da + k);
+        c[0] = c[1] = c[2] = c[3] = c[4] = c[5] = 0.f;
+        c[3 + k] = 1.f;
+        float* cr = cdof() + 12 * (da + 3 + k);
+        float ax[3] = {R[k], R[3 + k], R[6 + k]}, lin[3];
+        bt_cross(ax, off, lin);
+        cr[0] = ax[0]; cr[1] = ax[1]; cr[2] = ax[2]; cr[3] = lin[0]; cr[4] = lin[1]; cr[5] = lin[2];
+      }
+      return;
+    }
+    float* rec = cdof() + 12 * da;
+    float al[3] = {rec[0], rec[1], rec[2]}, nl[3] = {rec[3], rec[4], rec[5]}, ax[3], an[3], lin[3];
+    if (p == 0) {
+      ax[0] = al[0]; ax[1] = al[1]; ax[2] = al[2]; an[0] = nl[0]; an[1] = nl[1]; an[2] = nl[2];
+    } else {
+      bt_rotate(al, xquat() + 4 * p, ax);
+      bt_rotate(nl, xquat() + 4 * p, an);
+      an[0] += xpos()[3 * p]; an[1] += xpos()[3 * p + 1]; an[2] += xpos()[3 * p + 2];
+    }
+    const float off[3] = {rp[0] - an[0], rp[1] - an[1], rp[2] - an[2]};
+    bt_cross(ax, off, lin);
+    rec[0] = ax[0]; rec[1] = ax[1]; rec[2] = ax[2]; rec[3] = lin[0]; rec[4] = lin[1]; rec[5] = lin[2];
   }
 
   BT_DEV void body_local(int b) {
@@ -233,8 +198,16 @@ struct BtEnv {
     for (int k = 0; k < 3; k++) { pos[k] = xpos()[3 * b + k]; rp[k] = ref()[3 * rs + k]; }
 #pragma unroll
     for (int k = 0; k < 4; k++) quat[k] = xquat()[4 * b + k];
+    const int ld = BT_LDG(m.body_lastdof + b);  // last dof on the chain root -> body: the body moves with it
+    if (ld >= 0) {
 #pragma unroll
-    for (int k = 0; k < 6; k++) { cvel[k] = cv[12 * b + k]; cacc[k] = cv[12 * b + 6 + k]; }
+      for (int k = 0; k < 6; k++) { cvel[k] = cv[12 * ld + k]; cacc[k] = cv[12 * ld + 6 + k]; }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 6; k++) cvel[k] = 0.f;
+      cacc[0] = cacc[1] = cacc[2] = 0.f;
+      cacc[3] = -m.grav_x; cacc[4] = -m.grav_y; cacc[5] = -m.grav_z;
+    }
     // body inertia about the tree reference point, world axes
     const float mass = BT_LDG(m.body_mass + b);
     float ci[10], cf[6];
@@ -308,12 +281,80 @@ struct BtEnv {
       xpos()[0] = xpos()[1] = xpos()[2] = 0.f;
       xquat()[0] = 1.f; xquat()[1] = xquat()[2] = xquat()[3] = 0.f;
     }
+    for (int b = 1 + lane; b < m.nbody; b += G) body_frame(b);
+    W::sync();
+    // ---- compose: world pose = parent pose o local frame
     for (int cl = 0; cl < m.nbclev; cl++) {
       const int c0 = BT_LDG(m.bclev_adr + cl), c1 = BT_LDG(m.bclev_adr + cl + 1);
       for (int ci = c0 + lane; ci < c1; ci += G) {
         const int c = BT_LDG(m.bclev_chain + ci), b0 = BT_LDG(m.bchain_b0 + c), b1 = b0 + BT_LDG(m.bchain_len + c);
-        float pos[3], quat[4], cvel[6], cacc[6], rp[3];
-        for (int b = b0; b < b1; b++) body_pose(b, b == b0, pos, quat, cvel, cacc, rp);
+        const int p = BT_LDG(m.body_parentid + b0);
+        float pos[3], quat[4];
+#pragma unroll
+        for (int k = 0; k < 3; k++) pos[k] = xpos()[3 * p + k];
+#pragma unroll
+        for (int k = 0; k < 4; k++) quat[k] = xquat()[4 * p + k];
+        for (int b = b0; b < b1; b++) {
+          float pl[3] = {xpos()[3 * b], xpos()[3 * b + 1], xpos()[3 * b + 2]}, r[3];
+          bt_rotate(pl, quat, r);
+          pos[0] += r[0]; pos[1] += r[1]; pos[2] += r[2];
+          if (!(BT_LDG(m.body_flags + b) & 2)) {  // model-uniform: jointless bodies with an identity frame only translate
+            float ql[4] = {xquat()[4 * b], xquat()[4 * b + 1], xquat()[4 * b + 2], xquat()[4 * b + 3]}, q2[4];
+            bt_quat_mul(quat, ql, q2);
+            quat[0] = q2[0]; quat[1] = q2[1]; quat[2] = q2[2]; quat[3] = q2[3];
+            bt_quat_normalize(quat);
+          }
+#pragma unroll
+          for (int k = 0; k < 3; k++) xpos()[3 * b + k] = pos[k];
+#pragma unroll
+          for (int k = 0; k < 4; k++) xquat()[4 * b + k] = quat[k];
+          if (b == b0 && p == 0) {  // reference point of the tree = position of its root body
+            const int rs = BT_LDG(m.body_ref + b);
+            ref()[3 * rs] = pos[0]; ref()[3 * rs + 1] = pos[1]; ref()[3 * rs + 2] = pos[2];
+          }
+        }
+      }
+      W::sync();
+    }
+    for (int j = lane; j < m.njnt; j += G) joint_cdof(j);
+    W::sync();
+    // ---- velocity sweep on the dof chains: inclusive cvel / cacc per dof (12 floats) in the pvec.. region
+    float* cv = pvec();
+    for (int cl = 0; cl < m.nclev; cl++) {
+      const int c0 = BT_LDG(m.clev_adr + cl), c1 = BT_LDG(m.clev_adr + cl + 1);
+      for (int ci = c0 + lane; ci < c1; ci += G) {
+        const int c = BT_LDG(m.clev_chain + ci), k0 = BT_LDG(m.chain_k0 + c), kb = k0 + BT_LDG(m.chain_len + c) - 1;
+        const int par = BT_LDG(m.dof_parentid + k0);
+        float cvel[6], cacc[6], snap[6];
+        if (par >= 0) {
+#pragma unroll
+          for (int i = 0; i < 6; i++) { cvel[i] = cv[12 * par + i]; cacc[i] = cv[12 * par + 6 + i]; }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 6; i++) cvel[i] = 0.f;
+          cacc[0] = cacc[1] = cacc[2] = 0.f;
+          cacc[3] = -m.grav_x; cacc[4] = -m.grav_y; cacc[5] = -m.grav_z;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; i++) snap[i] = cvel[i];
+        for (int k = k0; k <= kb; k++) {
+          float S[6], cd[6];
+          bt_ld6(cdof() + 12 * k, S);
+          const float qv = qvel()[k];
+          const int vf = BT_LDG(m.dof_vflag + k);  // 0 hinge, 1 free translation, 2 first / 3 later free rotation dof
+          if (vf == 2) {
+#pragma unroll
+            for (int i = 0; i < 6; i++) snap[i] = cvel[i];
+          }
+          if (vf != 1) {
+            // MuJoCo: the three rotational dofs of a free joint all use the velocity after its translational dofs
+            bt_motion_cross(vf >= 2 ? snap : cvel, S, cd);
+#pragma unroll
+            for (int i = 0; i < 6; i++) cacc[i] += cd[i] * qv;
+          }
+#pragma unroll
+          for (int i = 0; i < 6; i++) { cvel[i] += S[i] * qv; cv[12 * k + i] = cvel[i]; cv[12 * k + 6 + i] = cacc[i]; }
+        }
       }
       W::sync();
     }

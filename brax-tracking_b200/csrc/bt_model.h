@@ -30,10 +30,10 @@
 
 // ---- int tables ----
 #define BT_INT_TABLES(X) \
-  X(body_parentid) X(body_jntadr) X(body_jntnum) X(body_ref) X(body_flags) X(level_adr) X(level_body) X(child_adr) X(child_id)\
+  X(body_parentid) X(body_jntadr) X(body_jntnum) X(body_ref) X(body_flags) X(body_lastdof) X(level_adr) X(level_body) X(child_adr) X(child_id)\
   X(bchain_b0) X(bchain_len) X(bclev_adr) X(bclev_chain)                                                        \
-  X(jnt_type) X(jnt_qposadr) X(jnt_dofadr) X(jnt_flags)                                                                      \
-  X(dof_bodyid) X(dof_parentid) X(dof_qposadr) X(dof_limited)                                                   \
+  X(jnt_type) X(jnt_qposadr) X(jnt_dofadr) X(jnt_flags) X(jnt_bodyid)                                                                      \
+  X(dof_bodyid) X(dof_parentid) X(dof_qposadr) X(dof_limited) X(dof_vflag)                                                   \
   X(chain_k0) X(chain_len) X(clev_adr) X(clev_chain) X(dof_chain) X(dchild_adr) X(dchild_id) X(dofbody_adr) X(dofbody_id)                                                                      \
   X(cgeom_bodyid) X(cb_adr) X(cb_dof) X(cb_ref)                                                                 \
   X(con_g1) X(con_g2) X(con_cb1) X(con_cb2) X(con_ref) X(con_fn) X(con_sub) X(con_dim)                          \

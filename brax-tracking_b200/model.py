@@ -103,8 +103,10 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
     t["body_jntadr"] = _i(a["body_jntadr"])
     t["body_jntnum"] = _i(a["body_jntnum"])
     t["body_ref"] = body_ref
-    # bit 0: body_quat is the identity (the frame composition with the parent is skipped)
-    t["body_flags"] = _i([int(np.abs(a["body_quat"][b] - np.array([1.0, 0, 0, 0])).max() == 0.0) for b in range(nbody)])
+    # bit 0: body_quat is the identity; bit 1: additionally no joints -> the local frame is a pure translation
+    ident = [int(np.abs(a["body_quat"][b] - np.array([1.0, 0, 0, 0])).max() == 0.0) for b in range(nbody)]
+    t["body_flags"] = _i([ident[b] | (2 if ident[b] and a["body_jntnum"][b] == 0 else 0) for b in range(nbody)])
+    t["body_lastdof"] = _i(a["body_lastdof"])
     t["level_adr"] = level_adr
     t["level_body"] = _i(order)
     t["child_adr"] = child_adr
@@ -127,6 +129,11 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
     t["jnt_pos"] = _f(a["jnt_pos"]); t["jnt_axis"] = _f(a["jnt_axis"])
     # bit 0: the joint sits at the body origin (anchor = body position, no offset rotations)
     t["jnt_flags"] = _i([int(np.abs(a["jnt_pos"][j]).max() == 0.0) for j in range(njnt)])
+    t["jnt_bodyid"] = _i(a["jnt_bodyid"])
+    for j in range(njnt):
+        if a["jnt_type"][j] == mjcf.JNT_FREE:
+            bj = a["jnt_bodyid"][j]
+            assert parent[bj] == 0 and a["body_jntnum"][bj] == 1, "free joints must be the only joint of a tree root"
     t["qpos0"] = _f(a["qpos0"])
     dof_jnt = a["dof_jntid"]
     dof_qadr = np.full(nv, -1, dtype=np.int32)
@@ -147,6 +154,13 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
             dof_solimp[i] = a["jnt_solimp"][j]
             dof_margin[i] = a["jnt_margin"][j]
     t["dof_bodyid"] = _i(a["dof_bodyid"]); t["dof_parentid"] = _i(a["dof_parentid"])
+    # velocity-sweep flag: 0 hinge, 1 free translation, 2 first / 3 later rotational dof of a free joint
+    vflag = np.zeros(nv, dtype=np.int32)
+    for j in range(njnt):
+        if a["jnt_type"][j] == mjcf.JNT_FREE:
+            d0 = a["jnt_dofadr"][j]
+            vflag[d0:d0 + 3] = 1; vflag[d0 + 3] = 2; vflag[d0 + 4:d0 + 6] = 3
+    t["dof_vflag"] = vflag
     t["dof_qposadr"] = dof_qadr; t["dof_limited"] = dof_lim
     t["dof_stiffness"] = _f(dof_stiff); t["dof_springref"] = _f(dof_spring)
     t["dof_armature"] = _f(a["dof_armature"]); t["dof_damping"] = _f(a["dof_damping"])
@@ -408,15 +422,15 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
     R("T", max(6 * nbody, 36 * nchain, 18 * ncon + 6 * max(ncb, 1)))
     R("ref", 3 * max(len(roots), 1))
     R("actdot", max(na, 1))
-    # pvec (sweep state, 6/dof) and the solver vectors behind it are contiguous: together they hold cvel/cacc (12/body)
+    # pvec (sweep state, 6/dof) and the solver vectors behind it are contiguous: together they hold cvel/cacc (12/dof)
     # during the forward tree pass, when none of them is live
     w12 = off
     R("pvec", 6 * nv)
     for v in ("qfrc_smooth", "qacc_smooth", "qacc", "search", "qfrc_c"):
         R(v, nv)
     R("x", max(nv, nu))
-    if off - w12 < 12 * nbody:
-        off = w12 + 12 * nbody
+    if off - w12 < 12 * nv:    # inclusive cvel / cacc per dof during the velocity sweep
+        off = w12 + 12 * nv
     lay["aforce"] = lay["x"]            # actuator forces live only inside smooth_forces()
     lay["tmpv"] = lay["qacc_smooth"]    # solve() temp (g_k): qacc_smooth is consumed (into registers) before the first CG solve
     for k, v in lay.items():
