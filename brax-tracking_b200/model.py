@@ -209,6 +209,19 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
     t["dof_chain"] = dof_chain
     t["dchild_adr"] = _i(dchild_adr); t["dchild_id"] = _i(dchild_id) if dchild_id else np.zeros(1, np.int32)
     t["dofbody_adr"] = _i(dofbody_adr); t["dofbody_id"] = _i(dofbody_id) if dofbody_id else np.zeros(1, np.int32)
+    # link records: the inertia / RNE force of all bodies carried by a dof are summed into the slot of its FIRST body
+    # (tree_forward's merge pass), so the serial sweeps read one record per dof: dof_irec = that body, or -1
+    dof_irec = np.full(nv, -1, dtype=np.int32)
+    merge_adr, merge_dst, merge_src = [0], [], []
+    for i in range(nv):
+        if dofbody[i]:
+            dof_irec[i] = dofbody[i][0]
+            if len(dofbody[i]) > 1:
+                merge_dst.append(dofbody[i][0]); merge_src.extend(dofbody[i][1:]); merge_adr.append(len(merge_src))
+    S("nmerge", len(merge_dst))
+    t["dof_irec"] = dof_irec; t["merge_adr"] = _i(merge_adr)
+    t["merge_dst"] = _i(merge_dst) if merge_dst else np.zeros(1, np.int32)
+    t["merge_src"] = _i(merge_src) if merge_src else np.zeros(1, np.int32)
 
     def chain(body):
         out, d = [], a["body_lastdof"][body]
