@@ -83,6 +83,10 @@ struct BtEnv {
   BT_DEV float* cdof() const { return s + m.o_cdof; }
   BT_DEV float* crb() const { return s + m.o_crb; }
   BT_DEV float* Dinv() const { return s + m.o_Dinv; }
+  BT_DEV float* Dd() const { return s + m.o_Dd; }  // the pivots D_k themselves (mul_M through the factor)
+  // ancestor-chain sums of cdof * v per contact body, by-products of the root->leaves sweeps: slot 0 v = qvel (velocity
+  // sweep), 1 v = qacc_warmstart (mulM_down), 2 v = qacc_smooth (solve_down)
+  BT_DEV float* cbJ(int slot) const { return s + m.o_cbJ + slot * 6 * m.ncb; }
   BT_DEV float* pvec() const { return s + m.o_pvec; }  // 6 per dof: sweep state of solve() / mul_M(); with the vectors behind it: cvel/cacc in the tree pass
   BT_DEV float* T() const { return s + m.o_T; }
   BT_DEV float* ref() const { return s + m.o_ref; }
@@ -356,6 +360,11 @@ struct BtEnv {
           }
 #pragma unroll
           for (int i = 0; i < 6; i++) { cvel[i] += S[i] * qv; cv[12 * k + i] = cvel[i]; cv[12 * k + 6 + i] = cacc[i]; }
+          const int cbi = BT_LDG(m.dof_cb + k);
+          if (cbi >= 0) {
+#pragma unroll
+            for (int i = 0; i < 6; i++) cbJ(0)[6 * cbi + i] = cvel[i];
+          }
         }
       }
       W::sync();
@@ -468,11 +477,6 @@ struct BtEnv {
   static constexpr int kGrp = G >= 8 ? 8 : 1;     // lanes per chain in aba_factor
   static constexpr int kNR = G >= 8 ? 1 : 6;      // inertia rows per lane
 
-  BT_DEV void link_inertia(int k, float I10[10]) const {
-    const int rb = BT_LDG(m.dof_irec + k);
-#pragma unroll
-    for (int j = 0; j < 10; j++) I10[j] = rb >= 0 ? crb()[10 * rb + j] : 0.f;
-  }
   // Lane r of a chain's 8-lane group owns row r of the 6x6 articulated inertia A.  Row r of a link's spatial inertia
   // [[Ibar, [h]x], [-[h]x, m 1]] is six signed picks out of its 10 numbers: the per-row index / sign tables below turn
   // the 6x6 expansion into six lane-indexed shared-memory loads (no selects).
@@ -552,7 +556,7 @@ struct BtEnv {
             for (int i = 0; i < kNR; i++) {
               const float ui = u[i] * inv;
               cdof()[12 * k + 6 + rl + i] = ui;  // G_k = U_k / D_k
-              if (rl + i == 0) Dinv()[k] = inv;
+              if (rl + i == 0) { Dinv()[k] = inv; Dd()[k] = D; }
 #pragma unroll
               for (int j = 0; j < 6; j++) a[i][j] -= ui * U[j];
             }
@@ -570,21 +574,32 @@ struct BtEnv {
   }
 
   // x <- M^-1 x  (M = qM + diag(h * damping) of the last aba_factor): the articulated-body solve, two O(nv) sweeps
-  //   leaves->root:  p_k = sum_children pbar_c;  u_k = x_k - S_k . p_k;  pbar_k = p_k + G_k u_k        (G_k = U_k / D_k)
-  //   root->leaves:  a = a_parent;  x_k = u_k / D_k - G_k . a;  a_k = a + S_k x_k
-  // one lane per chain, p / a carried in registers along the chain
-  BT_DEV void solve(float* x) {
+  //   leaves->root (solve_up):   p_k = sum_children pbar_c;  u_k = x_k - S_k . p_k;  pbar_k = p_k + G_k u_k     (G_k = U_k / D_k)
+  //   root->leaves (solve_down): a = a_parent;  x_k = u_k / D_k - G_k . a;  a_k = a + S_k x_k
+  // one lane per chain, p / a carried in registers along the chain.  Run backwards, the same recursions apply M:
+  //   root->leaves (mulM_down):  w_k = D_k (v_k + G_k . a);  a_k = a + S_k v_k
+  //   leaves->root:              y_k = w_k + S_k . q_k;  qbar_k = q_k + G_k w_k
+  // and the second half rides in solve_up<true> on the record loads of the smooth solve (two independent dependency
+  // chains in one instruction stream).  a_k is the spatial acceleration of the bodies behind dof k: stored at the last dof
+  // of every contact body it IS the ancestor-chain sum the constraint Jacobian needs (cbout).
+  template <bool kDual>
+  BT_DEV void solve_up(float* x, const float* w, float* y) {
     float* pv = pvec();
+    float* qv = T();  // second accumulator per chain top (the T region is idle between aba_factor and collide)
     float* uu = tmpv();
     for (int cl = m.nclev - 1; cl >= 0; cl--) {
       const int c0 = BT_LDG(m.clev_adr + cl), c1 = BT_LDG(m.clev_adr + cl + 1);
       for (int ci = c0 + lane; ci < c1; ci += G) {
         const int c = BT_LDG(m.clev_chain + ci), k0 = BT_LDG(m.chain_k0 + c), kb = k0 + BT_LDG(m.chain_len + c) - 1;
-        float p[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float p[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, q[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int e = BT_LDG(m.dchild_adr + kb); e < BT_LDG(m.dchild_adr + kb + 1); e++) {
-          const float* pc = pv + 6 * BT_LDG(m.dchild_id + e);
+          const int ch = BT_LDG(m.dchild_id + e);
 #pragma unroll
-          for (int j = 0; j < 6; j++) p[j] += pc[j];
+          for (int j = 0; j < 6; j++) p[j] += pv[6 * ch + j];
+          if (kDual) {
+#pragma unroll
+            for (int j = 0; j < 6; j++) q[j] += qv[6 * ch + j];
+          }
         }
 #pragma unroll 2
         for (int k = kb; k >= k0; k--) {
@@ -594,12 +609,26 @@ struct BtEnv {
           uu[k] = u * Dinv()[k];  // g_k = u_k / D_k, consumed by the root->leaves pass
 #pragma unroll
           for (int j = 0; j < 6; j++) p[j] += SG[6 + j] * u;
+          if (kDual) {
+            const float wk = w[k];
+            y[k] = wk + bt_dot6(SG, q);
+#pragma unroll
+            for (int j = 0; j < 6; j++) q[j] += SG[6 + j] * wk;
+          }
         }
 #pragma unroll
         for (int j = 0; j < 6; j++) pv[6 * k0 + j] = p[j];
+        if (kDual) {
+#pragma unroll
+          for (int j = 0; j < 6; j++) qv[6 * k0 + j] = q[j];
+        }
       }
       W::sync();
     }
+  }
+  BT_DEV void solve_down(float* x, float* cbout) {
+    float* pv = pvec();
+    float* uu = tmpv();
     for (int cl = 0; cl < m.nclev; cl++) {
       const int c0 = BT_LDG(m.clev_adr + cl), c1 = BT_LDG(m.clev_adr + cl + 1);
       for (int ci = c0 + lane; ci < c1; ci += G) {
@@ -619,6 +648,11 @@ struct BtEnv {
           x[k] = xk;
 #pragma unroll
           for (int j = 0; j < 6; j++) a[j] += SG[j] * xk;
+          const int cbi = cbout ? BT_LDG(m.dof_cb + k) : -1;
+          if (cbi >= 0) {
+#pragma unroll
+            for (int j = 0; j < 6; j++) cbout[6 * cbi + j] = a[j];
+          }
         }
 #pragma unroll
         for (int j = 0; j < 6; j++) pv[6 * kb + j] = a[j];
@@ -626,10 +660,12 @@ struct BtEnv {
       W::sync();
     }
   }
-
-  // y = qM v without qM: inverse dynamics at zero velocity (a_k = a_parent + S_k v_k; f_k = I_k a_k + sum_children f_c;
-  // y_k = S_k . f_k + armature_k v_k); same chain schedule as solve()
-  BT_DEV void mul_M(const float* v, float* y) {
+  BT_DEV void solve(float* x, float* cbout) {
+    solve_up<false>(x, nullptr, nullptr);
+    solve_down(x, cbout);
+  }
+  // first half of y = M v through the factor (the second half runs inside solve_up<true>)
+  BT_DEV void mulM_down(const float* v, float* w, float* cbout) {
     float* pv = pvec();
     for (int cl = 0; cl < m.nclev; cl++) {
       const int c0 = BT_LDG(m.clev_adr + cl), c1 = BT_LDG(m.clev_adr + cl + 1);
@@ -641,35 +677,22 @@ struct BtEnv {
 #pragma unroll
           for (int j = 0; j < 6; j++) a[j] = pv[6 * par + j];
         }
+#pragma unroll 2
         for (int k = k0; k <= kb; k++) {
+          float SG[12];
+          bt_ld12(cdof() + 12 * k, SG);
           const float vk = v[k];
-          const float* S = cdof() + 12 * k;
+          w[k] = Dd()[k] * (vk + bt_dot6(SG + 6, a));
 #pragma unroll
-          for (int j = 0; j < 6; j++) { a[j] += S[j] * vk; pv[6 * k + j] = a[j]; }
-        }
-      }
-      W::sync();
-    }
-    for (int cl = m.nclev - 1; cl >= 0; cl--) {
-      const int c0 = BT_LDG(m.clev_adr + cl), c1 = BT_LDG(m.clev_adr + cl + 1);
-      for (int ci = c0 + lane; ci < c1; ci += G) {
-        const int c = BT_LDG(m.clev_chain + ci), k0 = BT_LDG(m.chain_k0 + c), kb = k0 + BT_LDG(m.chain_len + c) - 1;
-        float f[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int e = BT_LDG(m.dchild_adr + kb); e < BT_LDG(m.dchild_adr + kb + 1); e++) {
-          const float* fc = pv + 6 * BT_LDG(m.dchild_id + e);
+          for (int j = 0; j < 6; j++) a[j] += SG[j] * vk;
+          const int cbi = BT_LDG(m.dof_cb + k);
+          if (cbi >= 0) {
 #pragma unroll
-          for (int j = 0; j < 6; j++) f[j] += fc[j];
-        }
-        for (int k = kb; k >= k0; k--) {
-          float I[10], t[6];
-          link_inertia(k, I);
-          bt_inert_mul(I, pv + 6 * k, t);
-#pragma unroll
-          for (int j = 0; j < 6; j++) f[j] += t[j];
-          y[k] = bt_dot6(cdof() + 12 * k, f) + BT_LDG(m.dof_armature + k) * v[k];
+            for (int j = 0; j < 6; j++) cbout[6 * cbi + j] = a[j];
+          }
         }
 #pragma unroll
-        for (int j = 0; j < 6; j++) pv[6 * k0 + j] = f[j];
+        for (int j = 0; j < 6; j++) pv[6 * kb + j] = a[j];
       }
       W::sync();
     }
@@ -801,20 +824,9 @@ struct BtEnv {
   }
 
   // ================================================================== matrix-free constraint Jacobian
-  // out[sl][k] = frame_k . (J_point(body2) - J_point(body1)) v   for lane-owned contacts
-  BT_DEV void jdot(const float* v, float out[CS][3]) {
-    const int nitem = m.ncb * 6;
-    for (int it = lane; it < nitem; it += G) {
-      const int cb = it / 6, k = it - cb * 6;
-      float acc = 0.f;
-#pragma unroll 4
-      for (int e = BT_LDG(m.cb_adr + cb); e < BT_LDG(m.cb_adr + cb + 1); e++) {
-        const int d = BT_LDG(m.cb_dof + e);
-        acc += cdof()[12 * d + k] * v[d];
-      }
-      cbA()[it] = acc;
-    }
-    W::sync();
+  // out[sl][k] = frame_k . (J_point(body2) - J_point(body1)) v   for lane-owned contacts, from the per-contact-body
+  // ancestor-chain sums `cbs` = sum_{d in chain(cb)} cdof_d v_d left behind by the root->leaves sweep that handled v
+  BT_DEV void jproj(const float* cbs, float out[CS][3]) {
 #pragma unroll
     for (int sl = 0; sl < CS; sl++) {
       const int c = lane + sl * G;
@@ -822,15 +834,14 @@ struct BtEnv {
       if (c >= m.ncon) continue;
       const int cb1 = BT_LDG(m.con_cb1 + c), cb2 = BT_LDG(m.con_cb2 + c);
       float A[6] = {0, 0, 0, 0, 0, 0};
-      if (cb2 >= 0) for (int k = 0; k < 6; k++) A[k] += cbA()[6 * cb2 + k];
-      if (cb1 >= 0) for (int k = 0; k < 6; k++) A[k] -= cbA()[6 * cb1 + k];
+      if (cb2 >= 0) for (int k = 0; k < 6; k++) A[k] += cbs[6 * cb2 + k];
+      if (cb1 >= 0) for (int k = 0; k < 6; k++) A[k] -= cbs[6 * cb1 + k];
       const float* cg = congeo() + 12 * c;
       float w[3];
       bt_cross(A, cg, w);
       w[0] += A[3]; w[1] += A[4]; w[2] += A[5];
       out[sl][0] = bt_dot3(cg + 3, w); out[sl][1] = bt_dot3(cg + 6, w); out[sl][2] = bt_dot3(cg + 9, w);
     }
-    W::sync();
   }
 
   // ================================================================== constraint rows (registers)
@@ -1153,7 +1164,7 @@ struct BtEnv {
       for (int c = 0; c < 3; c++) {
         const float* vec = c == 0 ? qvel() : (c == 1 ? warm() : qacc_smooth());
         float jb[CS][3];
-        jdot(vec, jb);
+        jproj(cbJ(c), jb);
         if (c == 0) {
           make_rows(e, jb, aref, laref);
           continue;
@@ -1207,6 +1218,9 @@ struct BtEnv {
     float grad[DS], Mgrad[DS], mv[DS];
 #pragma unroll
     for (int sl = 0; sl < DS; sl++) grad[sl] = Mgrad[sl] = mv[sl] = 0.f;
+    float sb[CS][3];  // J * search in the contact frames, carried by the same recurrence as the search direction
+#pragma unroll
+    for (int sl = 0; sl < CS; sl++) sb[sl][0] = sb[sl][1] = sb[sl][2] = 0.f;
     float cost = INFINITY, prev_cost = 0.f;
     const float nvf = (float)(m.nv > 1 ? m.nv : 1);
     const float scale = 1.0f / (m.meaninertia * nvf);
@@ -1245,7 +1259,7 @@ struct BtEnv {
       }
       if (active) {
       W::sync();
-      solve(xv());
+      solve(xv(), cbA());  // leaves the ancestor-chain sums of Mgrad in cbA
       float g_Mg = 0.f;
 #pragma unroll
       for (int sl = 0; sl < DS; sl++) {
@@ -1269,10 +1283,15 @@ struct BtEnv {
       // ---- exact line search along `search` (MJX solver._linesearch)
       float jv[CS][4], ljv[DS];
       {
-        float sb[CS][3];
-        jdot(search(), sb);
+        // search = -Mgrad + beta * search  =>  J search = -J Mgrad + beta * J search
+        float mb[CS][3];
+        jproj(cbA(), mb);
 #pragma unroll
-        for (int sl = 0; sl < CS; sl++) row_combine(e, sl, sb[sl], jv[sl]);
+        for (int sl = 0; sl < CS; sl++) {
+#pragma unroll
+          for (int k = 0; k < 3; k++) sb[sl][k] = -mb[sl][k] + (it > 0 ? beta * sb[sl][k] : 0.f);
+          row_combine(e, sl, sb[sl], jv[sl]);
+        }
       }
       float sn = 0.f, g1 = 0.f, g2 = 0.f;
 #pragma unroll
@@ -1369,10 +1388,16 @@ struct BtEnv {
       if (live) aba_factor(phase ? h : 0.f);
       if (stop == BT_STOP_M || stop == BT_STOP_FACTOR) return false;
       if (live) {
-        if (phase == 0) mul_M(warm(), qfrc_c());  // qM * qacc_warmstart, consumed by the solver's warm-start test
         for (int i = lane; i < m.nv; i += G) xv()[i] = qfrc_smooth()[i] + (phase ? qfrc_c()[i] : 0.f);
-        W::sync();
-        solve(xv());
+        if (phase == 0) {
+          // qM * qacc_warmstart (consumed by the solver's warm-start test) through the factor, fused with the smooth solve
+          mulM_down(warm(), qacc(), cbJ(1));
+          solve_up<true>(xv(), qacc(), qfrc_c());
+        } else {
+          W::sync();
+          solve_up<false>(xv(), nullptr, nullptr);
+        }
+        solve_down(xv(), phase == 0 ? cbJ(2) : nullptr);
       }
       if (phase == 0) {
         if (live) {

@@ -16,7 +16,7 @@
   X(n_endeff_idxs) X(torso_idx) X(terminate_when_unhealthy) X(steps_for_cur_frame) X(episode_length)            \
   X(start_frame_range) X(obs_size)                                                                              \
   /* per-environment scratch layout (offsets in floats) */                                                      \
-  X(o_qpos) X(o_qvel) X(o_act) X(o_ctrl) X(o_warm) X(o_xpos) X(o_xquat) X(o_cdof) X(o_crb) X(o_Dinv) X(o_pvec)    \
+  X(o_qpos) X(o_qvel) X(o_act) X(o_ctrl) X(o_warm) X(o_xpos) X(o_xquat) X(o_cdof) X(o_crb) X(o_Dinv) X(o_Dd) X(o_cbJ) X(o_pvec)    \
   X(o_T) X(o_ref) X(o_aforce) X(o_actdot) X(o_qfrc_smooth) X(o_qacc_smooth) X(o_qacc) X(o_x) X(o_search)        \
   X(o_qfrc_c) X(o_tmpv) X(smem_floats)
 
@@ -37,7 +37,7 @@
   X(chain_k0) X(chain_len) X(clev_adr) X(clev_chain) X(dof_chain) X(dchild_adr) X(dchild_id) X(dofbody_adr) X(dofbody_id) X(dof_irec) X(merge_adr) X(merge_dst) X(merge_src)                                                                     \
   X(cgeom_bodyid) X(cb_adr) X(cb_dof) X(cb_ref)                                                                 \
   X(con_g1) X(con_g2) X(con_cb1) X(con_cb2) X(con_ref) X(con_fn) X(con_sub) X(con_dim)                          \
-  X(cbcon_adr) X(cbcon_c) X(dofcb_adr) X(dofcb_id)                                                                                     \
+  X(cbcon_adr) X(cbcon_c) X(dofcb_adr) X(dofcb_id) X(dof_cb)                                                                                     \
   X(act_wrap_adr) X(act_wrap_qadr) X(act_wrap_dadr) X(dofact_adr) X(dofact_u)                                   \
   X(actuator_dyntype) X(actuator_gaintype) X(actuator_biastype) X(actuator_ctrllimited)                         \
   X(actuator_forcelimited) X(actuator_actadr)                                                                   \

@@ -271,14 +271,22 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
     t["cgeom_quat"] = _f([a["geom_quat"][g] for g in cgeoms]) if cgeoms else np.zeros(4, np.float32)
     t["cgeom_size"] = _f([a["geom_size"][g] for g in cgeoms]) if cgeoms else np.zeros(3, np.float32)
     # contact bodies (bodies that carry dofs and appear in a contact): chain lists for the matrix-free J
-    cbs, cb_slot = [], {}
+    # keyed by the body's last dof: bodies riding on the same dof share one slot (same chain, same sums)
+    cbs, cb_slot, dof_slot = [], {}, {}
     for c in con:
         for b in (c["b1"], c["b2"]):
-            if a["body_lastdof"][b] >= 0 and b not in cb_slot:
-                cb_slot[b] = len(cbs)
-                cbs.append(b)
+            d = int(a["body_lastdof"][b])
+            if d >= 0 and b not in cb_slot:
+                if d not in dof_slot:
+                    dof_slot[d] = len(cbs)
+                    cbs.append(b)
+                cb_slot[b] = dof_slot[d]
     ncb = len(cbs)
     S("ncb", ncb)
+    dof_cb = np.full(nv, -1, dtype=np.int32)  # contact-body slot whose chain ends at this dof
+    for d, k in dof_slot.items():
+        dof_cb[d] = k
+    t["dof_cb"] = dof_cb
     cb_adr, cb_dof = [0], []
     for b in cbs:
         cb_dof.extend(chain(b))
@@ -429,10 +437,11 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
     R("xpos", 3 * nbody); R("xquat", 4 * nbody)
     ALIGN4()
     R("cdof", 12 * nv)   # per dof: S_k = cdof_k (6) | G_k = U_k / D_k (6); 16-byte aligned records
-    R("crb", 10 * nbody); R("Dinv", nv)
+    R("crb", 10 * nbody); R("Dinv", nv); R("Dd", nv)
+    R("cbJ", 18 * max(ncb, 1))   # three sets of per-contact-body chain sums (qvel, qacc_warmstart, qacc_smooth)
     # T region: cfrc (tree passes) -> the 6x6 reduced articulated inertia of every chain top (aba_factor)
     # -> contact geometry + wrenches + chain sums (solver)
-    R("T", max(6 * nbody, 36 * nchain, 18 * ncon + 6 * max(ncb, 1)))
+    R("T", max(6 * nbody, 36 * nchain, 6 * nv, 18 * ncon + 6 * max(ncb, 1)))
     R("ref", 3 * max(len(roots), 1))
     R("actdot", max(na, 1))
     # pvec (sweep state, 6/dof) and the solver vectors behind it are contiguous: together they hold cvel/cacc (12/dof)
