@@ -360,14 +360,14 @@ struct BtEnv {
           }
 #pragma unroll
           for (int i = 0; i < 6; i++) { cvel[i] += S[i] * qv; cv[12 * k + i] = cvel[i]; cv[12 * k + 6 + i] = cacc[i]; }
-          const int cbi = BT_LDG(m.dof_cb + k);
-          if (cbi >= 0) {
-#pragma unroll
-            for (int i = 0; i < 6; i++) cbJ(0)[6 * cbi + i] = cvel[i];
-          }
         }
       }
       W::sync();
+    }
+    // J qvel chain sums: cvel at the last dof of every contact body
+    for (int it = lane; it < 6 * m.ncb; it += G) {
+      const int cb = it / 6, j = it - 6 * cb;
+      cbJ(0)[it] = cv[12 * BT_LDG(m.cb_lastdof + cb) + j];
     }
     for (int b = 1 + lane; b < m.nbody; b += G) body_local(b);
     W::sync();
@@ -582,6 +582,8 @@ struct BtEnv {
   // and the second half rides in solve_up<true> on the record loads of the smooth solve (two independent dependency
   // chains in one instruction stream).  a_k is the spatial acceleration of the bodies behind dof k: stored at the last dof
   // of every contact body it IS the ancestor-chain sum the constraint Jacobian needs (cbout).
+  // The per-dof loops are software-pipelined by hand (two register sets, the next dof's record is in flight while the
+  // current one is consumed): the recursion is one dependent chain per lane, so shared-memory latency is otherwise exposed.
   template <bool kDual>
   BT_DEV void solve_up(float* x, const float* w, float* y) {
     float* pv = pvec();
@@ -601,21 +603,32 @@ struct BtEnv {
             for (int j = 0; j < 6; j++) q[j] += qv[6 * ch + j];
           }
         }
-#pragma unroll 2
-        for (int k = kb; k >= k0; k--) {
-          float SG[12];
-          bt_ld12(cdof() + 12 * k, SG);
-          const float u = x[k] - bt_dot6(SG, p);
-          uu[k] = u * Dinv()[k];  // g_k = u_k / D_k, consumed by the root->leaves pass
+        auto load = [&](int k, float (&R)[12], float& xk, float& dk, float& wk) {
+          bt_ld12(cdof() + 12 * k, R);
+          xk = x[k]; dk = Dinv()[k];
+          if (kDual) wk = w[k];
+        };
+        auto step = [&](const float (&R)[12], float xk, float dk, float wk, int k) {
+          const float u = xk - bt_dot6(R, p);
+          uu[k] = u * dk;  // g_k = u_k / D_k, consumed by the root->leaves pass
 #pragma unroll
-          for (int j = 0; j < 6; j++) p[j] += SG[6 + j] * u;
+          for (int j = 0; j < 6; j++) p[j] += R[6 + j] * u;
           if (kDual) {
-            const float wk = w[k];
-            y[k] = wk + bt_dot6(SG, q);
+            y[k] = wk + bt_dot6(R, q);
 #pragma unroll
-            for (int j = 0; j < 6; j++) q[j] += SG[6 + j] * wk;
+            for (int j = 0; j < 6; j++) q[j] += R[6 + j] * wk;
           }
+        };
+        float A[12], B[12], xa, da, wa = 0.f, xb, db, wb = 0.f;
+        int k = kb;
+        load(k, A, xa, da, wa);
+        for (; k > k0; k -= 2) {
+          load(k - 1, B, xb, db, wb);
+          step(A, xa, da, wa, k);
+          if (k - 2 >= k0) load(k - 2, A, xa, da, wa);
+          step(B, xb, db, wb, k - 1);
         }
+        if (k == k0) step(A, xa, da, wa, k);
 #pragma unroll
         for (int j = 0; j < 6; j++) pv[6 * k0 + j] = p[j];
         if (kDual) {
@@ -626,9 +639,11 @@ struct BtEnv {
       W::sync();
     }
   }
-  BT_DEV void solve_down(float* x, float* cbout) {
+  // root->leaves sweeps: kMul = false: solve_down (x_k = g_k - G_k . a);  kMul = true: mulM_down (w_k = D_k (v_k + G_k . a)).
+  // A chain is walked in SEGMENTS that end at the last dof of a contact body (seg_* tables), where `a` is written to cbout.
+  template <bool kMul>
+  BT_DEV void sweep_down(const float* in, const float* dscale, float* out, float* cbout) {
     float* pv = pvec();
-    float* uu = tmpv();
     for (int cl = 0; cl < m.nclev; cl++) {
       const int c0 = BT_LDG(m.clev_adr + cl), c1 = BT_LDG(m.clev_adr + cl + 1);
       for (int ci = c0 + lane; ci < c1; ci += G) {
@@ -639,16 +654,36 @@ struct BtEnv {
 #pragma unroll
           for (int j = 0; j < 6; j++) a[j] = pv[6 * par + j];
         }
-#pragma unroll 2
-        for (int k = k0; k <= kb; k++) {
-          float SG[12];
-          bt_ld12(cdof() + 12 * k, SG);
-          // x_k = (u_k - U_k . a) / D_k = g_k - G_k . a
-          const float xk = uu[k] - bt_dot6(SG + 6, a);
-          x[k] = xk;
+        auto load = [&](int k, float (&R)[12], float& ik, float& dk) {
+          bt_ld12(cdof() + 12 * k, R);
+          ik = in[k];
+          if (kMul) dk = dscale[k];
+        };
+        auto step = [&](const float (&R)[12], float ik, float dk, int k) {
+          if (kMul) {
+            out[k] = dk * (ik + bt_dot6(R + 6, a));
 #pragma unroll
-          for (int j = 0; j < 6; j++) a[j] += SG[j] * xk;
-          const int cbi = cbout ? BT_LDG(m.dof_cb + k) : -1;
+            for (int j = 0; j < 6; j++) a[j] += R[j] * ik;
+          } else {
+            const float xk = ik - bt_dot6(R + 6, a);  // x_k = (u_k - U_k . a) / D_k = g_k - G_k . a
+            out[k] = xk;
+#pragma unroll
+            for (int j = 0; j < 6; j++) a[j] += R[j] * xk;
+          }
+        };
+        float A[12], B[12], ia, da = 0.f, ib, db = 0.f;
+        int k = k0;
+        for (int sgi = BT_LDG(m.seg_adr + c); sgi < BT_LDG(m.seg_adr + c + 1); sgi++) {
+          const int ke = BT_LDG(m.seg_end + sgi);
+          load(k, A, ia, da);
+          for (; k < ke; k += 2) {
+            load(k + 1, B, ib, db);
+            step(A, ia, da, k);
+            if (k + 2 <= ke) load(k + 2, A, ia, da);
+            step(B, ib, db, k + 1);
+          }
+          if (k == ke) { step(A, ia, da, k); k++; }
+          const int cbi = cbout ? BT_LDG(m.seg_cb + sgi) : -1;
           if (cbi >= 0) {
 #pragma unroll
             for (int j = 0; j < 6; j++) cbout[6 * cbi + j] = a[j];
@@ -660,42 +695,12 @@ struct BtEnv {
       W::sync();
     }
   }
+  BT_DEV void solve_down(float* x, float* cbout) { sweep_down<false>(tmpv(), nullptr, x, cbout); }
+  // first half of y = M v through the factor (the second half runs inside solve_up<true>)
+  BT_DEV void mulM_down(const float* v, float* w, float* cbout) { sweep_down<true>(v, Dd(), w, cbout); }
   BT_DEV void solve(float* x, float* cbout) {
     solve_up<false>(x, nullptr, nullptr);
     solve_down(x, cbout);
-  }
-  // first half of y = M v through the factor (the second half runs inside solve_up<true>)
-  BT_DEV void mulM_down(const float* v, float* w, float* cbout) {
-    float* pv = pvec();
-    for (int cl = 0; cl < m.nclev; cl++) {
-      const int c0 = BT_LDG(m.clev_adr + cl), c1 = BT_LDG(m.clev_adr + cl + 1);
-      for (int ci = c0 + lane; ci < c1; ci += G) {
-        const int c = BT_LDG(m.clev_chain + ci), k0 = BT_LDG(m.chain_k0 + c), kb = k0 + BT_LDG(m.chain_len + c) - 1;
-        const int par = BT_LDG(m.dof_parentid + k0);
-        float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (par >= 0) {
-#pragma unroll
-          for (int j = 0; j < 6; j++) a[j] = pv[6 * par + j];
-        }
-#pragma unroll 2
-        for (int k = k0; k <= kb; k++) {
-          float SG[12];
-          bt_ld12(cdof() + 12 * k, SG);
-          const float vk = v[k];
-          w[k] = Dd()[k] * (vk + bt_dot6(SG + 6, a));
-#pragma unroll
-          for (int j = 0; j < 6; j++) a[j] += SG[j] * vk;
-          const int cbi = BT_LDG(m.dof_cb + k);
-          if (cbi >= 0) {
-#pragma unroll
-            for (int j = 0; j < 6; j++) cbout[6 * cbi + j] = a[j];
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 6; j++) pv[6 * kb + j] = a[j];
-      }
-      W::sync();
-    }
   }
 
   // ================================================================== P8: collision (static contact list)

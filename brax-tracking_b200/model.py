@@ -283,10 +283,19 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
                 cb_slot[b] = dof_slot[d]
     ncb = len(cbs)
     S("ncb", ncb)
-    dof_cb = np.full(nv, -1, dtype=np.int32)  # contact-body slot whose chain ends at this dof
-    for d, k in dof_slot.items():
-        dof_cb[d] = k
-    t["dof_cb"] = dof_cb
+    t["cb_lastdof"] = _i([a["body_lastdof"][b] for b in cbs]) if cbs else np.zeros(1, np.int32)
+    # the root->leaves sweeps walk a dof chain in segments that end at the last dof of a contact body (where the running
+    # spatial acceleration is the chain sum the constraint Jacobian needs) or at the chain end (seg_cb = -1)
+    seg_adr, seg_end, seg_cb = [0], [], []
+    for c in range(nchain):
+        kb = chain_k0[c] + chain_len[c] - 1
+        for d in range(chain_k0[c], kb + 1):
+            if d in dof_slot:
+                seg_end.append(d); seg_cb.append(dof_slot[d])
+        if kb not in dof_slot:
+            seg_end.append(kb); seg_cb.append(-1)
+        seg_adr.append(len(seg_end))
+    t["seg_adr"] = _i(seg_adr); t["seg_end"] = _i(seg_end); t["seg_cb"] = _i(seg_cb)
     cb_adr, cb_dof = [0], []
     for b in cbs:
         cb_dof.extend(chain(b))
