@@ -499,7 +499,7 @@ struct BtEnv {
       for (int q = 1; q < 6; q++) { pi = r == q ? kIdx[q] : pi; ps = r == q ? kSgn[q] : ps; }
 #pragma unroll
       for (int j = 0; j < 6; j++) {
-        ix[i][j] = (pi >> (4 * j)) & 15;
+        ix[i][j] = 4 * ((pi >> (4 * j)) & 15);  // byte offset into the 10-float record
         const unsigned c = (ps >> (2 * j)) & 3;
         sg[i][j] = c == 0 ? 0.f : (c == 1 ? 1.f : -1.f);
 #ifdef __CUDACC__
@@ -539,26 +539,26 @@ struct BtEnv {
           float S[6], u[kNR], U[6];
           const int rb = act ? BT_LDG(m.dof_irec + ks) : -1;
           if (rb >= 0) {
-            const float* ci_ = crb() + 10 * rb;
+            const char* ci_ = reinterpret_cast<const char*>(crb() + 10 * rb);
 #pragma unroll
             for (int i = 0; i < kNR; i++)
 #pragma unroll
-              for (int j = 0; j < 6; j++) a[i][j] += sg[i][j] * ci_[ix[i][j]];
+              for (int j = 0; j < 6; j++) a[i][j] += sg[i][j] * *reinterpret_cast<const float*>(ci_ + ix[i][j]);
           }
           bt_ld6(cdof() + 12 * ks, S);
 #pragma unroll
           for (int i = 0; i < kNR; i++) u[i] = bt_dot6(a[i], S);
           W::template gather6<kNR>(u, U, lane);
-          const float D = Dinv()[ks] + bt_dot6(S, U);
-          const float inv = bt_rcp(D);
+          // lanes without a dof in this step get D = 1 (their result is discarded; 0 would only cost a denormal path)
+          const float D = k >= k0 ? Dinv()[ks] + bt_dot6(S, U) : 1.0f;
+          const float inv = bt_rcp_pos(D);
           if (act) {
 #pragma unroll
             for (int i = 0; i < kNR; i++) {
               const float ui = u[i] * inv;
               cdof()[12 * k + 6 + rl + i] = ui;  // G_k = U_k / D_k
               if (rl + i == 0) { Dinv()[k] = inv; Dd()[k] = D; }
-#pragma unroll
-              for (int j = 0; j < 6; j++) a[i][j] -= ui * U[j];
+              bt_axpy6(a[i], U, -ui);
             }
           }
         }
@@ -611,12 +611,10 @@ struct BtEnv {
         auto step = [&](const float (&R)[12], float xk, float dk, float wk, int k) {
           const float u = xk - bt_dot6(R, p);
           uu[k] = u * dk;  // g_k = u_k / D_k, consumed by the root->leaves pass
-#pragma unroll
-          for (int j = 0; j < 6; j++) p[j] += R[6 + j] * u;
+          bt_axpy6(p, R + 6, u);
           if (kDual) {
             y[k] = wk + bt_dot6(R, q);
-#pragma unroll
-            for (int j = 0; j < 6; j++) q[j] += R[6 + j] * wk;
+            bt_axpy6(q, R + 6, wk);
           }
         };
         float A[12], B[12], xa, da, wa = 0.f, xb, db, wb = 0.f;
@@ -662,13 +660,11 @@ struct BtEnv {
         auto step = [&](const float (&R)[12], float ik, float dk, int k) {
           if (kMul) {
             out[k] = dk * (ik + bt_dot6(R + 6, a));
-#pragma unroll
-            for (int j = 0; j < 6; j++) a[j] += R[j] * ik;
+            bt_axpy6(a, R, ik);
           } else {
             const float xk = ik - bt_dot6(R + 6, a);  // x_k = (u_k - U_k . a) / D_k = g_k - G_k . a
             out[k] = xk;
-#pragma unroll
-            for (int j = 0; j < 6; j++) a[j] += R[j] * xk;
+            bt_axpy6(a, R, xk);
           }
         };
         float A[12], B[12], ia, da = 0.f, ib, db = 0.f;
@@ -1370,7 +1366,10 @@ struct BtEnv {
       gauss = 0.5f * W::allsum(g);
       it++;
       }
-      if (!active) break;  // no CTA barrier here: the warps share this loop's code whatever their iteration
+      // the warps share this loop's code whatever their iteration; with sync bit 16 they also walk it in step (a warp that
+      // has converged idles through the remaining passes: it would wait at the next substep barrier anyway)
+      if (m.sync_mode & 16) { if (!W::cta_any(active)) break; }
+      else if (!active) break;
     }
     niter = it;
     if (live) for (int i = lane; i < m.nv; i += G) warm()[i] = qacc()[i];
@@ -1381,15 +1380,19 @@ struct BtEnv {
   // Both phases share ONE call site of aba_factor / solve: phase 0 uses qM, phase 1 qM + h * diag(damping) (MJX euler
   // with implicit joint damping).
   // returns false when stopped early by a debug stop point.
-  BT_DEV bool substep(bool do_euler, int stop = BT_STOP_NONE) {
+  BT_DEV bool substep(bool do_euler, int stop = BT_STOP_NONE, int frame = 0) {
     // `live` is warp-uniform and `stop` / `do_euler` are CTA-uniform, so every warp of the CTA reaches every barrier
-    W::cta_sync();
+    // sync_mode bits: 1 substep start, 2 after the tree pass, 4 before each factorisation, 8 before collision, 16 every CG pass
+    const int sm = m.sync_mode;
+    if (sm & 1) W::cta_sync();
     if (live) tree_forward();
     if (stop == BT_STOP_TREE) return false;
+    if (sm & 2) W::cta_sync();
     if (live) smooth_forces();
     if (stop == BT_STOP_SMOOTH) return false;
     const float h = m.timestep;
     for (int phase = 0; phase < (do_euler ? 2 : 1); phase++) {
+      if (sm & 4) W::cta_sync();
       if (live) aba_factor(phase ? h : 0.f);
       if (stop == BT_STOP_M || stop == BT_STOP_FACTOR) return false;
       if (live) {
@@ -1410,6 +1413,7 @@ struct BtEnv {
           W::sync();
         }
         if (stop == BT_STOP_QACC_SMOOTH) return false;
+        if (sm & 8) W::cta_sync();
         if (live) collide();
         if (stop == BT_STOP_COLLISION) return false;
         solve_constraints();
@@ -1419,7 +1423,7 @@ struct BtEnv {
     return true;
   }
   BT_DEV bool forward(int stop = BT_STOP_NONE) { return substep(false, stop); }
-  BT_DEV void step() { substep(true); }
+  BT_DEV void step(int frame = 0) { substep(true, BT_STOP_NONE, frame); }
 
   // mjx _advance with qacc = xv (the implicitly damped acceleration)
   BT_DEV void integrate() {

@@ -10,7 +10,7 @@
 // ---- scalar ints (1-element int tables, by name) ----
 #define BT_INT_SCALARS(X) \
   X(nq) X(nv) X(nu) X(na) X(nbody) X(njnt) X(nlevel) X(nchain) X(nclev) X(nbchain) X(nbclev) X(nroot) X(ncon) X(ncgeom) X(ncb) X(nmerge)           \
-  X(cone) X(iterations) X(ls_iterations) X(n_frames)                                                            \
+  X(cone) X(iterations) X(ls_iterations) X(n_frames) X(sync_mode)                                                           \
   /* env layer */                                                                                               \
   X(free_jnt) X(seed_root_from_clip) X(ref_len) X(clip_len) X(clip_nj) X(n_joint_idxs) X(n_body_idxs)           \
   X(n_endeff_idxs) X(torso_idx) X(terminate_when_unhealthy) X(steps_for_cur_frame) X(episode_length)            \

@@ -41,7 +41,7 @@ BT_DEV void bt_prog_step(const BtDev& m, float* s, int lane, int env, bool live,
     W::sync();
   }
   for (int f = 0; f < m.n_frames; f++) {
-    E.step();
+    E.step(f);
     time += m.timestep;
   }
   if (!live) return;

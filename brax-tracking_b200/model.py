@@ -13,6 +13,8 @@ from __future__ import annotations
 
 from typing import Dict
 
+import os
+
 import numpy as np
 
 from . import mjcf
@@ -393,6 +395,8 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
     # ------------------------------------------------------------------ options
     S("cone", m.cone); S("iterations", m.iterations); S("ls_iterations", m.ls_iterations)
     S("n_frames", cfg["n_frames"])
+    # CTA phase alignment of the step kernel: 1 = one barrier per substep (default), 2 = one per control step, 0 = none
+    S("sync_mode", int(os.environ.get("BT_SYNC", "1")))
     SF("timestep", m.timestep)
     SF("grav_x", m.gravity[0]); SF("grav_y", m.gravity[1]); SF("grav_z", m.gravity[2])
     SF("density", m.density); SF("viscosity", m.viscosity); SF("impratio", m.impratio)
