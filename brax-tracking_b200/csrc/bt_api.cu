@@ -33,7 +33,7 @@ BT_VARIANTS(X)
 
 static const BtVariantOps kVariants[] = {
 #define X(d, c)                                                                                                     \
-  {d, c, bt_prepare_step_##d##_##c, bt_prepare_reset_##d##_##c, bt_prepare_physics_##d##_##c, bt_prepare_reward_##d##_##c, \
+  {d, c, BT_VARIANT_MAX_WARPS(d, c), bt_prepare_step_##d##_##c, bt_prepare_reset_##d##_##c, bt_prepare_physics_##d##_##c, bt_prepare_reward_##d##_##c, \
    bt_prepare_debug_##d##_##c, bt_launch_step_##d##_##c, bt_launch_reset_##d##_##c, bt_launch_physics_##d##_##c,      \
    bt_launch_reward_##d##_##c, bt_launch_debug_##d##_##c},
     BT_VARIANTS(X)
@@ -114,7 +114,7 @@ int bt_model_create(int n, const char* const* names, const void* const* data, co
   BT_CUDA(cudaGetDeviceProperties(&prop, device));
   const size_t per_env = (size_t)m->dev.smem_floats * 4;
   int warps = (int)(prop.sharedMemPerBlockOptin / per_env);
-  if (warps > BT_MAX_WARPS) warps = BT_MAX_WARPS;
+  if (warps > m->ops->max_warps) warps = m->ops->max_warps;
   if (warps < 1) {
     snprintf(g_err, sizeof(g_err), "per-environment scratch (%zu B) exceeds shared memory", per_env);
     cudaFree(blob); delete m; return BT_E_UNSUPPORTED;
