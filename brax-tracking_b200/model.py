@@ -83,10 +83,15 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
             body_chain[b] = len(bchain_b0)
             bchain_b0.append(b); bchain_len.append(1)
     nbchain = len(bchain_b0)
-    bclevel = np.zeros(nbchain, dtype=np.int32)
-    for c in range(nbchain):
+    # scheduled by HEIGHT (distance to the deepest leaf chain below), root-most first: a chain only waits for its own
+    # ancestors, so short leaf chains hanging off the root run beside the long ones (rodent: 2 + 7 + 30 steps, not 2 + 9 + 30)
+    bheight = np.zeros(nbchain, dtype=np.int32)
+    for c in reversed(range(nbchain)):   # DFS numbering: children chains have larger ids
         pb = parent[bchain_b0[c]]
-        bclevel[c] = 0 if pb == 0 else bclevel[body_chain[pb]] + 1
+        if pb != 0:
+            pc = body_chain[pb]
+            bheight[pc] = max(bheight[pc], bheight[c] + 1)
+    bclevel = bheight.max() - bheight if nbchain else bheight
     nbclev = int(bclevel.max()) + 1
     t["bchain_b0"] = _i(bchain_b0); t["bchain_len"] = _i(bchain_len)
     t["bclev_adr"] = np.concatenate([[0], np.cumsum([int(np.sum(bclevel == L)) for L in range(nbclev)])]).astype(np.int32)
@@ -209,6 +214,19 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
     S("nchain", nchain); S("nclev", nclev)
     t["chain_k0"] = _i(chain_k0); t["chain_len"] = _i(chain_len); t["clev_adr"] = clev_adr; t["clev_chain"] = _i(corder)
     t["dof_chain"] = dof_chain
+    # the one-lane-per-chain sweeps are scheduled by chain HEIGHT instead (see the body chains above); aba_factor keeps the
+    # depth levels, which pack its four 8-lane groups better
+    cheight = np.zeros(nchain, dtype=np.int32)
+    for c in reversed(range(nchain)):
+        par = a["dof_parentid"][chain_k0[c]]
+        if par >= 0:
+            pc = dof_chain[par]
+            cheight[pc] = max(cheight[pc], cheight[c] + 1)
+    hlevel = cheight.max() - cheight if nchain else cheight
+    nhlev = int(hlevel.max()) + 1 if nchain else 1
+    S("nhlev", nhlev)
+    t["hlev_adr"] = np.concatenate([[0], np.cumsum([int(np.sum(hlevel == L)) for L in range(nhlev)])]).astype(np.int32)
+    t["hlev_chain"] = _i(sorted(range(nchain), key=lambda c: (hlevel[c], c)))
     t["dchild_adr"] = _i(dchild_adr); t["dchild_id"] = _i(dchild_id) if dchild_id else np.zeros(1, np.int32)
     t["dofbody_adr"] = _i(dofbody_adr); t["dofbody_id"] = _i(dofbody_id) if dofbody_id else np.zeros(1, np.int32)
     # link records: the inertia / RNE force of all bodies carried by a dof are summed into the slot of its FIRST body
@@ -454,13 +472,13 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
     R("cbJ", 18 * max(ncb, 1))   # three sets of per-contact-body chain sums (qvel, qacc_warmstart, qacc_smooth)
     # T region: cfrc (tree passes) -> the 6x6 reduced articulated inertia of every chain top (aba_factor)
     # -> contact geometry + wrenches + chain sums (solver)
-    R("T", max(6 * nbody, 36 * nchain, 6 * nv, 18 * ncon + 6 * max(ncb, 1)))
+    R("T", max(6 * nbody, 6 * nv, 18 * ncon + 6 * max(ncb, 1)))
     R("ref", 3 * max(len(roots), 1))
     R("actdot", max(na, 1))
     # pvec (sweep state, 6/dof) and the solver vectors behind it are contiguous: together they hold cvel/cacc (12/dof)
     # during the forward tree pass, when none of them is live
     w12 = off
-    R("pvec", 6 * nv)
+    R("pvec", max(6 * nv, 48 * nchain))  # also the 8 x 6 chain-top rows of aba_factor
     for v in ("qfrc_smooth", "qacc_smooth", "qacc", "search", "qfrc_c"):
         R(v, nv)
     R("x", max(nv, nu))
