@@ -24,6 +24,65 @@ struct BtLanes<32> {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
   }
+  // N sums at once by recursive halving: at every butterfly step a lane keeps one half of its values and trades the other
+  // half with its partner, so the 5 steps cost ~N + log N shuffles instead of 5 N; the totals end up spread over the lanes
+  // (value j in the lane whose bits select it) and are broadcast back.  Summation order differs from allsum() only in
+  // association.
+  template <int N>
+  static BT_DEV void allsumN(float (&v)[N], int lane) {
+    constexpr int h1 = (N + 1) / 2, h2 = (h1 + 1) / 2, h3 = (h2 + 1) / 2, h4 = (h3 + 1) / 2;
+    float a[h1 > 0 ? h1 : 1];
+    int src = 0;
+    {
+      const bool hi = lane & 16;
+#pragma unroll
+      for (int i = 0; i < h1; i++) {
+        const float up = h1 + i < N ? v[h1 + i] : 0.f;
+        const float keep = hi ? up : v[i], send = hi ? v[i] : up;
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+      src += hi ? h1 : 0;
+    }
+    if (h1 > 1) {
+      const bool hi = lane & 8;
+#pragma unroll
+      for (int i = 0; i < h2; i++) {
+        const float up = h2 + i < h1 ? a[h2 + i] : 0.f;
+        const float keep = hi ? up : a[i], send = hi ? a[i] : up;
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+    } else a[0] += __shfl_xor_sync(0xffffffffu, a[0], 8);
+    if (h2 > 1) {
+      const bool hi = lane & 4;
+#pragma unroll
+      for (int i = 0; i < h3; i++) {
+        const float up = h3 + i < h2 ? a[h3 + i] : 0.f;
+        const float keep = hi ? up : a[i], send = hi ? a[i] : up;
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+    } else a[0] += __shfl_xor_sync(0xffffffffu, a[0], 4);
+    if (h3 > 1) {
+      const bool hi = lane & 2;
+#pragma unroll
+      for (int i = 0; i < h4; i++) {
+        const float up = h4 + i < h3 ? a[h4 + i] : 0.f;
+        const float keep = hi ? up : a[i], send = hi ? a[i] : up;
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+      }
+    } else a[0] += __shfl_xor_sync(0xffffffffu, a[0], 2);
+    static_assert(h4 == 1, "allsumN supports up to 16 values");
+    a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+    // value j sits in the lanes whose (16, 8, 4, 2) bits spell its position in the halving tree
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+      int l = 0, r = j;
+      if (r >= h1) { l |= 16; r -= h1; }
+      if (h1 > 1 && r >= h2) { l |= 8; r -= h2; }
+      if (h2 > 1 && r >= h3) { l |= 4; r -= h3; }
+      if (h3 > 1 && r >= h4) { l |= 2; r -= h4; }
+      v[j] = __shfl_sync(0xffffffffu, a[0], l);
+    }
+  }
   static BT_DEV int any(int p) { return __any_sync(0xffffffffu, p); }
   static BT_DEV int allmax(int v) { return __reduce_max_sync(0xffffffffu, v); }
   // CTA-wide phase alignment: the warps of a CTA own different environments but are kept in the same phase of the
@@ -43,6 +102,8 @@ template <>
 struct BtLanes<1> {
   static BT_DEV void sync() {}
   static BT_DEV float allsum(float v) { return v; }
+  template <int N>
+  static BT_DEV void allsumN(float (&)[N], int) {}
   static BT_DEV int any(int p) { return p; }
   static BT_DEV int allmax(int v) { return v; }
   static BT_DEV void cta_sync() {}
@@ -1112,9 +1173,13 @@ struct BtEnv {
       for (int p = 0; p < NP; p++)
         if (ja + alpha[p] * v < 0.f) { q0[p] += a0; q1[p] += a1; q2[p] += a2; }
     }
+    float red[3 * NP];
+#pragma unroll
+    for (int p = 0; p < NP; p++) { red[3 * p] = q0[p]; red[3 * p + 1] = q1[p]; red[3 * p + 2] = q2[p]; }
+    W::template allsumN<3 * NP>(red, lane);
 #pragma unroll
     for (int p = 0; p < NP; p++) {
-      const float s0 = W::allsum(q0[p]) + qg[0], s1 = W::allsum(q1[p]) + qg[1], s2 = W::allsum(q2[p]) + qg[2];
+      const float s0 = red[3 * p] + qg[0], s1 = red[3 * p + 1] + qg[1], s2 = red[3 * p + 2] + qg[2];
       const float al = alpha[p];
       out[p].alpha = al;
       out[p].cost = al * al * s2 + al * s1 + s0;
@@ -1254,7 +1319,7 @@ struct BtEnv {
         Mgrad[sl] = i < m.nv ? xv()[i] : 0.f;
         g_Mg += grad[sl] * Mgrad[sl];
       }
-      pg_pMg = W::allsum(pg_pMg); g_pMg = W::allsum(g_pMg); g_Mg = W::allsum(g_Mg);
+      { float r3[3] = {pg_pMg, g_pMg, g_Mg}; if (G > 1) { W::template allsumN<3>(r3, lane); pg_pMg = r3[0]; g_pMg = r3[1]; g_Mg = r3[2]; } }
       float beta = 0.f;
       if (it > 0) {
         beta = (g_Mg - g_pMg) / (pg_pMg > BT_MINVAL ? pg_pMg : BT_MINVAL);
@@ -1290,7 +1355,7 @@ struct BtEnv {
         g1 += sv * (Ma[sl] - qfs[sl]);
         g2 += 0.5f * sv * mv[sl];
       }
-      sn = W::allsum(sn); g1 = W::allsum(g1); g2 = W::allsum(g2);
+      { float r3[3] = {sn, g1, g2}; if (G > 1) { W::template allsumN<3>(r3, lane); sn = r3[0]; g1 = r3[1]; g2 = r3[2]; } }
       const float qg[3] = {gauss, g1, g2};
       const float gtol = m.tolerance * m.ls_tolerance * sqrtf(sn) * m.meaninertia * nvf;
       LsPt p0, lo, hi;
@@ -1298,11 +1363,18 @@ struct BtEnv {
       lo = hi = p0;
       // stage 0: p0 = point(0); stage 1: lo = point(newton step from p0); stage >= 2: bracketing iterations
       bool swap = true;
-      for (int stage = 0;; stage++) {
+      // stages 0 / 1 evaluate a single point each (one call site of the 1-point evaluator)
+      for (int stage = 0; stage < 2; stage++) {
+        const float a1 = stage == 0 ? 0.f : p0.alpha - p0.d0 / p0.d1;
+        LsPt pt1;
+        ls_eval<1>(e, jv, ljv, qg, &a1, &pt1);
+        if (stage == 0) p0 = pt1;
+        else if (pt1.d0 < p0.d0) { lo = pt1; hi = p0; }
+        else { lo = p0; hi = pt1; }
+      }
+      for (int stage = 2;; stage++) {
         float al[3];
-        if (stage == 0) { al[0] = al[1] = al[2] = 0.f; }
-        else if (stage == 1) { al[0] = al[1] = al[2] = p0.alpha - p0.d0 / p0.d1; }
-        else {
+        {
           bool done = stage - 2 >= m.ls_iterations;
           done |= !swap;
           done |= (lo.d0 < 0.f) && (lo.d0 > -gtol);
@@ -1312,11 +1384,6 @@ struct BtEnv {
         }
         LsPt pt[3];
         ls_eval<3>(e, jv, ljv, qg, al, pt);
-        if (stage == 0) { p0 = pt[0]; continue; }
-        if (stage == 1) {
-          if (pt[0].d0 < p0.d0) { lo = pt[0]; hi = p0; } else { lo = p0; hi = pt[0]; }
-          continue;
-        }
         const bool s_lo_next = (lo.d0 > 0.f) || (lo.d0 < pt[0].d0);
         if (s_lo_next) lo = pt[0];
         const bool s_lo_mid = (pt[2].d0 < 0.f) && (lo.d0 < pt[2].d0);
