@@ -216,11 +216,16 @@ struct BtEnv {
         }
       }
     }
+    float* bp = pose_pos(m.nbanc & 1);
+    float* bq = pose_quat(m.nbanc & 1);
 #pragma unroll
-    for (int k = 0; k < 3; k++) xpos()[3 * b + k] = p[k];
+    for (int k = 0; k < 3; k++) bp[3 * b + k] = p[k];
 #pragma unroll
-    for (int k = 0; k < 4; k++) xquat()[4 * b + k] = q[k];
+    for (int k = 0; k < 4; k++) bq[4 * b + k] = q[k];
   }
+  // the two pose buffers of the pointer-jumping composition: 0 = (xpos, xquat), 1 = the T region (idle during the tree pass)
+  BT_DEV float* pose_pos(int which) const { return which ? T() : xpos(); }
+  BT_DEV float* pose_quat(int which) const { return which ? T() + 3 * m.nbody : xquat(); }
 
   BT_DEV void joint_cdof(int j) {
     const int b = BT_LDG(m.jnt_bodyid + j), p = BT_LDG(m.body_parentid + b), da = BT_LDG(m.jnt_dofadr + j);
@@ -349,36 +354,39 @@ struct BtEnv {
     }
     for (int b = 1 + lane; b < m.nbody; b += G) body_frame(b);
     W::sync();
-    // ---- compose: world pose = parent pose o local frame
-    for (int cl = 0; cl < m.nbclev; cl++) {
-      const int c0 = BT_LDG(m.bclev_adr + cl), c1 = BT_LDG(m.bclev_adr + cl + 1);
-      for (int ci = c0 + lane; ci < c1; ci += G) {
-        const int c = BT_LDG(m.bclev_chain + ci), b0 = BT_LDG(m.bchain_b0 + c), b1 = b0 + BT_LDG(m.bchain_len + c);
-        const int p = BT_LDG(m.body_parentid + b0);
-        float pos[3], quat[4];
-#pragma unroll
-        for (int k = 0; k < 3; k++) pos[k] = xpos()[3 * p + k];
-#pragma unroll
-        for (int k = 0; k < 4; k++) quat[k] = xquat()[4 * p + k];
-        for (int b = b0; b < b1; b++) {
-          float pl[3] = {xpos()[3 * b], xpos()[3 * b + 1], xpos()[3 * b + 2]}, r[3];
-          bt_rotate(pl, quat, r);
-          pos[0] += r[0]; pos[1] += r[1]; pos[2] += r[2];
-          if (!(BT_LDG(m.body_flags + b) & 2)) {  // model-uniform: jointless bodies with an identity frame only translate
-            float ql[4] = {xquat()[4 * b], xquat()[4 * b + 1], xquat()[4 * b + 2], xquat()[4 * b + 3]}, q2[4];
-            bt_quat_mul(quat, ql, q2);
-            quat[0] = q2[0]; quat[1] = q2[1]; quat[2] = q2[2]; quat[3] = q2[3];
-            bt_quat_normalize(quat);
-          }
-#pragma unroll
-          for (int k = 0; k < 3; k++) xpos()[3 * b + k] = pos[k];
-#pragma unroll
-          for (int k = 0; k < 4; k++) xquat()[4 * b + k] = quat[k];
-          if (b == b0 && p == 0) {  // reference point of the tree = position of its root body
+    // ---- compose: world pose = parent pose o local frame, by pointer jumping over the body tree: after round r every body
+    // holds its pose relative to its 2^(r+1)-th ancestor (or the world), so ceil(log2(depth)) lane-parallel rounds replace a
+    // 39-body serial chain.  Rounds ping-pong between the two pose buffers; the last one writes (xpos, xquat).
+    for (int r = 0; r < m.nbanc; r++) {
+      const float* sp = pose_pos((m.nbanc - r) & 1);
+      const float* sq = pose_quat((m.nbanc - r) & 1);
+      float* dp = pose_pos((m.nbanc - 1 - r) & 1);
+      float* dq = pose_quat((m.nbanc - 1 - r) & 1);
+      const bool last = r == m.nbanc - 1;
+      for (int b = 1 + lane; b < m.nbody; b += G) {
+        const int a = BT_LDG(m.body_anc + r * m.nbody + b);
+        float pos[3] = {sp[3 * b], sp[3 * b + 1], sp[3 * b + 2]};
+        float quat[4] = {sq[4 * b], sq[4 * b + 1], sq[4 * b + 2], sq[4 * b + 3]};
+        if (a > 0) {
+          const float pa[3] = {sp[3 * a], sp[3 * a + 1], sp[3 * a + 2]};
+          const float qa[4] = {sq[4 * a], sq[4 * a + 1], sq[4 * a + 2], sq[4 * a + 3]};
+          float rr[3], q2[4];
+          bt_rotate(pos, qa, rr);
+          pos[0] = pa[0] + rr[0]; pos[1] = pa[1] + rr[1]; pos[2] = pa[2] + rr[2];
+          bt_quat_mul(qa, quat, q2);
+          quat[0] = q2[0]; quat[1] = q2[1]; quat[2] = q2[2]; quat[3] = q2[3];
+        }
+        if (last) {
+          bt_quat_normalize(quat);
+          if (BT_LDG(m.body_parentid + b) == 0) {  // reference point of the tree = position of its root body
             const int rs = BT_LDG(m.body_ref + b);
             ref()[3 * rs] = pos[0]; ref()[3 * rs + 1] = pos[1]; ref()[3 * rs + 2] = pos[2];
           }
         }
+#pragma unroll
+        for (int k = 0; k < 3; k++) dp[3 * b + k] = pos[k];
+#pragma unroll
+        for (int k = 0; k < 4; k++) dq[4 * b + k] = quat[k];
       }
       W::sync();
     }

@@ -97,6 +97,19 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
     t["bclev_adr"] = np.concatenate([[0], np.cumsum([int(np.sum(bclevel == L)) for L in range(nbclev)])]).astype(np.int32)
     t["bclev_chain"] = _i(sorted(range(nbchain), key=lambda c: (bclevel[c], c)))
     S("nbchain", nbchain); S("nbclev", nbclev)
+    # pointer-jumping ancestor tables of the pose composition: round r composes a body with body_anc[r][b] (its 2^r-th ancestor;
+    # 0 = the pose is already a world pose)
+    bdepth = np.zeros(nbody, dtype=np.int32)
+    for b in range(1, nbody):
+        bdepth[b] = bdepth[parent[b]] + 1
+    nbanc = max(1, int(np.ceil(np.log2(max(int(bdepth.max()), 1)))))
+    anc = np.zeros((nbanc, nbody), dtype=np.int32)
+    anc[0] = parent
+    for r in range(1, nbanc):
+        anc[r] = anc[r - 1][anc[r - 1]]
+    assert nbanc == 1 or not anc[nbanc - 1][anc[nbanc - 1]].any()
+    S("nbanc", nbanc)
+    t["body_anc"] = anc.reshape(-1)
     # reference point of every kinematic tree: the position of the tree's root body (a free root moves with
     # qpos[0:3]; a static root is a model constant).  MJX uses the subtree COM here; any fixed point gives the
     # same qM / qfrc_bias (DESIGN.md "reference point").
@@ -472,7 +485,7 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
     R("cbJ", 18 * max(ncb, 1))   # three sets of per-contact-body chain sums (qvel, qacc_warmstart, qacc_smooth)
     # T region: cfrc (tree passes) -> the 6x6 reduced articulated inertia of every chain top (aba_factor)
     # -> contact geometry + wrenches + chain sums (solver)
-    R("T", max(6 * nbody, 6 * nv, 18 * ncon + 6 * max(ncb, 1)))
+    R("T", max(7 * nbody, 6 * nv, 18 * ncon + 6 * max(ncb, 1)))   # 7 * nbody: second pose buffer of the composition
     R("ref", 3 * max(len(roots), 1))
     R("actdot", max(na, 1))
     # pvec (sweep state, 6/dof) and the solver vectors behind it are contiguous: together they hold cvel/cacc (12/dof)
