@@ -251,10 +251,12 @@ def run_gpu(args):
         }
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
-            ce = 32 * cores
-            v, dt = cpu_port_run(args.model, ce, 4, cores)
+            # bounded sample of the same workload: ~10-30 CPU-seconds (wall time x threads) on the box's host cores
+            ce = 128 * cores
+            v, dt = cpu_port_run(args.model, ce, 8, cores)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{ce} envs x 4 control steps, oracle port (C restatement of mjx.step, float32) + numpy env layer, {dt:.1f} s"}
+                                    "sample": f"{ce} envs x 8 control steps, oracle port (C restatement of mjx.step, float32) + numpy env layer, "
+                                              f"{dt:.1f} s wall = {dt * cores:.0f} CPU-s"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
