@@ -538,12 +538,20 @@ struct BtEnv {
     // idx (4 bits each) and sign (2 bits each: 0 -> 0, 1 -> +1, 2 -> -1) of row r, packed
     const unsigned kIdx[6] = {0x780430u, 0x608513u, 0x067254u, 0x009780u, 0x090608u, 0x900067u};
     const unsigned kSgn[6] = {0x615u, 0x855u, 0x195u, 0x064u, 0x112u, 0x409u};
-    int ix[kNR][6];
-    float sg[kNR][6];
+    int ix[kNR][6], rbase[kNR], rstride[kNR];
+    float sg[kNR][6], rc[kNR][4];
 #pragma unroll
     for (int i = 0; i < kNR; i++) {
       const int row = rl + i;
       const int r = row < 6 ? row : 0;
+      // where the row's per-dof result goes (s[rbase + k * rstride]) and how it is formed: see the loop below
+      rbase[i] = row < 6 ? m.o_cdof + 6 + row : (row == 6 ? (kRne ? m.o_qfrc_smooth : m.o_tmpv) : m.o_x);
+      rstride[i] = row < 6 ? 12 : 1;
+      rc[i][0] = row == 7 ? 1.f : 0.f; rc[i][1] = row == 6 ? 0.f : 1.f;
+      rc[i][2] = row < 6 ? 1.f : (row == 6 ? 0.f : -1.f); rc[i][3] = row == 6 ? 1.f : 0.f;
+#ifdef __CUDACC__
+      asm volatile("" : "+r"(rbase[i]), "+r"(rstride[i]), "+f"(rc[i][0]), "+f"(rc[i][1]), "+f"(rc[i][2]), "+f"(rc[i][3]));
+#endif
       unsigned pi = kIdx[0], ps = kSgn[0];
 #pragma unroll
       for (int q = 1; q < 6; q++) { pi = r == q ? kIdx[q] : pi; ps = r == q ? kSgn[q] : ps; }
@@ -610,14 +618,12 @@ struct BtEnv {
 #pragma unroll
             for (int i = 0; i < kNR; i++) {
               const int row = rl + i;
-              // rows 0..5: a_r -= (u_r / D) U;  row 6: untouched;  row 7: p += ((x_k - S . p) / D) U.  Branch-free (selects): the
-              // three kinds of rows share one instruction stream.
-              float ui = (u[i] - (row == 7 ? xk : 0.f)) * inv;
-              ui = row == 6 ? 0.f : ui;
+              // rows 0..5: a_r -= (u_r / D) U;  row 6: untouched;  row 7: p += ((x_k - S . p) / D) U.  Branch-free: the three
+              // kinds of rows share one instruction stream through per-row constants (c7 = [row 7], n6 = [row != 6]).
+              const float ui = (u[i] - rc[i][0] * xk) * (inv * rc[i][1]);
               // one store per row: G_k[row] = U_row / D (rows 0..5); qfrc_smooth_k = x_k (row 6; a scratch slot when !kRne);
               // xv_k = g_k = u_k / D_k (row 7, consumed by solve_down)
-              const int at = row < 6 ? m.o_cdof + 12 * k + 6 + row : (row == 6 ? (kRne ? m.o_qfrc_smooth : m.o_tmpv) + k : m.o_x + k);
-              s[at] = row < 6 ? ui : (row == 6 ? xk : -ui);
+              s[rbase[i] + k * rstride[i]] = rc[i][2] * ui + rc[i][3] * xk;
               if (row == 0) { Dinv()[k] = inv; Dd()[k] = D; }
               bt_axpy6(a[i], U, -ui);
             }
