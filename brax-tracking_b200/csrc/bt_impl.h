@@ -538,7 +538,7 @@ struct BtEnv {
     // idx (4 bits each) and sign (2 bits each: 0 -> 0, 1 -> +1, 2 -> -1) of row r, packed
     const unsigned kIdx[6] = {0x780430u, 0x608513u, 0x067254u, 0x009780u, 0x090608u, 0x900067u};
     const unsigned kSgn[6] = {0x615u, 0x855u, 0x195u, 0x064u, 0x112u, 0x409u};
-    int ix[kNR][6], rbase[kNR], rstride[kNR];
+    int ix[kNR][6], rbase[kNR], rstride[kNR], pmul[kNR];
     float sg[kNR][6], rc[kNR][4];
 #pragma unroll
     for (int i = 0; i < kNR; i++) {
@@ -547,9 +547,11 @@ struct BtEnv {
       // where the row's per-dof result goes (s[rbase + k * rstride]) and how it is formed: see the loop below
       rbase[i] = row < 6 ? m.o_cdof + 6 + row : (row == 6 ? (kRne ? m.o_qfrc_smooth : m.o_tmpv) : m.o_x);
       rstride[i] = row < 6 ? 12 : 1;
+      pmul[i] = row == 6 ? 24 : 40;  // bytes per body-force / link-inertia record
       rc[i][0] = row == 7 ? 1.f : 0.f; rc[i][1] = row == 6 ? 0.f : 1.f;
       rc[i][2] = row < 6 ? 1.f : (row == 6 ? 0.f : -1.f); rc[i][3] = row == 6 ? 1.f : 0.f;
 #ifdef __CUDACC__
+      asm volatile("" : "+r"(pmul[i]));
       asm volatile("" : "+r"(rbase[i]), "+r"(rstride[i]), "+f"(rc[i][0]), "+f"(rc[i][1]), "+f"(rc[i][2]), "+f"(rc[i][3]));
 #endif
       unsigned pi = kIdx[0], ps = kSgn[0];
@@ -562,6 +564,7 @@ struct BtEnv {
         sg[i][j] = c == 0 ? 0.f : (c == 1 ? 1.f : -1.f);
         if (row == 6) { ix[i][j] = 4 * j; sg[i][j] = kRne ? 1.f : 0.f; }  // the 6-float body-force record
         if (row == 7) { ix[i][j] = 0; sg[i][j] = 0.f; }
+        ix[i][j] += 4 * (row == 6 ? m.o_T : m.o_crb);  // byte offset from the scratch base; + rb * pmul selects the record
 #ifdef __CUDACC__
         // opaque to the optimiser: otherwise the decode above is rematerialised inside the per-dof loop
         asm volatile("" : "+r"(ix[i][j]), "+f"(sg[i][j]));
@@ -591,42 +594,58 @@ struct BtEnv {
 #pragma unroll
               for (int j = 0; j < 6; j++) a[i][j] += cr[6 * (rl + i) + j];
           }
+        // running cursors of this group's current dof (they freeze on the last dof once the chain is exhausted, so
+        // predicated-off lanes keep reading valid memory and store nothing)
+        const int nstep = kb - k0 + 1;            // <= 0: no chain in this pass
+        int kc = nstep > 0 ? kb : 0;
+        const float* recp = cdof() + 12 * kc;
+        const float* xp = X + kc;
+        float* dp = Dinv() + kc;
+        float* outp[kNR];
+#pragma unroll
+        for (int i = 0; i < kNR; i++) outp[i] = s + rbase[i] + kc * rstride[i];
         for (int t = 0; t < maxlen; t++) {
-          const int k = kb - t;
-          const bool act = k >= k0;
-          const int ks = act ? k : 0;  // predicated-off lanes read dof 0 and store nothing
+          const bool act = t < nstep;
           float S[6], u[kNR], U[7];
-          const int rb = act ? BT_LDG(m.dof_irec + ks) : -1;
+          const int rb = act ? BT_LDG(m.dof_irec + kc) : -1;
           if (rb >= 0) {
 #pragma unroll
             for (int i = 0; i < kNR; i++) {
-              const char* ci_ = reinterpret_cast<const char*>(rl + i == 6 ? T() + 6 * rb : crb() + 10 * rb);
+              int off = rb * pmul[i];  // ix holds the region base too
+#ifdef __CUDACC__
+              asm volatile("" : "+r"(off));  // keep the product out of the six address computations (one 3-input add each)
+#endif
 #pragma unroll
-              for (int j = 0; j < 6; j++) a[i][j] += sg[i][j] * *reinterpret_cast<const float*>(ci_ + ix[i][j]);
+              for (int j = 0; j < 6; j++)
+                a[i][j] += sg[i][j] * *reinterpret_cast<const float*>(reinterpret_cast<const char*>(s) + off + ix[i][j]);
             }
           }
-          bt_ld6(cdof() + 12 * ks, S);
-          const float Xk = X[ks];
+          bt_ld6(recp, S);
+          const float Xk = *xp;
 #pragma unroll
           for (int i = 0; i < kNR; i++) u[i] = bt_dot6(a[i], S);
           W::template gather7<kNR>(u, U, lane);  // U[0..5] = A S, U[6] = S . f = bias_k
           // lanes without a dof in this step get D = 1 (their result is discarded; 0 would only cost a denormal path)
-          const float D = act ? Dinv()[ks] + bt_dot6(S, U) : 1.0f;
+          const float D = act ? *dp + bt_dot6(S, U) : 1.0f;
           const float inv = bt_rcp_pos(D);
           const float xk = kRne ? Xk - U[6] : Xk;
           if (act) {
 #pragma unroll
             for (int i = 0; i < kNR; i++) {
-              const int row = rl + i;
               // rows 0..5: a_r -= (u_r / D) U;  row 6: untouched;  row 7: p += ((x_k - S . p) / D) U.  Branch-free: the three
               // kinds of rows share one instruction stream through per-row constants (c7 = [row 7], n6 = [row != 6]).
               const float ui = (u[i] - rc[i][0] * xk) * (inv * rc[i][1]);
               // one store per row: G_k[row] = U_row / D (rows 0..5); qfrc_smooth_k = x_k (row 6; a scratch slot when !kRne);
               // xv_k = g_k = u_k / D_k (row 7, consumed by solve_down)
-              s[rbase[i] + k * rstride[i]] = rc[i][2] * ui + rc[i][3] * xk;
-              if (row == 0) { Dinv()[k] = inv; Dd()[k] = D; }
+              *outp[i] = rc[i][2] * ui + rc[i][3] * xk;
+              if (rl + i == 0) { *dp = inv; Dd()[kc] = D; }
               bt_axpy6(a[i], U, -ui);
             }
+          }
+          if (t + 1 < nstep) {
+            kc--; recp -= 12; xp--; dp--;
+#pragma unroll
+            for (int i = 0; i < kNR; i++) outp[i] -= rstride[i];
           }
         }
         if (kb >= 0) {
