@@ -685,31 +685,38 @@ struct BtEnv {
 #pragma unroll
           for (int j = 0; j < 6; j++) p[j] += pv[6 * ch + j];
         }
-        auto load = [&](int k, float (&R)[12], float& xk, float& dk) {
-          bt_ld12(cdof() + 12 * k, R);
-          xk = x[k];
-          if (!kMul) dk = Dinv()[k];
+        // running cursors at dof k: the pair (k, k - 1) is addressed with immediate offsets
+        const float* rp = cdof() + 12 * kb;
+        float* xq = x + kb;
+        const float* dq = Dinv() + kb;
+        float* yq = kMul ? y + kb : nullptr;
+        auto load = [&](int o, float (&R)[12], float& xk, float& dk) {  // dof k - o
+          bt_ld12(rp - 12 * o, R);
+          xk = xq[-o];
+          if (!kMul) dk = dq[-o];
         };
-        auto step = [&](const float (&R)[12], float xk, float dk, int k) {
+        auto step = [&](const float (&R)[12], float xk, float dk, int o) {
           if (kMul) {
-            y[k] = xk + bt_dot6(R, p);
+            yq[-o] = xk + bt_dot6(R, p);
             bt_axpy6(p, R + 6, xk);
           } else {
             const float u = xk - bt_dot6(R, p);
-            x[k] = u * dk;  // in place: g_k = u_k / D_k, consumed by the root->leaves pass
+            xq[-o] = u * dk;  // in place: g_k = u_k / D_k, consumed by the root->leaves pass
             bt_axpy6(p, R + 6, u);
           }
         };
         float A[12], B[12], xa, da = 0.f, xb, db = 0.f;
         int k = kb;
-        load(k, A, xa, da);
+        load(0, A, xa, da);
         for (; k > k0; k -= 2) {
-          load(k - 1, B, xb, db);
-          step(A, xa, da, k);
-          if (k - 2 >= k0) load(k - 2, A, xa, da);
-          step(B, xb, db, k - 1);
+          load(1, B, xb, db);
+          step(A, xa, da, 0);
+          if (k - 2 >= k0) load(2, A, xa, da);
+          step(B, xb, db, 1);
+          rp -= 24; xq -= 2; dq -= 2;
+          if (kMul) yq -= 2;
         }
-        if (k == k0) step(A, xa, da, k);
+        if (k == k0) step(A, xa, da, 0);
 #pragma unroll
         for (int j = 0; j < 6; j++) pv[6 * k0 + j] = p[j];
       }
@@ -731,18 +738,23 @@ struct BtEnv {
 #pragma unroll
           for (int j = 0; j < 6; j++) a[j] = pv[6 * par + j];
         }
-        auto load = [&](int k, float (&R)[12], float& ik, float& dk) {
-          bt_ld12(cdof() + 12 * k, R);
-          ik = in[k];
-          if (kMul) dk = dscale[k];
+        // running cursors at dof k: the pair (k, k + 1) is addressed with immediate offsets
+        const float* rp = cdof() + 12 * k0;
+        const float* iq = in + k0;
+        float* oq = out + k0;
+        const float* dq = kMul ? dscale + k0 : nullptr;
+        auto load = [&](int o, float (&R)[12], float& ik, float& dk) {  // dof k + o
+          bt_ld12(rp + 12 * o, R);
+          ik = iq[o];
+          if (kMul) dk = dq[o];
         };
-        auto step = [&](const float (&R)[12], float ik, float dk, int k) {
+        auto step = [&](const float (&R)[12], float ik, float dk, int o) {
           if (kMul) {
-            out[k] = dk * (ik + bt_dot6(R + 6, a));
+            oq[o] = dk * (ik + bt_dot6(R + 6, a));
             bt_axpy6(a, R, ik);
           } else {
             const float xk = ik - bt_dot6(R + 6, a);  // x_k = (u_k - U_k . a) / D_k = g_k - G_k . a
-            out[k] = xk;
+            oq[o] = xk;
             bt_axpy6(a, R, xk);
           }
         };
@@ -750,14 +762,20 @@ struct BtEnv {
         int k = k0;
         for (int sgi = BT_LDG(m.seg_adr + c); sgi < BT_LDG(m.seg_adr + c + 1); sgi++) {
           const int ke = BT_LDG(m.seg_end + sgi);
-          load(k, A, ia, da);
+          load(0, A, ia, da);
           for (; k < ke; k += 2) {
-            load(k + 1, B, ib, db);
-            step(A, ia, da, k);
-            if (k + 2 <= ke) load(k + 2, A, ia, da);
-            step(B, ib, db, k + 1);
+            load(1, B, ib, db);
+            step(A, ia, da, 0);
+            if (k + 2 <= ke) load(2, A, ia, da);
+            step(B, ib, db, 1);
+            rp += 24; iq += 2; oq += 2;
+            if (kMul) dq += 2;
           }
-          if (k == ke) { step(A, ia, da, k); k++; }
+          if (k == ke) {
+            step(A, ia, da, 0);
+            k++; rp += 12; iq++; oq++;
+            if (kMul) dq++;
+          }
           const int cbi = cbout ? BT_LDG(m.seg_cb + sgi) : -1;
           if (cbi >= 0) {
 #pragma unroll
