@@ -198,21 +198,21 @@ def run_gpu(args):
     # ---------------- end to end through the public API with HOST buffers
     h_act = torch.from_numpy(np.tanh(rng.standard_normal((n_act, n, m.nu))).astype(np.float32)).pin_memory()
     d_act = torch.empty(n, m.nu, dtype=torch.float32, device=dev)
-    h_obs = torch.empty(n, env.observation_size, dtype=torch.float32).pin_memory()
     h_rew = torch.empty(n, dtype=torch.float32).pin_memory()
     h_done = torch.empty(n, dtype=torch.float32).pin_memory()
+    # observations of a host-side consumer: the kernel writes each env's row straight into page-locked host memory
+    # (mapped pointer; the device->host transfer of the 20 MB of observations overlaps the launch)
+    h_obs = env.bind_host_obs(state)
     for i in range(2):
         d_act.copy_(h_act[i % n_act], non_blocking=True)
         state = env.step(state, d_act)
-        h_obs.copy_(state.obs, non_blocking=True)
     barrier()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K):
         d_act.copy_(h_act[i % n_act], non_blocking=True)
-        state = env.step(state, d_act)
-        h_obs.copy_(state.obs, non_blocking=True)
+        state = env.step(state, d_act)          # obs rows land in h_obs (host) during the launch
         h_rew.copy_(state.reward, non_blocking=True)
         h_done.copy_(state.done, non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the host consumes obs/reward/done every step

@@ -178,6 +178,17 @@ class AutoResetWrapperTracking:
         self.env._native.step(action, state.pipeline_state, r["first"], r["first_obs"], r["first_info_i"], r)
         return state
 
+    def bind_host_obs(self, state: State):
+        """For host-side consumers of the observations (a CPU policy, logging): from now on ``state.obs`` lives in page-locked
+        host memory and the step kernel writes each environment's row there directly (mapped pointer, zero-copy), spread
+        over the launch instead of a device->host copy after it.  Valid after the stream is synchronised.  Returns the tensor."""
+        import torch
+        h = torch.empty(state.obs.shape, dtype=torch.float32).pin_memory()
+        h.copy_(state.obs)
+        state._raw["obs"] = h
+        state.obs = h
+        return h
+
 
 class RenderRolloutWrapperTracking:
     """custom_brax/custom_wrappers.py:82-125: "always resets to 0" -- deterministic start frame for evaluation / rendering

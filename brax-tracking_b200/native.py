@@ -129,8 +129,12 @@ class NativeModel:
     def _p(self, t, shape, dtype=None):
         torch = self._torch()
         dtype = dtype or torch.float32
-        if t.dtype != dtype or not t.is_contiguous() or tuple(t.shape) != tuple(shape) or t.device != self._dev():
-            raise ValueError(f"expected a contiguous {dtype} tensor of shape {tuple(shape)} on cuda:{self.device}, got {t.dtype} {tuple(t.shape)}")
+        # page-locked host tensors are accepted too: under unified addressing the kernel writes them through the same pointer
+        # (zero-copy device->host, used for the observation rows of host-side consumers)
+        on_dev = t.device == self._dev() or (t.device.type == "cpu" and t.is_pinned())
+        if t.dtype != dtype or not t.is_contiguous() or tuple(t.shape) != tuple(shape) or not on_dev:
+            raise ValueError(f"expected a contiguous {dtype} tensor of shape {tuple(shape)} on cuda:{self.device} (or pinned host memory), "
+                             f"got {t.dtype} {tuple(t.shape)} on {t.device}")
         return C.c_void_p(t.data_ptr())
 
     def _stream(self):

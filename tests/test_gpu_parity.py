@@ -104,6 +104,26 @@ def test_full_size_properties(rodent_cuda):
     assert set(np.unique(out_a["done"])) <= {0.0, 1.0}
 
 
+def test_host_bound_observations():
+    """wrap(env).bind_host_obs: the kernel writes the observation rows into page-locked host memory (zero-copy);
+    the rows equal the device-resident ones of an identical rollout, bit for bit."""
+    import torch
+    from brax_tracking_b200 import envs
+    m, cfg, clip, _ = common.setup("rodent")
+    n = 96
+    keys = common.jax_keys(n, seed=4)
+    acts = torch.from_numpy(common.actions(3, n, m.nu, seed=6, scale=0.5)).cuda()
+    env = envs.wrap(envs.RodentSingleClip(clip, mj_model=m), episode_length=cfg["episode_length"])
+    sd, sh = env.reset(keys), env.reset(keys)
+    h = env.bind_host_obs(sh)
+    assert h.is_pinned() and sh.obs is h
+    for t in range(3):
+        sd, sh = env.step(sd, acts[t]), env.step(sh, acts[t])
+        torch.cuda.synchronize()
+        assert np.array_equal(sd.obs.cpu().numpy(), h.numpy())
+        assert np.array_equal(sd.reward.cpu().numpy(), sh.reward.cpu().numpy())
+
+
 def test_two_rodent_stress_model():
     """configs[3]: 4096-env kernel variant (5 dof slots, 4 contact slots per lane)."""
     from backends import CudaBackend
