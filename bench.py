@@ -158,6 +158,7 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=dev)
     n, K, Wm = args.envs, args.steps, args.warmup
     base = presets.make_env(args.model, device=local)
