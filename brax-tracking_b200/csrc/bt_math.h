@@ -145,6 +145,16 @@ BT_DEV void bt_ld12(const float* p, float* o) {
   for (int j = 0; j < 12; j++) o[j] = p[j];
 #endif
 }
+// 16-byte aligned 12-float record store (a then b)
+BT_DEV void bt_st12(float* p, const float* a, const float* b) {
+#ifdef __CUDACC__
+  *reinterpret_cast<float4*>(p) = make_float4(a[0], a[1], a[2], a[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(a[4], a[5], b[0], b[1]);
+  *reinterpret_cast<float4*>(p + 8) = make_float4(b[2], b[3], b[4], b[5]);
+#else
+  for (int j = 0; j < 6; j++) { p[j] = a[j]; p[6 + j] = b[j]; }
+#endif
+}
 BT_DEV void bt_ld6(const float* p, float* o) {
 #ifdef __CUDACC__
   const float4 a = *reinterpret_cast<const float4*>(p);

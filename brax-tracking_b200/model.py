@@ -490,6 +490,7 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
     R("actdot", max(na, 1))
     # pvec (sweep state, 6/dof) and the solver vectors behind it are contiguous: together they hold cvel/cacc (12/dof)
     # during the forward tree pass, when none of them is live
+    ALIGN4()   # 16-byte aligned: the 12-float (cvel | cacc) records of the velocity sweep move with 128-bit accesses
     w12 = off
     R("pvec", max(6 * nv, 48 * nchain))  # also the 8 x 6 chain-top rows of aba_factor
     for v in ("qfrc_smooth", "qacc_smooth", "qacc", "search", "qfrc_c"):
