@@ -187,8 +187,14 @@ def train(environment, num_timesteps: int, episode_length: int, action_repeat: i
           normalize_observations: bool = False, reward_scaling: float = 1.0, clipping_epsilon: float = 0.3, gae_lambda: float = 0.95,
           policy_hidden_layer_sizes: Sequence[int] = (256, 256), value_hidden_layer_sizes: Sequence[int] = (256, 256),
           progress_fn: Callable[[int, Dict], None] = lambda *a: None, normalize_advantage: bool = True,
-          policy_params_fn: Callable[..., None] = lambda *a: None, restore_checkpoint_path: Optional[str] = None):
-    """PPO training on the fused B200 step.  Returns (make_policy, params, metrics) like the reference."""
+          policy_params_fn: Callable[..., None] = lambda *a: None, restore_checkpoint_path: Optional[str] = None,
+          matmul_precision: str = "tf32"):
+    """PPO training on the fused B200 step.  Returns (make_policy, params, metrics) like the reference.
+
+    ``matmul_precision``: "tf32" (default; what XLA's DEFAULT precision gives the reference's f32 MLPs on Ampere and later
+    GPUs) or "highest" (plain fp32 matmuls)."""
+    torch.backends.cuda.matmul.allow_tf32 = matmul_precision == "tf32"
+    torch.backends.cudnn.allow_tf32 = matmul_precision == "tf32"
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
     assert batch_size * num_minibatches % num_envs == 0                      # custom_ppo.py:152
