@@ -173,6 +173,19 @@ struct BtEnv {
   BT_DEV float* search() const { return s + m.o_search; }
   BT_DEV float* qfrc_c() const { return s + m.o_qfrc_c; }
   BT_DEV float* tmpv() const { return s + m.o_tmpv; }
+  // chain descriptor (model.py: chain_desc) and the 8-float slot that hands a chain's sweep state to its parent / children
+  struct ChainD { int k0, kb, pc, cadr, nch, sadr, nseg, pdof; };
+  BT_DEV ChainD chain_d(int c) const {
+#ifdef __CUDACC__
+    const int4 a = __ldg(reinterpret_cast<const int4*>(m.chain_desc + 8 * c));
+    const int4 b = __ldg(reinterpret_cast<const int4*>(m.chain_desc + 8 * c + 4));
+    return ChainD{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#else
+    const int* d = m.chain_desc + 8 * c;
+    return ChainD{d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7]};
+#endif
+  }
+  BT_DEV float* ctop(int c) const { return pvec() + 8 * c; }
   // T-region views during the constraint phase
   BT_DEV float* congeo() const { return T(); }                          // [ncon][12] off(3) frame(9)
   BT_DEV float* wrench() const { return T() + 12 * m.ncon; }            // [ncon][6]
@@ -413,8 +426,8 @@ struct BtEnv {
     for (int cl = 0; cl < m.nhlev; cl++) {
       const int c0 = BT_LDG(m.hlev_adr + cl), c1 = BT_LDG(m.hlev_adr + cl + 1);
       for (int ci = c0 + lane; ci < c1; ci += G) {
-        const int c = BT_LDG(m.hlev_chain + ci), k0 = BT_LDG(m.chain_k0 + c), kb = k0 + BT_LDG(m.chain_len + c) - 1;
-        const int par = BT_LDG(m.dof_parentid + k0);
+        const ChainD chd = chain_d(BT_LDG(m.hlev_chain + ci));
+        const int k0 = chd.k0, kb = chd.kb, par = chd.pdof;
         float cvel[6], cacc[6], snap[6];
         if (par >= 0) {
           float r12[12];
@@ -614,22 +627,27 @@ struct BtEnv {
       const int c0 = BT_LDG(m.clev_adr + cl), c1 = BT_LDG(m.clev_adr + cl + 1);
       for (int cb = c0; cb < c1; cb += kNG) {
         const int ci = cb + grp;
-        int c = 0, k0 = 0, kb = -1;
-        if (ci < c1) { c = BT_LDG(m.clev_chain + ci); k0 = BT_LDG(m.chain_k0 + c); kb = k0 + BT_LDG(m.chain_len + c) - 1; }
+        int c = 0, k0 = 0, kb = -1, cadr = 0, nch = 0;
+        if (ci < c1) {
+          c = BT_LDG(m.clev_chain + ci);
+          const ChainD cd = chain_d(c);
+          k0 = cd.k0; kb = cd.kb; cadr = cd.cadr; nch = cd.nch;
+        }
         const int maxlen = W::allmax(kb - k0 + 1);
         float a[kNR][6];
 #pragma unroll
         for (int i = 0; i < kNR; i++)
 #pragma unroll
           for (int j = 0; j < 6; j++) a[i][j] = 0.f;
-        if (kb >= 0)
-          for (int e = BT_LDG(m.dchild_adr + kb); e < BT_LDG(m.dchild_adr + kb + 1); e++) {
-            const float* cr = Ab + 48 * BT_LDG(m.dof_chain + BT_LDG(m.dchild_id + e));
+        for (int e = 0; e < nch; e++) {
+          {
+            const float* cr = Ab + 48 * BT_LDG(m.cchild_id + cadr + e);
 #pragma unroll
             for (int i = 0; i < kNR; i++)
 #pragma unroll
               for (int j = 0; j < 6; j++) a[i][j] += cr[6 * (rl + i) + j];
           }
+        }
         // running cursors of this group's current dof (they freeze on the last dof once the chain is exhausted, so
         // predicated-off lanes keep reading valid memory and store nothing)
         const int nstep = kb - k0 + 1;            // <= 0: no chain in this pass
@@ -710,16 +728,18 @@ struct BtEnv {
   // kMul = true: the leaves->root half of y = M v (y_k = w_k + S_k . q; q += G_k w_k), w from mulM_down
   template <bool kMul>
   BT_DEV void sweep_up(float* x, float* y) {
-    float* pv = pvec();
     for (int cl = m.nhlev - 1; cl >= 0; cl--) {
       const int c0 = BT_LDG(m.hlev_adr + cl), c1 = BT_LDG(m.hlev_adr + cl + 1);
       for (int ci = c0 + lane; ci < c1; ci += G) {
-        const int c = BT_LDG(m.hlev_chain + ci), k0 = BT_LDG(m.chain_k0 + c), kb = k0 + BT_LDG(m.chain_len + c) - 1;
+        const int c = BT_LDG(m.hlev_chain + ci);
+        const ChainD cd = chain_d(c);
+        const int k0 = cd.k0, kb = cd.kb;
         float p[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int e = BT_LDG(m.dchild_adr + kb); e < BT_LDG(m.dchild_adr + kb + 1); e++) {
-          const int ch = BT_LDG(m.dchild_id + e);
+        for (int e = 0; e < cd.nch; e++) {
+          float t6[6];
+          bt_ld6(ctop(BT_LDG(m.cchild_id + cd.cadr + e)), t6);
 #pragma unroll
-          for (int j = 0; j < 6; j++) p[j] += pv[6 * ch + j];
+          for (int j = 0; j < 6; j++) p[j] += t6[j];
         }
         // running cursors at dof k: the pair (k, k - 1) is addressed with immediate offsets
         const float* rp = cdof() + 12 * kb;
@@ -753,8 +773,7 @@ struct BtEnv {
           if (kMul) yq -= 2;
         }
         if (k == k0) step(A, xa, da, 0);
-#pragma unroll
-        for (int j = 0; j < 6; j++) pv[6 * k0 + j] = p[j];
+        bt_st6(ctop(c), p);
       }
       W::sync();
     }
@@ -763,17 +782,14 @@ struct BtEnv {
   // A chain is walked in SEGMENTS that end at the last dof of a contact body (seg_* tables), where `a` is written to cbout.
   template <bool kMul>
   BT_DEV void sweep_down(const float* in, const float* dscale, float* out, float* cbout) {
-    float* pv = pvec();
     for (int cl = 0; cl < m.nhlev; cl++) {
       const int c0 = BT_LDG(m.hlev_adr + cl), c1 = BT_LDG(m.hlev_adr + cl + 1);
       for (int ci = c0 + lane; ci < c1; ci += G) {
-        const int c = BT_LDG(m.hlev_chain + ci), k0 = BT_LDG(m.chain_k0 + c), kb = k0 + BT_LDG(m.chain_len + c) - 1;
-        const int par = BT_LDG(m.dof_parentid + k0);
+        const int c = BT_LDG(m.hlev_chain + ci);
+        const ChainD cd = chain_d(c);
+        const int k0 = cd.k0;
         float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (par >= 0) {
-#pragma unroll
-          for (int j = 0; j < 6; j++) a[j] = pv[6 * par + j];
-        }
+        if (cd.pc >= 0) bt_ld6(ctop(cd.pc), a);
         // running cursors at dof k: the pair (k, k + 1) is addressed with immediate offsets
         const float* rp = cdof() + 12 * k0;
         const float* iq = in + k0;
@@ -796,7 +812,7 @@ struct BtEnv {
         };
         float A[12], B[12], ia, da = 0.f, ib, db = 0.f;
         int k = k0;
-        for (int sgi = BT_LDG(m.seg_adr + c); sgi < BT_LDG(m.seg_adr + c + 1); sgi++) {
+        for (int sgi = cd.sadr; sgi < cd.sadr + cd.nseg; sgi++) {
           const int ke = BT_LDG(m.seg_end + sgi);
           load(0, A, ia, da);
           for (; k < ke; k += 2) {
@@ -818,8 +834,7 @@ struct BtEnv {
             for (int j = 0; j < 6; j++) cbout[6 * cbi + j] = a[j];
           }
         }
-#pragma unroll
-        for (int j = 0; j < 6; j++) pv[6 * kb + j] = a[j];
+        bt_st6(ctop(c), a);
       }
       W::sync();
     }

@@ -155,6 +155,15 @@ BT_DEV void bt_st12(float* p, const float* a, const float* b) {
   for (int j = 0; j < 6; j++) { p[j] = a[j]; p[6 + j] = b[j]; }
 #endif
 }
+// 6 floats to a 16-byte aligned slot
+BT_DEV void bt_st6(float* p, const float* a) {
+#ifdef __CUDACC__
+  *reinterpret_cast<float4*>(p) = make_float4(a[0], a[1], a[2], a[3]);
+  *reinterpret_cast<float2*>(p + 4) = make_float2(a[4], a[5]);
+#else
+  for (int j = 0; j < 6; j++) p[j] = a[j];
+#endif
+}
 BT_DEV void bt_ld6(const float* p, float* o) {
 #ifdef __CUDACC__
   const float4 a = *reinterpret_cast<const float4*>(p);

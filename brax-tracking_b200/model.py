@@ -329,6 +329,25 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
             seg_end.append(kb); seg_cb.append(-1)
         seg_adr.append(len(seg_end))
     t["seg_adr"] = _i(seg_adr); t["seg_end"] = _i(seg_end); t["seg_cb"] = _i(seg_cb)
+    # one 8-int descriptor per chain (two 128-bit loads in the sweep prologues): k0, kb, parent chain, first child slot,
+    # number of child chains, first segment, number of segments, parent dof
+    cchild = [[] for _ in range(nchain)]
+    cparent = np.full(nchain, -1, dtype=np.int32)
+    for c in range(nchain):
+        par = a["dof_parentid"][chain_k0[c]]
+        if par >= 0:
+            cparent[c] = dof_chain[par]
+            assert par == chain_k0[cparent[c]] + chain_len[cparent[c]] - 1, "child chains attach at the end of the parent chain"
+            cchild[cparent[c]].append(c)
+    cchild_adr, cchild_id = [0], []
+    for c in range(nchain):
+        cchild_id.extend(cchild[c]); cchild_adr.append(len(cchild_id))
+    desc = np.zeros((max(nchain, 1), 8), dtype=np.int32)
+    for c in range(nchain):
+        desc[c] = [chain_k0[c], chain_k0[c] + chain_len[c] - 1, cparent[c], cchild_adr[c], len(cchild[c]),
+                   seg_adr[c], seg_adr[c + 1] - seg_adr[c], a["dof_parentid"][chain_k0[c]]]
+    t["chain_desc"] = desc.reshape(-1)
+    t["cchild_id"] = _i(cchild_id) if cchild_id else np.zeros(1, np.int32)
     cb_adr, cb_dof = [0], []
     for b in cbs:
         cb_dof.extend(chain(b))
