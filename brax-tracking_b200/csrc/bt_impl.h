@@ -658,10 +658,12 @@ struct BtEnv {
         float* outp[kNR];
 #pragma unroll
         for (int i = 0; i < kNR; i++) outp[i] = s + rbase[i] + kc * rstride[i];
+        int rbn = nstep > 0 ? BT_LDG(m.dof_irec + kc) : -1;  // link record of the current dof, fetched one step ahead
         for (int t = 0; t < maxlen; t++) {
           const bool act = t < nstep;
           float S[6], u[kNR], U[7];
-          const int rb = act ? BT_LDG(m.dof_irec + kc) : -1;
+          const int rb = rbn;
+          rbn = t + 1 < nstep ? BT_LDG(m.dof_irec + kc - 1) : -1;
           if (rb >= 0) {
 #pragma unroll
             for (int i = 0; i < kNR; i++) {
@@ -1195,8 +1197,11 @@ struct BtEnv {
     for (int it = lane; it < m.ncb * 6; it += G) {
       const int cb = it / 6, j = it - cb * 6;
       float acc = 0.f;
-      for (int k = BT_LDG(m.cbcon_adr + cb); k < BT_LDG(m.cbcon_adr + cb + 1); k++)
-        acc += BT_LDG(m.cbcon_sign + k) * wrench()[6 * BT_LDG(m.cbcon_c + k) + j];
+      for (int k = BT_LDG(m.cbcon_adr + cb), k1 = BT_LDG(m.cbcon_adr + cb + 1); k < k1; k++) {
+        const int cs = BT_LDG(m.cbcon_cs + k);  // contact index, sign in the top bit (body of geom1: -1)
+        const float w = wrench()[6 * (cs & 0x7fffffff) + j];
+        acc += cs < 0 ? -w : w;
+      }
       cbA()[it] = acc;
     }
     W::sync();
@@ -1207,7 +1212,7 @@ struct BtEnv {
         float acc = e.lsg[sl] * lforce[sl];
         float S[6];
         bt_ld6(cdof() + 12 * i, S);
-        for (int k = BT_LDG(m.dofcb_adr + i); k < BT_LDG(m.dofcb_adr + i + 1); k++) acc += bt_dot6(S, cbA() + 6 * BT_LDG(m.dofcb_id + k));
+        for (int k = BT_LDG(m.dofcb_adr + i), k1 = BT_LDG(m.dofcb_adr + i + 1); k < k1; k++) acc += bt_dot6(S, cbA() + 6 * BT_LDG(m.dofcb_id + k));
         qfrc_c()[i] = acc;
       }
     }

@@ -402,6 +402,9 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
         dofcb_id.extend(dofcb[d])
         dofcb_adr.append(len(dofcb_id))
     t["cbcon_adr"] = _i(cbcon_adr); t["cbcon_c"] = _i(cbcon_c) if cbcon_c else Z(1, np.int32)
+    # contact index with the sign in the top bit (one load per term of the contact-body wrench sums)
+    t["cbcon_cs"] = (np.array([c | (0x80000000 if sg < 0 else 0) for c, sg in zip(cbcon_c, cbcon_s)], dtype=np.uint32).view(np.int32)
+                     if cbcon_c else Z(1, np.int32))
     t["cbcon_sign"] = _f(cbcon_s) if cbcon_s else Z(1, np.float32)
     t["dofcb_adr"] = _i(dofcb_adr); t["dofcb_id"] = _i(dofcb_id) if dofcb_id else Z(1, np.int32)
 
