@@ -188,7 +188,7 @@ def train(environment, num_timesteps: int, episode_length: int, action_repeat: i
           policy_hidden_layer_sizes: Sequence[int] = (256, 256), value_hidden_layer_sizes: Sequence[int] = (256, 256),
           progress_fn: Callable[[int, Dict], None] = lambda *a: None, normalize_advantage: bool = True,
           policy_params_fn: Callable[..., None] = lambda *a: None, restore_checkpoint_path: Optional[str] = None,
-          matmul_precision: str = "tf32"):
+          matmul_precision: str = "tf32", use_cuda_graph: bool = True):
     """PPO training on the fused B200 step.  Returns (make_policy, params, metrics) like the reference.
 
     ``matmul_precision``: "tf32" (default; what XLA's DEFAULT precision gives the reference's f32 MLPs on Ampere and later
@@ -219,7 +219,7 @@ def train(environment, num_timesteps: int, episode_length: int, action_repeat: i
     policy = MLP([obs_size, *policy_hidden_layer_sizes, 2 * nu]).to(device)
     value = MLP([obs_size, *value_hidden_layer_sizes, 1]).to(device)
     params = list(policy.parameters()) + list(value.parameters())
-    opt = torch.optim.Adam(params, lr=learning_rate, eps=1e-8)
+    opt = torch.optim.Adam(params, lr=learning_rate, eps=1e-8, capturable=device.type == "cuda")
     ts = TrainingState(policy, value, opt, RunningStatistics(obs_size, device))
     if restore_checkpoint_path is not None:
         load_checkpoint(ts, restore_checkpoint_path)
@@ -236,11 +236,65 @@ def train(environment, num_timesteps: int, episode_length: int, action_repeat: i
 
     n_unrolls = batch_size * num_minibatches // num_envs
     T = unroll_length
+    # rollout buffers, time-major per unroll; only the LAST next_observation of an unroll is ever used (bootstrap value,
+    # brax compute_ppo_loss: data.next_observation[-1]), so that is all that is kept
     buf = dict(observation=torch.empty(n_unrolls, T, n_local, obs_size, device=device),
-               next_observation=torch.empty(n_unrolls, T, n_local, obs_size, device=device),
+               next_observation=torch.empty(n_unrolls, 1, n_local, obs_size, device=device),
                raw_action=torch.empty(n_unrolls, T, n_local, nu, device=device),
                log_prob=torch.empty(n_unrolls, T, n_local, device=device), reward=torch.empty(n_unrolls, T, n_local, device=device),
                discount=torch.empty(n_unrolls, T, n_local, device=device), truncation=torch.empty(n_unrolls, T, n_local, device=device))
+    # learner-side view of the same data, batch-major [n_unrolls * n_local, T, ...] (custom_ppo.py:316-320), in static
+    # storage so that the minibatch update can be replayed as one CUDA graph
+    B = n_unrolls * n_local
+    data = {k: torch.empty(B, v.shape[1], *v.shape[3:], device=device) for k, v in buf.items()}
+    mb_size = B // num_minibatches
+    mb_idx = torch.zeros(mb_size, dtype=torch.long, device=device)
+    mb_noise = torch.zeros(T, mb_size, nu, device=device)
+    mb_data = {k: torch.empty(mb_size, *v.shape[1:], device=device) for k, v in data.items()}
+    ident = lambda x: x
+    graph = {"g": None, "lm": None, "tried": False}
+
+    def minibatch_update():
+        """One SGD step on the minibatch selected by mb_idx / mb_noise (custom_ppo.py:250-284)."""
+        for k, v in data.items():
+            torch.index_select(v, 0, mb_idx, out=mb_data[k])
+        # observations were normalised once for the whole batch (the statistics are fixed during the SGD epochs)
+        loss, lm = compute_ppo_loss(policy, value, ident, mb_data, mb_noise, entropy_cost, discounting, reward_scaling, gae_lambda,
+                                    clipping_epsilon, normalize_advantage)
+        opt.zero_grad(set_to_none=False)
+        loss.backward()
+        if world > 1:
+            _flat_allreduce_mean(params, world)                              # lax.pmean(grads, 'i')
+        opt.step()
+        return lm
+
+    def run_minibatch():
+        if not use_cuda_graph or world > 1 or device.type != "cuda":
+            return minibatch_update()
+        if graph["g"] is None and not graph["tried"]:
+            graph["tried"] = True
+            try:  # three eager (real) updates on a side stream, then capture the fourth
+                side = torch.cuda.Stream(device)
+                side.wait_stream(torch.cuda.current_stream(device))
+                with torch.cuda.stream(side):
+                    for _ in range(3):
+                        minibatch_update()
+                torch.cuda.current_stream(device).wait_stream(side)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    graph["lm"] = minibatch_update()
+                graph["g"] = g
+                g.replay()  # capture only records: this minibatch's update runs now
+                return graph["lm"]
+            except Exception as e:  # pragma: no cover - capture is an optimisation, never a requirement
+                print(f"[ppo] CUDA graph capture of the minibatch update failed ({e!r}); running eagerly", flush=True)
+                graph["g"] = None
+                return minibatch_update()
+        if graph["g"] is None:
+            return minibatch_update()
+        graph["g"].replay()
+        return graph["lm"]
+
     metrics: Dict[str, float] = {}
     t_start = time.time()
     for it in range(num_evals_after_init):
@@ -256,29 +310,26 @@ def train(environment, num_timesteps: int, episode_length: int, action_repeat: i
                     buf["raw_action"][u, t].copy_(raw)
                     buf["log_prob"][u, t].copy_(NormalTanh.log_prob(logits, raw))
                     state = env.step(state, action.contiguous())
-                    buf["next_observation"][u, t].copy_(state.obs)
+                    if t == T - 1:
+                        buf["next_observation"][u, 0].copy_(state.obs)
                     buf["reward"][u, t].copy_(state.reward)
                     buf["discount"][u, t].copy_(1.0 - state.done)
                     buf["truncation"][u, t].copy_(state.info["truncation"])
             ep_reward = float(buf["reward"].mean())
             # [n_unrolls, T, n, ...] -> [n_unrolls * n, T, ...]  (custom_ppo.py:316-320)
-            data = {k: v.transpose(1, 2).reshape(n_unrolls * n_local, T, *v.shape[3:]) for k, v in buf.items()}
+            for k, v in buf.items():
+                data[k].view(n_unrolls, n_local, *data[k].shape[1:]).copy_(v.transpose(1, 2))
             if normalize_observations:
                 ts.normalizer.update(data["observation"], world)             # custom_ppo.py:323-327
+                for k in ("observation", "next_observation"):
+                    data[k].sub_(ts.normalizer.mean).div_(ts.normalizer.std)
             # ---- SGD: num_updates_per_batch x num_minibatches (custom_ppo.py:250-284,329-334)
-            B = data["reward"].shape[0]
             for _ in range(num_updates_per_batch):
                 perm = torch.randperm(B, device=device, generator=gen)
                 for mb in perm.reshape(num_minibatches, -1):
-                    mbd = {k: v[mb] for k, v in data.items()}
-                    noise = torch.randn(T, mb.shape[0], nu, device=device, generator=gen)
-                    loss, lm = compute_ppo_loss(policy, value, norm, mbd, noise, entropy_cost, discounting, reward_scaling, gae_lambda,
-                                                clipping_epsilon, normalize_advantage)
-                    opt.zero_grad(set_to_none=False)
-                    loss.backward()
-                    if world > 1:
-                        _flat_allreduce_mean(params, world)                  # lax.pmean(grads, 'i')
-                    opt.step()
+                    mb_idx.copy_(mb)
+                    mb_noise.normal_(generator=gen)
+                    lm = run_minibatch()
             ts.env_steps += env_step_per_training_step
         torch.cuda.synchronize(device)
         dt = time.time() - t0
