@@ -448,8 +448,10 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
     # ------------------------------------------------------------------ options
     S("cone", m.cone); S("iterations", m.iterations); S("ls_iterations", m.ls_iterations)
     S("n_frames", cfg["n_frames"])
-    # CTA phase alignment of the step kernel: 1 = one barrier per substep (default), 2 = one per control step, 0 = none
-    S("sync_mode", int(os.environ.get("BT_SYNC", "1")))
+    # phase alignment of the step kernel's warps, one barrier per substep (bits, csrc/bt_impl.h::substep): 1 = all warps of
+    # the CTA, 32 / 64 / 128 = only within a contiguous half / equal parity / equal (index mod 4); 2..16 = extra barrier
+    # points; 0 = none.  Measured (rodent, 8192 envs): 0: 1.39 M (r1q), 1: 2.756 M, 32: 2.777 M, 64: 2.781 M, 128: 2.61 M.
+    S("sync_mode", int(os.environ.get("BT_SYNC", "64")))
     SF("timestep", m.timestep)
     SF("grav_x", m.gravity[0]); SF("grav_y", m.gravity[1]); SF("grav_z", m.gravity[2])
     SF("density", m.density); SF("viscosity", m.viscosity); SF("impratio", m.impratio)
