@@ -174,17 +174,19 @@ struct BtEnv {
   BT_DEV float* qfrc_c() const { return s + m.o_qfrc_c; }
   BT_DEV float* tmpv() const { return s + m.o_tmpv; }
   // chain descriptor (model.py: chain_desc) and the 8-float slot that hands a chain's sweep state to its parent / children
-  struct ChainD { int k0, kb, pc, cadr, nch, sadr, nseg, pdof; };
-  BT_DEV ChainD chain_d(int c) const {
+  struct ChainD { int k0, kb, pc, c, cadr, nch, nseg, sadr, pdof; };
+  BT_DEV ChainD desc_at(const int* d) const {
 #ifdef __CUDACC__
-    const int4 a = __ldg(reinterpret_cast<const int4*>(m.chain_desc + 8 * c));
-    const int4 b = __ldg(reinterpret_cast<const int4*>(m.chain_desc + 8 * c + 4));
-    return ChainD{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    const int4 a = __ldg(reinterpret_cast<const int4*>(d));
+    const int4 b = __ldg(reinterpret_cast<const int4*>(d + 4));
+    return ChainD{a.x, a.y, a.z, a.w, b.x, b.y & 0xffff, b.y >> 16, b.z, b.w};
 #else
-    const int* d = m.chain_desc + 8 * c;
-    return ChainD{d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7]};
+    return ChainD{d[0], d[1], d[2], d[3], d[4], d[5] & 0xffff, d[5] >> 16, d[6], d[7]};
 #endif
   }
+  BT_DEV ChainD chain_d(int c) const { return desc_at(m.chain_desc + 8 * c); }
+  // descriptor of the chain that virtual lane `vl` (0..31) walks in pass `ps` of the one-lane-per-chain sweeps (kb < k0: none)
+  BT_DEV ChainD pass_d(int ps, int vl) const { return desc_at(m.hpass_desc + 8 * (32 * ps + vl)); }
   BT_DEV float* ctop(int c) const { return pvec() + 8 * c; }
   // T-region views during the constraint phase
   BT_DEV float* congeo() const { return T(); }                          // [ncon][12] off(3) frame(9)
@@ -423,10 +425,10 @@ struct BtEnv {
     W::sync();
     // ---- velocity sweep on the dof chains: inclusive cvel / cacc per dof (12 floats) in the pvec.. region
     float* cv = pvec();
-    for (int cl = 0; cl < m.nhlev; cl++) {
-      const int c0 = BT_LDG(m.hlev_adr + cl), c1 = BT_LDG(m.hlev_adr + cl + 1);
-      for (int ci = c0 + lane; ci < c1; ci += G) {
-        const ChainD chd = chain_d(BT_LDG(m.hlev_chain + ci));
+    for (int ps = 0; ps < m.nhpass; ps++) {
+      for (int vl = lane; vl < 32; vl += G) {
+        const ChainD chd = pass_d(ps, vl);
+        if (chd.kb < chd.k0) continue;
         const int k0 = chd.k0, kb = chd.kb, par = chd.pdof;
         float cvel[6], cacc[6], snap[6];
         if (par >= 0) {
@@ -730,12 +732,11 @@ struct BtEnv {
   // kMul = true: the leaves->root half of y = M v (y_k = w_k + S_k . q; q += G_k w_k), w from mulM_down
   template <bool kMul>
   BT_DEV void sweep_up(float* x, float* y) {
-    for (int cl = m.nhlev - 1; cl >= 0; cl--) {
-      const int c0 = BT_LDG(m.hlev_adr + cl), c1 = BT_LDG(m.hlev_adr + cl + 1);
-      for (int ci = c0 + lane; ci < c1; ci += G) {
-        const int c = BT_LDG(m.hlev_chain + ci);
-        const ChainD cd = chain_d(c);
-        const int k0 = cd.k0, kb = cd.kb;
+    for (int ps = m.nhpass - 1; ps >= 0; ps--) {
+      for (int vl = lane; vl < 32; vl += G) {
+        const ChainD cd = pass_d(ps, vl);
+        if (cd.kb < cd.k0) continue;
+        const int c = cd.c, k0 = cd.k0, kb = cd.kb;
         float p[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int e = 0; e < cd.nch; e++) {
           float t6[6];
@@ -784,12 +785,11 @@ struct BtEnv {
   // A chain is walked in SEGMENTS that end at the last dof of a contact body (seg_* tables), where `a` is written to cbout.
   template <bool kMul>
   BT_DEV void sweep_down(const float* in, const float* dscale, float* out, float* cbout) {
-    for (int cl = 0; cl < m.nhlev; cl++) {
-      const int c0 = BT_LDG(m.hlev_adr + cl), c1 = BT_LDG(m.hlev_adr + cl + 1);
-      for (int ci = c0 + lane; ci < c1; ci += G) {
-        const int c = BT_LDG(m.hlev_chain + ci);
-        const ChainD cd = chain_d(c);
-        const int k0 = cd.k0;
+    for (int ps = 0; ps < m.nhpass; ps++) {
+      for (int vl = lane; vl < 32; vl += G) {
+        const ChainD cd = pass_d(ps, vl);
+        if (cd.kb < cd.k0) continue;
+        const int c = cd.c, k0 = cd.k0;
         float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (cd.pc >= 0) bt_ld6(ctop(cd.pc), a);
         // running cursors at dof k: the pair (k, k + 1) is addressed with immediate offsets

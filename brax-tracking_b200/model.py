@@ -342,11 +342,25 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
     cchild_adr, cchild_id = [0], []
     for c in range(nchain):
         cchild_id.extend(cchild[c]); cchild_adr.append(len(cchild_id))
+    # k0, kb, parent chain, chain id | first child slot, #children + (#segments << 16), first segment, parent dof
     desc = np.zeros((max(nchain, 1), 8), dtype=np.int32)
     for c in range(nchain):
-        desc[c] = [chain_k0[c], chain_k0[c] + chain_len[c] - 1, cparent[c], cchild_adr[c], len(cchild[c]),
-                   seg_adr[c], seg_adr[c + 1] - seg_adr[c], a["dof_parentid"][chain_k0[c]]]
+        desc[c] = [chain_k0[c], chain_k0[c] + chain_len[c] - 1, cparent[c], c, cchild_adr[c],
+                   len(cchild[c]) | ((seg_adr[c + 1] - seg_adr[c]) << 16), seg_adr[c], a["dof_parentid"][chain_k0[c]]]
     t["chain_desc"] = desc.reshape(-1)
+    # the one-lane-per-chain sweeps read their chain straight from a per-(pass, lane) copy of the descriptor: a pass is up to
+    # 32 chains of one height level (root-most level first); empty lanes carry kb < k0
+    passes = []
+    for L in range(nhlev):
+        cs = [c for c in sorted(range(nchain), key=lambda c: (hlevel[c], c)) if hlevel[c] == L]
+        for q in range(0, len(cs), 32):
+            row = np.zeros((32, 8), dtype=np.int32)
+            row[:, 1] = -1
+            for ln, c in enumerate(cs[q:q + 32]):
+                row[ln] = desc[c]
+            passes.append(row)
+    S("nhpass", len(passes))
+    t["hpass_desc"] = np.concatenate(passes).reshape(-1) if passes else np.zeros(256, np.int32)
     t["cchild_id"] = _i(cchild_id) if cchild_id else np.zeros(1, np.int32)
     cb_adr, cb_dof = [0], []
     for b in cbs:
