@@ -245,6 +245,12 @@ struct BtEnv {
         }
       }
     }
+    if (BT_LDG(m.body_parentid + b) == 0) {
+      // directly under the world: already a world pose; it is the reference point of its tree
+      bt_quat_normalize(q);
+      const int rs = BT_LDG(m.body_ref + b);
+      ref()[3 * rs] = p[0]; ref()[3 * rs + 1] = p[1]; ref()[3 * rs + 2] = p[2];
+    }
     float* bp = pose_pos(m.nbanc & 1);
     float* bq = pose_quat(m.nbanc & 1);
 #pragma unroll
@@ -393,12 +399,13 @@ struct BtEnv {
       const float* sq = pose_quat((m.nbanc - r) & 1);
       float* dp = pose_pos((m.nbanc - 1 - r) & 1);
       float* dq = pose_quat((m.nbanc - 1 - r) & 1);
-      const bool last = r == m.nbanc - 1;
-      for (int b = 1 + lane; b < m.nbody; b += G) {
-        const int a = BT_LDG(m.body_anc + r * m.nbody + b);
+      // work list of the round (model.py: cmp_item): compose with the 2^r-th ancestor, or copy a finished pose forward once
+      for (int it = BT_LDG(m.cmp_adr + r) + lane, i1 = BT_LDG(m.cmp_adr + r + 1); it < i1; it += G) {
+        const int w = BT_LDG(m.cmp_item + it);
+        const int b = w & 0xfff, a = (w >> 12) & 0xfff;
         float pos[3] = {sp[3 * b], sp[3 * b + 1], sp[3 * b + 2]};
         float quat[4] = {sq[4 * b], sq[4 * b + 1], sq[4 * b + 2], sq[4 * b + 3]};
-        if (a > 0) {
+        if (!(w & (1 << 29))) {
           const float pa[3] = {sp[3 * a], sp[3 * a + 1], sp[3 * a + 2]};
           const float qa[4] = {sq[4 * a], sq[4 * a + 1], sq[4 * a + 2], sq[4 * a + 3]};
           float rr[3], q2[4];
@@ -406,13 +413,7 @@ struct BtEnv {
           pos[0] = pa[0] + rr[0]; pos[1] = pa[1] + rr[1]; pos[2] = pa[2] + rr[2];
           bt_quat_mul(qa, quat, q2);
           quat[0] = q2[0]; quat[1] = q2[1]; quat[2] = q2[2]; quat[3] = q2[3];
-        }
-        if (last) {
-          bt_quat_normalize(quat);
-          if (BT_LDG(m.body_parentid + b) == 0) {  // reference point of the tree = position of its root body
-            const int rs = BT_LDG(m.body_ref + b);
-            ref()[3 * rs] = pos[0]; ref()[3 * rs + 1] = pos[1]; ref()[3 * rs + 2] = pos[2];
-          }
+          if (w & (1 << 28)) bt_quat_normalize(quat);  // world pose reached
         }
 #pragma unroll
         for (int k = 0; k < 3; k++) dp[3 * b + k] = pos[k];
@@ -1205,14 +1206,27 @@ struct BtEnv {
       cbA()[it] = acc;
     }
     W::sync();
+    // one summed wrench per GROUP of dofs with the same contact bodies below them (in the per-contact wrench slots, which
+    // are dead by now), then one dot product per dof
+    float* wg = wrench();
+    for (int it = lane; it < m.nwgrp * 6; it += G) {
+      const int g = it / 6, j = it - g * 6;
+      float acc = 0.f;
+      for (int k = BT_LDG(m.wgrp_adr + g), k1 = BT_LDG(m.wgrp_adr + g + 1); k < k1; k++) acc += cbA()[6 * BT_LDG(m.wgrp_cb + k) + j];
+      wg[it] = acc;
+    }
+    W::sync();
 #pragma unroll
     for (int sl = 0; sl < DS; sl++) {
       const int i = lane + sl * G;
       if (i < m.nv) {
         float acc = e.lsg[sl] * lforce[sl];
-        float S[6];
-        bt_ld6(cdof() + 12 * i, S);
-        for (int k = BT_LDG(m.dofcb_adr + i), k1 = BT_LDG(m.dofcb_adr + i + 1); k < k1; k++) acc += bt_dot6(S, cbA() + 6 * BT_LDG(m.dofcb_id + k));
+        const int g = BT_LDG(m.dof_wgrp + i);
+        if (g >= 0) {
+          float S[6];
+          bt_ld6(cdof() + 12 * i, S);
+          acc += bt_dot6(S, wg + 6 * g);
+        }
         qfrc_c()[i] = acc;
       }
     }

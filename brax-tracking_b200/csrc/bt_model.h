@@ -9,7 +9,7 @@
 
 // ---- scalar ints (1-element int tables, by name) ----
 #define BT_INT_SCALARS(X) \
-  X(nq) X(nv) X(nu) X(na) X(nbody) X(njnt) X(nlevel) X(nchain) X(nclev) X(nhlev) X(nhpass) X(nbchain) X(nbclev) X(nbanc) X(nroot) X(ncon) X(ncgeom) X(ncb) X(nmerge)           \
+  X(nq) X(nv) X(nu) X(na) X(nbody) X(njnt) X(nlevel) X(nchain) X(nclev) X(nhlev) X(nhpass) X(nbchain) X(nbclev) X(nbanc) X(nroot) X(ncon) X(ncgeom) X(ncb) X(nwgrp) X(nmerge)           \
   X(cone) X(iterations) X(ls_iterations) X(n_frames) X(sync_mode)                                                           \
   /* env layer */                                                                                               \
   X(free_jnt) X(seed_root_from_clip) X(ref_len) X(clip_len) X(clip_nj) X(n_joint_idxs) X(n_body_idxs)           \
@@ -31,13 +31,13 @@
 // ---- int tables ----
 #define BT_INT_TABLES(X) \
   X(body_parentid) X(body_jntadr) X(body_jntnum) X(body_ref) X(body_flags) X(body_lastdof) X(level_adr) X(level_body) X(child_adr) X(child_id)\
-  X(bchain_b0) X(bchain_len) X(bclev_adr) X(bclev_chain) X(body_anc)                                                        \
+  X(bchain_b0) X(bchain_len) X(bclev_adr) X(bclev_chain) X(body_anc) X(cmp_adr) X(cmp_item)                                                        \
   X(jnt_type) X(jnt_qposadr) X(jnt_dofadr) X(jnt_flags) X(jnt_bodyid)                                                                      \
   X(dof_bodyid) X(dof_parentid) X(dof_qposadr) X(dof_limited) X(dof_vflag)                                                   \
   X(chain_k0) X(chain_len) X(clev_adr) X(clev_chain) X(hlev_adr) X(hlev_chain) X(dof_chain) X(dchild_adr) X(dchild_id) X(dofbody_adr) X(dofbody_id) X(dof_irec) X(merge_adr) X(merge_dst) X(merge_src)                                                                     \
   X(cgeom_bodyid) X(cb_adr) X(cb_dof) X(cb_ref)                                                                 \
   X(con_g1) X(con_g2) X(con_cb1) X(con_cb2) X(con_ref) X(con_fn) X(con_sub) X(con_dim)                          \
-  X(cbcon_adr) X(cbcon_c) X(cbcon_cs) X(dofcb_adr) X(dofcb_id) X(cb_lastdof) X(seg_adr) X(seg_end) X(seg_cb) X(chain_desc) X(cchild_id) X(hpass_desc)                                                                                     \
+  X(cbcon_adr) X(cbcon_c) X(cbcon_cs) X(dof_wgrp) X(wgrp_adr) X(wgrp_cb) X(dofcb_adr) X(dofcb_id) X(cb_lastdof) X(seg_adr) X(seg_end) X(seg_cb) X(chain_desc) X(cchild_id) X(hpass_desc)                                                                                     \
   X(act_wrap_adr) X(act_wrap_qadr) X(act_wrap_dadr) X(dofact_adr) X(dofact_u)                                   \
   X(actuator_dyntype) X(actuator_gaintype) X(actuator_biastype) X(actuator_ctrllimited)                         \
   X(actuator_forcelimited) X(actuator_actadr)                                                                   \

@@ -110,6 +110,24 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
     assert nbanc == 1 or not anc[nbanc - 1][anc[nbanc - 1]].any()
     S("nbanc", nbanc)
     t["body_anc"] = anc.reshape(-1)
+    # per-round work lists of the composition (deepest bodies first, so the lists shrink to fewer 32-lane slots as the
+    # rounds go on): a body is composed while its 2^r-th ancestor exists; the round after it reached the world frame it
+    # copies its pose to the other ping-pong buffer once (later rounds read it from either).  Item = body | ancestor << 12 |
+    # final-after-this-round << 28 | copy-only << 29.
+    assert nbody < 4096
+    order = sorted(range(1, nbody), key=lambda b: -bdepth[b])
+    cmp_adr, cmp_item = [0], []
+    for r in range(nbanc):
+        for b in order:
+            if anc[r][b] > 0:
+                fin = 1 if (r == nbanc - 1 or anc[r + 1][b] == 0) else 0
+                cmp_item.append(b | (int(anc[r][b]) << 12) | (fin << 28))
+        for b in order:   # reached the world frame in the previous round (or, in round 0, directly under the world)
+            was_active = r > 0 and anc[r - 1][b] > 0
+            if anc[r][b] == 0 and (was_active or r == 0):
+                cmp_item.append(b | (1 << 29))
+        cmp_adr.append(len(cmp_item))
+    t["cmp_adr"] = _i(cmp_adr); t["cmp_item"] = _i(cmp_item)
     # reference point of every kinematic tree: the position of the tree's root body (a free root moves with
     # qpos[0:3]; a static root is a model constant).  MJX uses the subtree COM here; any fixed point gives the
     # same qM / qfrc_bias (DESIGN.md "reference point").
@@ -415,6 +433,22 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
     for d in range(nv):
         dofcb_id.extend(dofcb[d])
         dofcb_adr.append(len(dofcb_id))
+    # dofs with the same set of contact bodies below them share one summed wrench: J' f per dof is then ONE dot product
+    # (the root dofs of the rodent see all 8 contact bodies)
+    grp_of, grp_list = {}, []
+    dof_wgrp = np.full(nv, -1, dtype=np.int32)
+    for d in range(nv):
+        if dofcb[d]:
+            key = tuple(sorted(dofcb[d]))
+            if key not in grp_of:
+                grp_of[key] = len(grp_list); grp_list.append(key)
+            dof_wgrp[d] = grp_of[key]
+    wgrp_adr, wgrp_cb = [0], []
+    for key in grp_list:
+        wgrp_cb.extend(key); wgrp_adr.append(len(wgrp_cb))
+    S("nwgrp", len(grp_list))
+    assert 6 * len(grp_list) <= 6 * max(ncon, 1), "the group wrench sums reuse the per-contact wrench slots"
+    t["dof_wgrp"] = dof_wgrp; t["wgrp_adr"] = _i(wgrp_adr); t["wgrp_cb"] = _i(wgrp_cb) if wgrp_cb else Z(1, np.int32)
     t["cbcon_adr"] = _i(cbcon_adr); t["cbcon_c"] = _i(cbcon_c) if cbcon_c else Z(1, np.int32)
     # contact index with the sign in the top bit (one load per term of the contact-body wrench sums)
     t["cbcon_cs"] = (np.array([c | (0x80000000 if sg < 0 else 0) for c, sg in zip(cbcon_c, cbcon_s)], dtype=np.uint32).view(np.int32)
