@@ -203,13 +203,20 @@ struct BtEnv {
   //  * vel_sweep   (lane per dof chain)  cvel / cdof_dot / cacc, carried in registers along the chain;
   //  * body_local  (lane per body)       inertia about the reference point, RNE body force, fluid forces.
   BT_DEV void body_frame(int b) {
-    float p[3] = {BT_LDG(m.body_pos + 3 * b), BT_LDG(m.body_pos + 3 * b + 1), BT_LDG(m.body_pos + 3 * b + 2)};
-    float q[4] = {BT_LDG(m.body_quat + 4 * b), BT_LDG(m.body_quat + 4 * b + 1), BT_LDG(m.body_quat + 4 * b + 2),
-                  BT_LDG(m.body_quat + 4 * b + 3)};
-    const int jadr = BT_LDG(m.body_jntadr + b), jnum = BT_LDG(m.body_jntnum + b);
+    // packed constants (model.py: body_rec = pos quat jntadr jntnum parent ref; jnt_rec = type qposadr dofadr at_origin pos
+    // axis qpos0): three 128-bit loads each
+    float br[12];
+#pragma unroll
+    for (int q4 = 0; q4 < 3; q4++) bt_ldg4(m.body_rec + 12 * b + 4 * q4, br + 4 * q4);
+    float p[3] = {br[0], br[1], br[2]};
+    float q[4] = {br[3], br[4], br[5], br[6]};
+    const int jadr = (int)br[7], jnum = (int)br[8];
     for (int jj = 0; jj < jnum; jj++) {
-      const int j = jadr + jj, qa = BT_LDG(m.jnt_qposadr + j), da = BT_LDG(m.jnt_dofadr + j);
-      if (BT_LDG(m.jnt_type + j) == BT_JNT_FREE) {
+      float jr[12];
+#pragma unroll
+      for (int q4 = 0; q4 < 3; q4++) bt_ldg4(m.jnt_rec + 12 * (jadr + jj) + 4 * q4, jr + 4 * q4);
+      const int qa = (int)jr[1], da = (int)jr[2];
+      if ((int)jr[0] == BT_JNT_FREE) {
         // a free joint hangs off the world: the "local" frame is the absolute pose
         p[0] = qpos()[qa]; p[1] = qpos()[qa + 1]; p[2] = qpos()[qa + 2];
         q[0] = qpos()[qa + 3]; q[1] = qpos()[qa + 4]; q[2] = qpos()[qa + 5]; q[3] = qpos()[qa + 6];
@@ -218,9 +225,9 @@ struct BtEnv {
         // MJX kinematics stores the normalised quaternion back into qpos
         qpos()[qa + 3] = q[0]; qpos()[qa + 4] = q[1]; qpos()[qa + 5] = q[2]; qpos()[qa + 6] = q[3];
       } else {
-        float jp[3] = {BT_LDG(m.jnt_pos + 3 * j), BT_LDG(m.jnt_pos + 3 * j + 1), BT_LDG(m.jnt_pos + 3 * j + 2)};
-        float ja[3] = {BT_LDG(m.jnt_axis + 3 * j), BT_LDG(m.jnt_axis + 3 * j + 1), BT_LDG(m.jnt_axis + 3 * j + 2)};
-        const bool at_origin = BT_LDG(m.jnt_flags + j) & 1;  // model-uniform branch
+        const float jp[3] = {jr[4], jr[5], jr[6]};
+        const float ja[3] = {jr[7], jr[8], jr[9]};
+        const bool at_origin = jr[3] != 0.f;  // model-uniform branch
         float anchor[3] = {p[0], p[1], p[2]}, axis[3], r[3], ql[4], q2[4];
         if (!at_origin) {
           bt_rotate(jp, q, r);
@@ -229,7 +236,7 @@ struct BtEnv {
         bt_rotate(ja, q, axis);
         float* rec = cdof() + 12 * da;  // local axis / anchor, turned into cdof by joint_cdof()
         rec[0] = axis[0]; rec[1] = axis[1]; rec[2] = axis[2]; rec[3] = anchor[0]; rec[4] = anchor[1]; rec[5] = anchor[2];
-        const float ang = 0.5f * (qpos()[qa] - BT_LDG(m.qpos0 + qa));
+        const float ang = 0.5f * (qpos()[qa] - jr[10]);
         float sn, cs_;
 #ifdef __CUDACC__
         sincosf(ang, &sn, &cs_);
@@ -245,10 +252,10 @@ struct BtEnv {
         }
       }
     }
-    if (BT_LDG(m.body_parentid + b) == 0) {
+    if ((int)br[9] == 0) {
       // directly under the world: already a world pose; it is the reference point of its tree
       bt_quat_normalize(q);
-      const int rs = BT_LDG(m.body_ref + b);
+      const int rs = (int)br[10];
       ref()[3 * rs] = p[0]; ref()[3 * rs + 1] = p[1]; ref()[3 * rs + 2] = p[2];
     }
     float* bp = pose_pos(m.nbanc & 1);
@@ -511,49 +518,48 @@ struct BtEnv {
 
   // ================================================================== P3: actuation + smooth generalized forces
   BT_DEV void smooth_forces() {
-    // transmission + fwd_actuation, one lane per actuator
+    // transmission + fwd_actuation, one lane per actuator; the actuator's constants come as one packed
+    // 16-float record (model.py: act_rec; absent limits are +-3e38, non-affine gain / bias terms are zeros)
     for (int u = lane; u < m.nu; u += G) {
-      const float gear = BT_LDG(m.actuator_gear + u);
+      float r[16];
+#pragma unroll
+      for (int q = 0; q < 4; q++) bt_ldg4(m.act_rec + 16 * u + 4 * q, r + 4 * q);
+      const float gear = r[0];
       float len = 0.f, vel = 0.f;
-      for (int w = BT_LDG(m.act_wrap_adr + u); w < BT_LDG(m.act_wrap_adr + u + 1); w++) {
-        const float cf = BT_LDG(m.act_wrap_coef + w);
-        len += cf * qpos()[BT_LDG(m.act_wrap_qadr + w)];
-        vel += cf * qvel()[BT_LDG(m.act_wrap_dadr + w)];
+      for (int w = (int)r[14], w1 = w + (int)r[15]; w < w1; w++) {
+        float wr[4];
+        bt_ldg4(m.wrap_rec + 4 * w, wr);
+        len += wr[0] * qpos()[(int)wr[1]];
+        vel += wr[0] * qvel()[(int)wr[2]];
       }
       len *= gear; vel *= gear;
-      float c = ctrl()[u];
-      if (BT_LDG(m.actuator_ctrllimited + u))
-        c = bt_clampf(c, BT_LDG(m.actuator_ctrlrange + 2 * u), BT_LDG(m.actuator_ctrlrange + 2 * u + 1));
+      const float c = bt_clampf(ctrl()[u], r[1], r[2]);
       float ca = c;
-      const int aa = BT_LDG(m.actuator_actadr + u);
+      const int aa = (int)r[11];
       if (aa >= 0) {
-        float tau = BT_LDG(m.actuator_dynprm + 3 * u);
-        tau = tau < BT_MINVAL ? BT_MINVAL : tau;
         ca = act()[aa];
-        actdot()[aa] = (c - ca) / tau;
+        actdot()[aa] = (c - ca) / r[3];
       }
-      float gain = BT_LDG(m.actuator_gainprm + 3 * u);
-      if (BT_LDG(m.actuator_gaintype + u) == 1)
-        gain += BT_LDG(m.actuator_gainprm + 3 * u + 1) * len + BT_LDG(m.actuator_gainprm + 3 * u + 2) * vel;
-      float bias = 0.f;
-      if (BT_LDG(m.actuator_biastype + u) == 1)
-        bias = BT_LDG(m.actuator_biasprm + 3 * u) + BT_LDG(m.actuator_biasprm + 3 * u + 1) * len +
-               BT_LDG(m.actuator_biasprm + 3 * u + 2) * vel;
-      float f = gain * ca + bias;
-      if (BT_LDG(m.actuator_forcelimited + u))
-        f = bt_clampf(f, BT_LDG(m.actuator_forcerange + 2 * u), BT_LDG(m.actuator_forcerange + 2 * u + 1));
-      aforce()[u] = f;
+      const float gain = r[4] + (r[5] * len + r[6] * vel);
+      const float bias = r[8] + r[9] * len + r[10] * vel;
+      aforce()[u] = bt_clampf(gain * ca + bias, r[12], r[13]);
     }
     // tau = passive + actuator forces; the bias forces (RNE backward half) are subtracted inside aba_factor<true>, which
     // completes qfrc_smooth in place
     W::sync();
     for (int i = lane; i < m.nv; i += G) {
-      float f = -BT_LDG(m.dof_damping + i) * qvel()[i];
-      const int qa = BT_LDG(m.dof_qposadr + i);
-      if (qa >= 0) f -= BT_LDG(m.dof_stiffness + i) * (qpos()[qa] - BT_LDG(m.dof_springref + i));
+      float r[8];
+      bt_ldg4(m.dof_rec + 8 * i, r);
+      bt_ldg2(m.dof_rec + 8 * i + 4, r + 4);
+      float f = -r[0] * qvel()[i];
+      const int qa = (int)r[3];
+      if (qa >= 0) f -= r[1] * (qpos()[qa] - r[2]);
       float fa = 0.f;
-      for (int k = BT_LDG(m.dofact_adr + i); k < BT_LDG(m.dofact_adr + i + 1); k++)
-        fa += BT_LDG(m.dofact_coef + k) * aforce()[BT_LDG(m.dofact_u + k)];
+      for (int k = (int)r[4], k1 = k + (int)r[5]; k < k1; k++) {
+        float ar[2];
+        bt_ldg2(m.dofact_rec + 2 * k, ar);
+        fa += ar[0] * aforce()[(int)ar[1]];
+      }
       qfrc_smooth()[i] = f + fa;
     }
     W::sync();

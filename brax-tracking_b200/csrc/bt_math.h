@@ -155,6 +155,23 @@ BT_DEV void bt_st12(float* p, const float* a, const float* b) {
   for (int j = 0; j < 6; j++) { p[j] = a[j]; p[6 + j] = b[j]; }
 #endif
 }
+// 4 / 2 consecutive table floats through the read-only path (16- / 8-byte aligned)
+BT_DEV void bt_ldg4(const float* p, float* o) {
+#ifdef __CUDACC__
+  const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+  o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+#else
+  for (int j = 0; j < 4; j++) o[j] = p[j];
+#endif
+}
+BT_DEV void bt_ldg2(const float* p, float* o) {
+#ifdef __CUDACC__
+  const float2 v = __ldg(reinterpret_cast<const float2*>(p));
+  o[0] = v.x; o[1] = v.y;
+#else
+  o[0] = p[0]; o[1] = p[1];
+#endif
+}
 // 6 floats to a 16-byte aligned slot
 BT_DEV void bt_st6(float* p, const float* a) {
 #ifdef __CUDACC__

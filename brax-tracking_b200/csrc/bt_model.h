@@ -51,7 +51,7 @@
   X(dof_margin) X(dof_invweight0)                                                                               \
   X(cgeom_pos) X(cgeom_quat) X(cgeom_size)                                                                      \
   X(con_mu) X(con_solref) X(con_solimp) X(con_includemargin) X(con_invweight) X(cbcon_sign)                    \
-  X(act_wrap_coef) X(dofact_coef)                                                                               \
+  X(act_wrap_coef) X(dofact_coef) X(act_rec) X(wrap_rec) X(dof_rec) X(dofact_rec) X(body_rec) X(jnt_rec)                                                                               \
   X(actuator_gear) X(actuator_gainprm) X(actuator_biasprm) X(actuator_dynprm) X(actuator_ctrlrange)             \
   X(actuator_forcerange)                                                                                        \
   X(clip_position) X(clip_quaternion) X(clip_joints) X(clip_body_positions) X(clip_angular_velocity)

@@ -173,6 +173,19 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
             bj = a["jnt_bodyid"][j]
             assert parent[bj] == 0 and a["body_jntnum"][bj] == 1, "free joints must be the only joint of a tree root"
     t["qpos0"] = _f(a["qpos0"])
+    # packed constant records of body_frame (three 128-bit loads per body / per joint instead of ~10 scalar table reads)
+    body_rec = np.zeros((nbody, 12), dtype=np.float32)
+    for b in range(nbody):
+        body_rec[b, 0:3] = a["body_pos"][b]; body_rec[b, 3:7] = a["body_quat"][b]
+        body_rec[b, 7:11] = [a["body_jntadr"][b], a["body_jntnum"][b], parent[b], body_ref[b]]
+    t["body_rec"] = body_rec.reshape(-1)
+    jnt_rec = np.zeros((max(njnt, 1), 12), dtype=np.float32)
+    for j in range(njnt):
+        qa = int(a["jnt_qposadr"][j])
+        jnt_rec[j, 0:4] = [a["jnt_type"][j], qa, a["jnt_dofadr"][j], float(np.abs(a["jnt_pos"][j]).max() == 0.0)]
+        jnt_rec[j, 4:7] = a["jnt_pos"][j]; jnt_rec[j, 7:10] = a["jnt_axis"][j]
+        jnt_rec[j, 10] = a["qpos0"][qa]
+    t["jnt_rec"] = jnt_rec.reshape(-1)
     dof_jnt = a["dof_jntid"]
     dof_qadr = np.full(nv, -1, dtype=np.int32)
     dof_stiff = np.zeros(nv); dof_spring = np.zeros(nv)
@@ -485,6 +498,31 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
         for u, cf in dofact[d]:
             dofact_u.append(u); dofact_coef.append(cf)
         dofact_adr.append(len(dofact_u))
+    # packed per-actuator / per-dof constant records of smooth_forces (128-bit loads instead of ~20 scalar table reads)
+    BIG = np.float32(3.0e38)
+    act_rec = np.zeros((max(nu, 1), 16), dtype=np.float32)
+    for u in range(nu):
+        lim = bool(a["actuator_ctrllimited"][u]); flim = bool(a["actuator_forcelimited"][u])
+        aff_g = int(a["actuator_gaintype"][u]) == 1; aff_b = int(a["actuator_biastype"][u]) == 1
+        gp, bp = a["actuator_gainprm"][u], a["actuator_biasprm"][u]
+        act_rec[u] = [a["actuator_gear"][u],
+                      a["actuator_ctrlrange"][u][0] if lim else -BIG, a["actuator_ctrlrange"][u][1] if lim else BIG,
+                      max(float(a["actuator_dynprm"][u][0]), 1e-15),
+                      gp[0], gp[1] if aff_g else 0.0, gp[2] if aff_g else 0.0, 0.0,
+                      bp[0] if aff_b else 0.0, bp[1] if aff_b else 0.0, bp[2] if aff_b else 0.0, float(a["actuator_actadr"][u]),
+                      a["actuator_forcerange"][u][0] if flim else -BIG, a["actuator_forcerange"][u][1] if flim else BIG,
+                      float(wrap_adr[u]), float(wrap_adr[u + 1] - wrap_adr[u])]
+    t["act_rec"] = act_rec.reshape(-1)
+    wrap_d = [q2d[int(q)] for q in wrap_q]
+    t["wrap_rec"] = (np.array([[cf, q, d, 0.0] for cf, q, d in zip(wrap_coef, wrap_q, wrap_d)], dtype=np.float32).reshape(-1)
+                     if wrap_q else Z(4, np.float32))
+    dof_rec = np.zeros((nv, 8), dtype=np.float32)
+    for d in range(nv):
+        dof_rec[d] = [a["dof_damping"][d], dof_stiff[d], dof_spring[d], float(dof_qadr[d]), float(dofact_adr[d]),
+                      float(dofact_adr[d + 1] - dofact_adr[d]), 0.0, 0.0]
+    t["dof_rec"] = dof_rec.reshape(-1)
+    t["dofact_rec"] = (np.array([[cf, u] for cf, u in zip(dofact_coef, dofact_u)], dtype=np.float32).reshape(-1)
+                       if dofact_u else Z(2, np.float32))
     t["dofact_adr"] = _i(dofact_adr)
     t["dofact_u"] = _i(dofact_u) if dofact_u else Z(1, np.int32)
     t["dofact_coef"] = _f(dofact_coef) if dofact_coef else Z(1, np.float32)
