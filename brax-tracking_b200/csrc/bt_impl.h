@@ -306,12 +306,15 @@ struct BtEnv {
   BT_DEV void body_local(int b) {
     const float* cv = pvec();
     float pos[3], quat[4], cvel[6], cacc[6], rp[3];
-    const int rs = BT_LDG(m.body_ref + b);
+    float br[16];  // packed constants (model.py: bl_rec = ipos iquat inertia mass | fluidbox lastdof ref)
+#pragma unroll
+    for (int q4 = 0; q4 < 4; q4++) bt_ldg4(m.bl_rec + 16 * b + 4 * q4, br + 4 * q4);
+    const int rs = (int)br[15];
 #pragma unroll
     for (int k = 0; k < 3; k++) { pos[k] = xpos()[3 * b + k]; rp[k] = ref()[3 * rs + k]; }
 #pragma unroll
     for (int k = 0; k < 4; k++) quat[k] = xquat()[4 * b + k];
-    const int ld = BT_LDG(m.body_lastdof + b);  // last dof on the chain root -> body: the body moves with it
+    const int ld = (int)br[14];  // last dof on the chain root -> body: the body moves with it
     if (ld >= 0) {
       float r12[12];
       bt_ld12(cv + 12 * ld, r12);
@@ -324,13 +327,12 @@ struct BtEnv {
       cacc[3] = -m.grav_x; cacc[4] = -m.grav_y; cacc[5] = -m.grav_z;
     }
     // body inertia about the tree reference point, world axes
-    const float mass = BT_LDG(m.body_mass + b);
+    const float mass = br[10];
     float ci[10], cf[6];
     {
-      float ip[3] = {BT_LDG(m.body_ipos + 3 * b), BT_LDG(m.body_ipos + 3 * b + 1), BT_LDG(m.body_ipos + 3 * b + 2)};
-      float iq[4] = {BT_LDG(m.body_iquat + 4 * b), BT_LDG(m.body_iquat + 4 * b + 1), BT_LDG(m.body_iquat + 4 * b + 2),
-                     BT_LDG(m.body_iquat + 4 * b + 3)};
-      float in[3] = {BT_LDG(m.body_inertia + 3 * b), BT_LDG(m.body_inertia + 3 * b + 1), BT_LDG(m.body_inertia + 3 * b + 2)};
+      float ip[3] = {br[0], br[1], br[2]};
+      float iq[4] = {br[3], br[4], br[5], br[6]};
+      float in[3] = {br[7], br[8], br[9]};
       float r[3], q2[4], R[9], off[3];
       bt_rotate(ip, quat, r);
       off[0] = pos[0] + r[0] - rp[0]; off[1] = pos[1] + r[1] - rp[1]; off[2] = pos[2] + r[2] - rp[2];
@@ -352,7 +354,7 @@ struct BtEnv {
       for (int k = 0; k < 6; k++) cf[k] = t1[k] + t3[k];
       // passive fluid forces (inertia-box model): a wrench on the body, folded into cfrc with opposite sign
       if ((m.density > 0.f || m.viscosity > 0.f) && mass > 0.f) {
-        float box[3] = {BT_LDG(m.body_fluidbox + 3 * b), BT_LDG(m.body_fluidbox + 3 * b + 1), BT_LDG(m.body_fluidbox + 3 * b + 2)};
+        float box[3] = {br[11], br[12], br[13]};
         float c[3], lin[3], lang[3], llin[3], lf[6] = {0, 0, 0, 0, 0, 0};
         bt_cross(off, cvel, c);
         lin[0] = cvel[3] - c[0]; lin[1] = cvel[4] - c[1]; lin[2] = cvel[5] - c[2];
@@ -632,16 +634,10 @@ struct BtEnv {
     W::sync();
     // The chain loops are warp-uniform (every lane runs the longest chain of the pass; shorter / absent chains are
     // predicated off), so the row exchange is a full-mask shuffle and there is no divergence bookkeeping.
-    for (int cl = m.nclev - 1; cl >= 0; cl--) {
-      const int c0 = BT_LDG(m.clev_adr + cl), c1 = BT_LDG(m.clev_adr + cl + 1);
-      for (int cb = c0; cb < c1; cb += kNG) {
-        const int ci = cb + grp;
-        int c = 0, k0 = 0, kb = -1, cadr = 0, nch = 0;
-        if (ci < c1) {
-          c = BT_LDG(m.clev_chain + ci);
-          const ChainD cd = chain_d(c);
-          k0 = cd.k0; kb = cd.kb; cadr = cd.cadr; nch = cd.nch;
-        }
+    for (int ps = 0; ps < m.napass; ps++) {
+      for (int vg = grp; vg < 4; vg += kNG) {  // one iteration on the device (four 8-lane groups); four on the 1-lane host build
+        const ChainD cd = desc_at(m.apass_desc + 8 * (4 * ps + vg));
+        const int c = cd.c, k0 = cd.k0, kb = cd.kb, cadr = cd.cadr, nch = cd.nch;
         const int maxlen = W::allmax(kb - k0 + 1);
         float a[kNR][6];
 #pragma unroll

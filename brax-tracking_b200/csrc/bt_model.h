@@ -9,7 +9,7 @@
 
 // ---- scalar ints (1-element int tables, by name) ----
 #define BT_INT_SCALARS(X) \
-  X(nq) X(nv) X(nu) X(na) X(nbody) X(njnt) X(nlevel) X(nchain) X(nclev) X(nhlev) X(nhpass) X(nbchain) X(nbclev) X(nbanc) X(nroot) X(ncon) X(ncgeom) X(ncb) X(nwgrp) X(nmerge)           \
+  X(nq) X(nv) X(nu) X(na) X(nbody) X(njnt) X(nlevel) X(nchain) X(nclev) X(nhlev) X(nhpass) X(napass) X(nbchain) X(nbclev) X(nbanc) X(nroot) X(ncon) X(ncgeom) X(ncb) X(nwgrp) X(nmerge)           \
   X(cone) X(iterations) X(ls_iterations) X(n_frames) X(sync_mode)                                                           \
   /* env layer */                                                                                               \
   X(free_jnt) X(seed_root_from_clip) X(ref_len) X(clip_len) X(clip_nj) X(n_joint_idxs) X(n_body_idxs)           \
@@ -37,7 +37,7 @@
   X(chain_k0) X(chain_len) X(clev_adr) X(clev_chain) X(hlev_adr) X(hlev_chain) X(dof_chain) X(dchild_adr) X(dchild_id) X(dofbody_adr) X(dofbody_id) X(dof_irec) X(merge_adr) X(merge_dst) X(merge_src)                                                                     \
   X(cgeom_bodyid) X(cb_adr) X(cb_dof) X(cb_ref)                                                                 \
   X(con_g1) X(con_g2) X(con_cb1) X(con_cb2) X(con_ref) X(con_fn) X(con_sub) X(con_dim)                          \
-  X(cbcon_adr) X(cbcon_c) X(cbcon_cs) X(dof_wgrp) X(wgrp_adr) X(wgrp_cb) X(dofcb_adr) X(dofcb_id) X(cb_lastdof) X(seg_adr) X(seg_end) X(seg_cb) X(chain_desc) X(cchild_id) X(hpass_desc)                                                                                     \
+  X(cbcon_adr) X(cbcon_c) X(cbcon_cs) X(dof_wgrp) X(wgrp_adr) X(wgrp_cb) X(dofcb_adr) X(dofcb_id) X(cb_lastdof) X(seg_adr) X(seg_end) X(seg_cb) X(chain_desc) X(cchild_id) X(hpass_desc) X(apass_desc)                                                                                     \
   X(act_wrap_adr) X(act_wrap_qadr) X(act_wrap_dadr) X(dofact_adr) X(dofact_u)                                   \
   X(actuator_dyntype) X(actuator_gaintype) X(actuator_biastype) X(actuator_ctrllimited)                         \
   X(actuator_forcelimited) X(actuator_actadr)                                                                   \
@@ -51,7 +51,7 @@
   X(dof_margin) X(dof_invweight0)                                                                               \
   X(cgeom_pos) X(cgeom_quat) X(cgeom_size)                                                                      \
   X(con_mu) X(con_solref) X(con_solimp) X(con_includemargin) X(con_invweight) X(cbcon_sign)                    \
-  X(act_wrap_coef) X(dofact_coef) X(act_rec) X(wrap_rec) X(dof_rec) X(dofact_rec) X(body_rec) X(jnt_rec)                                                                               \
+  X(act_wrap_coef) X(dofact_coef) X(act_rec) X(wrap_rec) X(dof_rec) X(dofact_rec) X(body_rec) X(jnt_rec) X(bl_rec)                                                                               \
   X(actuator_gear) X(actuator_gainprm) X(actuator_biasprm) X(actuator_dynprm) X(actuator_ctrlrange)             \
   X(actuator_forcerange)                                                                                        \
   X(clip_position) X(clip_quaternion) X(clip_joints) X(clip_body_positions) X(clip_angular_velocity)

@@ -179,6 +179,13 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
         body_rec[b, 0:3] = a["body_pos"][b]; body_rec[b, 3:7] = a["body_quat"][b]
         body_rec[b, 7:11] = [a["body_jntadr"][b], a["body_jntnum"][b], parent[b], body_ref[b]]
     t["body_rec"] = body_rec.reshape(-1)
+    # body_local's constants: ipos iquat inertia mass | fluidbox lastdof ref (16 floats)
+    bl_rec = np.zeros((nbody, 16), dtype=np.float32)
+    for b in range(nbody):
+        bl_rec[b, 0:3] = a["body_ipos"][b]; bl_rec[b, 3:7] = a["body_iquat"][b]; bl_rec[b, 7:10] = a["body_inertia"][b]
+        bl_rec[b, 10] = a["body_mass"][b]
+        bl_rec[b, 11:14] = box[b]; bl_rec[b, 14] = a["body_lastdof"][b]; bl_rec[b, 15] = body_ref[b]
+    t["bl_rec"] = bl_rec.reshape(-1)
     jnt_rec = np.zeros((max(njnt, 1), 12), dtype=np.float32)
     for j in range(njnt):
         qa = int(a["jnt_qposadr"][j])
@@ -390,6 +397,18 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
             for ln, c in enumerate(cs[q:q + 32]):
                 row[ln] = desc[c]
             passes.append(row)
+    # the factor sweep walks four chains at a time (8-lane groups), by DEPTH level, deepest first: descriptor per (pass, group)
+    apasses = []
+    for L in range(nclev - 1, -1, -1):
+        cs = [c for c in corder if clevel[c] == L]
+        for q in range(0, len(cs), 4):
+            row = np.zeros((4, 8), dtype=np.int32)
+            row[:, 1] = -1
+            for g, c in enumerate(cs[q:q + 4]):
+                row[g] = desc[c]
+            apasses.append(row)
+    S("napass", len(apasses))
+    t["apass_desc"] = np.concatenate(apasses).reshape(-1) if apasses else np.zeros(32, np.int32)
     S("nhpass", len(passes))
     t["hpass_desc"] = np.concatenate(passes).reshape(-1) if passes else np.zeros(256, np.int32)
     t["cchild_id"] = _i(cchild_id) if cchild_id else np.zeros(1, np.int32)
