@@ -157,8 +157,13 @@ def run_gpu(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    saved_stdout = None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line (NCCL prints its version banner there)
+        # stdout carries exactly one JSON line: NCCL prints its version banner to fd 1 when the communicator is created, so
+        # fd 1 points at stderr until the line is printed
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     n, K, Wm = args.envs, args.steps, args.warmup
     base = presets.make_env(args.model, device=local)
@@ -258,7 +263,10 @@ def run_gpu(args):
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{ce} envs x 8 control steps, oracle port (C restatement of mjx.step, float32) + numpy env layer, "
                                               f"{dt:.1f} s wall = {dt * cores:.0f} CPU-s"}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        if saved_stdout is not None:
+            os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
