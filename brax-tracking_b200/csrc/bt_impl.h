@@ -1488,7 +1488,7 @@ struct BtEnv {
       bool swap = true;
       // stages 0 / 1 evaluate a single point each (one call site of the 1-point evaluator)
       for (int stage = 0; stage < 2; stage++) {
-        const float a1 = stage == 0 ? 0.f : p0.alpha - p0.d0 / p0.d1;
+        const float a1 = stage == 0 ? 0.f : p0.alpha - p0.d0 * bt_rcp_pos(p0.d1);
         LsPt pt1;
         ls_eval<1>(e, jv, ljv, qg, &a1, &pt1);
         if (stage == 0) p0 = pt1;
@@ -1503,7 +1503,8 @@ struct BtEnv {
           done |= (lo.d0 < 0.f) && (lo.d0 > -gtol);
           done |= (hi.d0 > 0.f) && (hi.d0 < gtol);
           if (done) break;
-          al[0] = lo.alpha - lo.d0 / lo.d1; al[1] = hi.alpha - hi.d0 / hi.d1; al[2] = 0.5f * (lo.alpha + hi.alpha);
+          // d1 = 2 s2 (+ MINVAL) > 0: Newton-refined reciprocal (<= 1 ulp) instead of the IEEE division sequence
+          al[0] = lo.alpha - lo.d0 * bt_rcp_pos(lo.d1); al[1] = hi.alpha - hi.d0 * bt_rcp_pos(hi.d1); al[2] = 0.5f * (lo.alpha + hi.alpha);
         }
         LsPt pt[3];
         ls_eval<3>(e, jv, ljv, qg, al, pt);
