@@ -36,11 +36,11 @@ static inline int bt_bind(BtDev* d, int n, const char* const* names, const void*
 #undef BT_NEED
   // size checks for the tables whose extents the kernels derive from the scalars
   struct { const char* nm; int64_t want; } chk[] = {
-      {"body_parentid", d->nbody}, {"body_pos", 3LL * d->nbody}, {"body_quat", 4LL * d->nbody},
-      {"level_adr", d->nlevel + 1LL}, {"level_body", d->nbody - 1LL}, {"child_adr", d->nbody + 1LL},
-      {"jnt_type", d->njnt}, {"qpos0", d->nq}, {"dof_bodyid", d->nv}, {"chain_k0", d->nchain}, {"chain_len", d->nchain},
-      {"clev_adr", d->nclev + 1LL}, {"clev_chain", d->nchain}, {"dof_chain", d->nv}, {"dchild_adr", d->nv + 1LL}, {"dofbody_adr", d->nv + 1LL}, {"dof_range", 2LL * d->nv}, {"dof_solimp", 5LL * d->nv},
-      {"dofcb_adr", d->nv + 1LL}, {"cbcon_adr", d->ncb + 1LL}, {"dofact_adr", d->nv + 1LL}, {"act_wrap_adr", d->nu + 1LL}, {"cb_adr", d->ncb + 1LL},
+      {"body_parentid", d->nbody}, {"body_rec", 12LL * d->nbody}, {"bl_rec", 16LL * d->nbody}, {"jnt_rec", 12LL * d->njnt},
+      {"jnt_type", d->njnt}, {"qpos0", d->nq}, {"dof_rec", 8LL * d->nv}, {"dof_irec", d->nv}, {"dof_wgrp", d->nv},
+      {"hpass_desc", 256LL * d->nhpass}, {"apass_desc", 32LL * d->napass}, {"cmp_adr", d->nbanc + 1LL},
+      {"dof_range", 2LL * d->nv}, {"dof_solimp", 5LL * d->nv}, {"cbcon_adr", d->ncb + 1LL}, {"wgrp_adr", d->nwgrp + 1LL},
+      {"act_rec", 16LL * (d->nu > 0 ? d->nu : 1)},
       {"clip_position", 3LL * d->clip_len}, {"clip_quaternion", 4LL * d->clip_len},
       {"clip_joints", (int64_t)d->clip_len * d->clip_nj}, {"clip_body_positions", 3LL * d->clip_len * d->nbody},
       {"clip_angular_velocity", 3LL * d->clip_len}, {"joint_idxs", d->n_joint_idxs}, {"body_idxs", d->n_body_idxs},

@@ -9,16 +9,16 @@
 
 // ---- scalar ints (1-element int tables, by name) ----
 #define BT_INT_SCALARS(X) \
-  X(nq) X(nv) X(nu) X(na) X(nbody) X(njnt) X(nlevel) X(nchain) X(nclev) X(nhlev) X(nhpass) X(napass) X(nbchain) X(nbclev) X(nbanc) X(nroot) X(ncon) X(ncgeom) X(ncb) X(nwgrp) X(nmerge)           \
-  X(cone) X(iterations) X(ls_iterations) X(n_frames) X(sync_mode)                                                           \
+  X(nq) X(nv) X(nu) X(na) X(nbody) X(njnt) X(nhpass) X(napass) X(nbanc) X(ncon) X(ncb) X(nwgrp) X(nmerge)       \
+  X(cone) X(iterations) X(ls_iterations) X(n_frames) X(sync_mode)                                               \
   /* env layer */                                                                                               \
   X(free_jnt) X(seed_root_from_clip) X(ref_len) X(clip_len) X(clip_nj) X(n_joint_idxs) X(n_body_idxs)           \
   X(n_endeff_idxs) X(torso_idx) X(terminate_when_unhealthy) X(steps_for_cur_frame) X(episode_length)            \
   X(start_frame_range) X(obs_size)                                                                              \
   /* per-environment scratch layout (offsets in floats) */                                                      \
-  X(o_qpos) X(o_qvel) X(o_act) X(o_ctrl) X(o_warm) X(o_xpos) X(o_xquat) X(o_cdof) X(o_crb) X(o_Dinv) X(o_Dd) X(o_cbJ) X(o_pvec)    \
-  X(o_T) X(o_ref) X(o_aforce) X(o_actdot) X(o_qfrc_smooth) X(o_qacc_smooth) X(o_qacc) X(o_x) X(o_search)        \
-  X(o_qfrc_c) X(o_tmpv) X(smem_floats)
+  X(o_qpos) X(o_qvel) X(o_act) X(o_ctrl) X(o_warm) X(o_xpos) X(o_xquat) X(o_cdof) X(o_crb) X(o_Dinv) X(o_Dd)    \
+  X(o_cbJ) X(o_pvec) X(o_T) X(o_ref) X(o_aforce) X(o_actdot) X(o_qfrc_smooth) X(o_qacc_smooth) X(o_qacc) X(o_x) \
+  X(o_search) X(o_qfrc_c) X(o_tmpv) X(smem_floats)
 
 // ---- scalar floats ----
 #define BT_FLT_SCALARS(X) \
@@ -29,31 +29,23 @@
   X(endeff_reward_weight) X(healthy_reward) X(healthy_z_min) X(healthy_z_max) X(reset_noise_scale)
 
 // ---- int tables ----
+// (model.py::pack emits more tables than the kernels bind: the unpacked per-field arrays behind the packed records below
+// stay in the dict for the host-side consumers -- tests, the oracle adapters, tools)
 #define BT_INT_TABLES(X) \
-  X(body_parentid) X(body_jntadr) X(body_jntnum) X(body_ref) X(body_flags) X(body_lastdof) X(level_adr) X(level_body) X(child_adr) X(child_id)\
-  X(bchain_b0) X(bchain_len) X(bclev_adr) X(bclev_chain) X(body_anc) X(cmp_adr) X(cmp_item)                                                        \
-  X(jnt_type) X(jnt_qposadr) X(jnt_dofadr) X(jnt_flags) X(jnt_bodyid)                                                                      \
-  X(dof_bodyid) X(dof_parentid) X(dof_qposadr) X(dof_limited) X(dof_vflag)                                                   \
-  X(chain_k0) X(chain_len) X(clev_adr) X(clev_chain) X(hlev_adr) X(hlev_chain) X(dof_chain) X(dchild_adr) X(dchild_id) X(dofbody_adr) X(dofbody_id) X(dof_irec) X(merge_adr) X(merge_dst) X(merge_src)                                                                     \
-  X(cgeom_bodyid) X(cb_adr) X(cb_dof) X(cb_ref)                                                                 \
-  X(con_g1) X(con_g2) X(con_cb1) X(con_cb2) X(con_ref) X(con_fn) X(con_sub) X(con_dim)                          \
-  X(cbcon_adr) X(cbcon_c) X(cbcon_cs) X(dof_wgrp) X(wgrp_adr) X(wgrp_cb) X(dofcb_adr) X(dofcb_id) X(cb_lastdof) X(seg_adr) X(seg_end) X(seg_cb) X(chain_desc) X(cchild_id) X(hpass_desc) X(apass_desc)                                                                                     \
-  X(act_wrap_adr) X(act_wrap_qadr) X(act_wrap_dadr) X(dofact_adr) X(dofact_u)                                   \
-  X(actuator_dyntype) X(actuator_gaintype) X(actuator_biastype) X(actuator_ctrllimited)                         \
-  X(actuator_forcelimited) X(actuator_actadr)                                                                   \
+  X(body_parentid) X(body_ref) X(cmp_adr) X(cmp_item)                                                           \
+  X(jnt_type) X(jnt_qposadr) X(jnt_dofadr) X(jnt_bodyid)                                                        \
+  X(dof_qposadr) X(dof_limited) X(dof_vflag) X(dof_irec) X(merge_adr) X(merge_dst) X(merge_src)                 \
+  X(chain_desc) X(cchild_id) X(hpass_desc) X(apass_desc) X(seg_end) X(seg_cb)                                   \
+  X(cgeom_bodyid) X(con_g1) X(con_g2) X(con_cb1) X(con_cb2) X(con_ref) X(con_fn) X(con_sub) X(con_dim)          \
+  X(cbcon_adr) X(cbcon_cs) X(dof_wgrp) X(wgrp_adr) X(wgrp_cb) X(cb_lastdof)                                     \
   X(joint_idxs) X(body_idxs) X(endeff_idxs)
 
 // ---- float tables ----
 #define BT_FLT_TABLES(X) \
-  X(body_pos) X(body_quat) X(body_ipos) X(body_iquat) X(body_mass) X(body_inertia) X(body_fluidbox)             \
-  X(jnt_pos) X(jnt_axis) X(qpos0)                                                                               \
-  X(dof_stiffness) X(dof_springref) X(dof_armature) X(dof_damping) X(dof_range) X(dof_solref) X(dof_solimp)     \
-  X(dof_margin) X(dof_invweight0)                                                                               \
+  X(qpos0) X(dof_armature) X(dof_damping) X(dof_range) X(dof_solref) X(dof_solimp) X(dof_margin) X(dof_invweight0) \
   X(cgeom_pos) X(cgeom_quat) X(cgeom_size)                                                                      \
-  X(con_mu) X(con_solref) X(con_solimp) X(con_includemargin) X(con_invweight) X(cbcon_sign)                    \
-  X(act_wrap_coef) X(dofact_coef) X(act_rec) X(wrap_rec) X(dof_rec) X(dofact_rec) X(body_rec) X(jnt_rec) X(bl_rec)                                                                               \
-  X(actuator_gear) X(actuator_gainprm) X(actuator_biasprm) X(actuator_dynprm) X(actuator_ctrlrange)             \
-  X(actuator_forcerange)                                                                                        \
+  X(con_mu) X(con_solref) X(con_solimp) X(con_includemargin) X(con_invweight)                                   \
+  X(act_rec) X(wrap_rec) X(dof_rec) X(dofact_rec) X(body_rec) X(jnt_rec) X(bl_rec)                              \
   X(clip_position) X(clip_quaternion) X(clip_joints) X(clip_body_positions) X(clip_angular_velocity)
 
 struct BtDev {
