@@ -172,7 +172,6 @@ struct BtEnv {
   BT_DEV float* xv() const { return s + m.o_x; }
   BT_DEV float* search() const { return s + m.o_search; }
   BT_DEV float* qfrc_c() const { return s + m.o_qfrc_c; }
-  BT_DEV float* tmpv() const { return s + m.o_tmpv; }
   // chain descriptor (model.py: chain_desc) and the 8-float slot that hands a chain's sweep state to its parent / children
   struct ChainD { int k0, kb, pc, c, cadr, nch, nseg, sadr, pdof; };
   BT_DEV ChainD desc_at(const int* d) const {
@@ -184,7 +183,6 @@ struct BtEnv {
     return ChainD{d[0], d[1], d[2], d[3], d[4], d[5] & 0xffff, d[5] >> 16, d[6], d[7]};
 #endif
   }
-  BT_DEV ChainD chain_d(int c) const { return desc_at(m.chain_desc + 8 * c); }
   // descriptor of the chain that virtual lane `vl` (0..31) walks in pass `ps` of the one-lane-per-chain sweeps (kb < k0: none)
   BT_DEV ChainD pass_d(int ps, int vl) const { return desc_at(m.hpass_desc + 8 * (32 * ps + vl)); }
   BT_DEV float* ctop(int c) const { return pvec() + 8 * c; }

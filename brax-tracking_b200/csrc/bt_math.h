@@ -119,13 +119,6 @@ BT_DEV void bt_axpy6(float* y, const float* x, float s) {
   for (int j = 0; j < 6; j++) y[j] += x[j] * s;
 #endif
 }
-BT_DEV float bt_rcp(float x) {
-#ifdef __CUDACC__
-  return __frcp_rn(x);
-#else
-  return 1.0f / x;
-#endif
-}
 // reciprocal of a positive, normal number (the pivots D_k): MUFU.RCP + one Newton step (<= 1 ulp), no range check / slow path
 BT_DEV float bt_rcp_pos(float x) {
 #ifdef __CUDACC__

@@ -35,7 +35,7 @@
   X(body_parentid) X(body_ref) X(cmp_adr) X(cmp_item)                                                           \
   X(jnt_type) X(jnt_qposadr) X(jnt_dofadr) X(jnt_bodyid)                                                        \
   X(dof_qposadr) X(dof_limited) X(dof_vflag) X(dof_irec) X(merge_adr) X(merge_dst) X(merge_src)                 \
-  X(chain_desc) X(cchild_id) X(hpass_desc) X(apass_desc) X(seg_end) X(seg_cb)                                   \
+  X(cchild_id) X(hpass_desc) X(apass_desc) X(seg_end) X(seg_cb)                                   \
   X(cgeom_bodyid) X(con_g1) X(con_g2) X(con_cb1) X(con_cb2) X(con_ref) X(con_fn) X(con_sub) X(con_dim)          \
   X(cbcon_adr) X(cbcon_cs) X(dof_wgrp) X(wgrp_adr) X(wgrp_cb) X(cb_lastdof)                                     \
   X(joint_idxs) X(body_idxs) X(endeff_idxs)
