@@ -7,8 +7,10 @@
 // What this replaces (reference call path): /root/reference/envs/fruitfly.py:497-596 (env.step) ->
 // brax PipelineEnv.pipeline_step -> mujoco.mjx.step x n_frames, plus
 // custom_brax/custom_wrappers.py:54-80 and brax EpisodeWrapper.  The formulation is deliberately different
-// from MJX's dense one (fruitfly.py:78): tree-sparse L'DL, matrix-free constraint Jacobian (ancestor-chain
-// sums of cdof), constraint rows held in registers, one forward and one backward tree pass per substep.
+// from MJX's dense one (fruitfly.py:78): no mass matrix and no factor are ever formed -- the articulated-body
+// recursion (aba_factor) yields what M^-1 v and M v need, both of which are two O(nv) chain sweeps; the
+// constraint Jacobian is matrix-free (its chain sums are by-products of those sweeps); constraint rows are held
+// in registers.  DESIGN.md section 2 describes the execution model.
 #pragma once
 #include "bt_math.h"
 #include "bt_model.h"
