@@ -1,0 +1,116 @@
+"""Structural invariants of the scheduling tables model.py::pack hands to the kernels (chain descriptors, sweep passes,
+contact segments, wrench groups, pose-composition work lists).  Pure host logic: no oracle, no GPU."""
+import numpy as np
+import pytest
+
+import common
+
+MODELS = ["rodent", "fly_free", "fly_tethered", "rodent_pair"]
+
+
+def _desc(row):
+    return dict(k0=row[0], kb=row[1], pc=row[2], c=row[3], cadr=row[4], nch=row[5] & 0xffff, nseg=row[5] >> 16, sadr=row[6], pdof=row[7])
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_chain_descriptors_cover_the_dof_tree(name):
+    m, cfg, clip, t = common.setup(name)
+    nv = m.nv
+    desc = t["chain_desc"].reshape(-1, 8)
+    par = np.asarray(m.a["dof_parentid"])
+    seen = np.zeros(nv, int)
+    for c, row in enumerate(desc):
+        d = _desc(row)
+        assert d["c"] == c and d["pdof"] == par[d["k0"]]
+        seen[d["k0"]:d["kb"] + 1] += 1
+        for k in range(d["k0"] + 1, d["kb"] + 1):           # a chain is a single-child path of consecutive dofs
+            assert par[k] == k - 1
+        kids = t["cchild_id"][d["cadr"]:d["cadr"] + d["nch"]]
+        for ch in kids:                                       # child chains hang off the END of their parent chain
+            assert desc[ch][2] == c and par[desc[ch][0]] == d["kb"]
+        ends = t["seg_end"][d["sadr"]:d["sadr"] + d["nseg"]]  # segments tile the chain; every inner end is a contact dof
+        assert list(ends) == sorted(ends) and ends[-1] == d["kb"] and ends[0] >= d["k0"]
+        cbs = t["seg_cb"][d["sadr"]:d["sadr"] + d["nseg"]]
+        assert all(cb >= 0 for cb in cbs[:-1])
+        for e, cb in zip(ends, cbs):
+            if cb >= 0:
+                assert t["cb_lastdof"][cb] == e
+    assert (seen == 1).all()
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_sweep_passes_respect_the_dependencies(name):
+    m, cfg, clip, t = common.setup(name)
+    desc = t["chain_desc"].reshape(-1, 8)
+    for key, width in (("hpass_desc", 32), ("apass_desc", 4)):
+        rows = t[key].reshape(-1, width, 8)
+        pass_of = {}
+        for p, row in enumerate(rows):
+            for lane in row:
+                if lane[1] >= lane[0]:
+                    assert np.array_equal(lane, desc[lane[3]])
+                    pass_of[int(lane[3])] = p
+        assert sorted(pass_of) == list(range(len(desc)))      # every chain exactly once
+        for c, p in pass_of.items():
+            pc = desc[c][2]
+            if pc >= 0:                                       # hpass: root-most first; apass: deepest first
+                assert pass_of[pc] < p if key == "hpass_desc" else pass_of[pc] > p
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_wrench_groups_and_merge_lists(name):
+    m, cfg, clip, t = common.setup(name)
+    par = np.asarray(m.a["dof_parentid"])
+    ncb = int(t["ncb"][0])
+    below = [set() for _ in range(m.nv)]                      # contact bodies whose ancestor chain contains the dof
+    for cb in range(ncb):
+        d = int(t["cb_lastdof"][cb])
+        while d >= 0:
+            below[d].add(cb); d = par[d]
+    for d in range(m.nv):
+        g = t["dof_wgrp"][d]
+        got = set(t["wgrp_cb"][t["wgrp_adr"][g]:t["wgrp_adr"][g + 1]]) if g >= 0 else set()
+        assert got == below[d]
+    # link records: every moving body is either the record of its dof or merged into it exactly once
+    lastdof = np.asarray(m.a["body_lastdof"])
+    owner = {}
+    for d in range(m.nv):
+        if t["dof_irec"][d] >= 0:
+            owner[int(t["dof_irec"][d])] = d
+    merged = {}
+    for r in range(int(t["nmerge"][0])):
+        for s in t["merge_src"][t["merge_adr"][r]:t["merge_adr"][r + 1]]:
+            merged[int(s)] = int(t["merge_dst"][r])
+    for b in range(1, m.nbody):
+        if lastdof[b] >= 0:
+            assert (b in owner and owner[b] == lastdof[b]) ^ (b in merged and owner[merged[b]] == lastdof[b])
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_pose_composition_work_lists(name):
+    """Replays the pointer-jumping rounds symbolically: every body ends at the world frame in buffer 0 (xpos / xquat)."""
+    m, cfg, clip, t = common.setup(name)
+    nb, R = m.nbody, int(t["nbanc"][0])
+    parent = np.asarray(m.a["body_parentid"])
+    depth = np.zeros(nb, int)
+    for b in range(1, nb):
+        depth[b] = depth[parent[b]] + 1
+    # buf[which][b] = how many levels above b its stored pose is expressed in (depth[b] = world); -1 = stale
+    buf = [np.full(nb, -1), np.full(nb, -1)]
+    buf[R & 1][1:] = 1                                        # body_frame: pose relative to the parent
+    buf[R & 1][depth == 1] = 1
+    for r in range(R):
+        src, dst = buf[(R - r) & 1], buf[(R - 1 - r) & 1]
+        new = dst.copy()
+        for w in t["cmp_item"][t["cmp_adr"][r]:t["cmp_adr"][r + 1]]:
+            b, a = w & 0xfff, (w >> 12) & 0xfff
+            assert src[b] > 0
+            if w & (1 << 29):
+                assert src[b] == depth[b]                     # copy-forward of a finished pose
+                new[b] = src[b]
+            else:
+                assert src[a] > 0 and depth[a] == depth[b] - src[b]   # a is the body the stored pose is relative to
+                new[b] = src[b] + src[a]
+                assert bool(w & (1 << 28)) == (new[b] == depth[b])
+        dst[:] = new
+    assert (buf[0][1:] == depth[1:]).all()
