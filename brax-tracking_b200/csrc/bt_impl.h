@@ -262,12 +262,11 @@ struct BtEnv {
     float* bq = pose_quat(m.nbanc & 1);
 #pragma unroll
     for (int k = 0; k < 3; k++) bp[3 * b + k] = p[k];
-#pragma unroll
-    for (int k = 0; k < 4; k++) bq[4 * b + k] = q[k];
+    bt_st4(bq + 4 * b, q);
   }
   // the two pose buffers of the pointer-jumping composition: 0 = (xpos, xquat), 1 = the T region (idle during the tree pass)
   BT_DEV float* pose_pos(int which) const { return which ? T() : xpos(); }
-  BT_DEV float* pose_quat(int which) const { return which ? T() + 3 * m.nbody : xquat(); }
+  BT_DEV float* pose_quat(int which) const { return which ? T() + ((3 * m.nbody + 3) & ~3) : xquat(); }  // 16-byte aligned
 
   BT_DEV void joint_cdof(int j) {
     const int b = BT_LDG(m.jnt_bodyid + j), p = BT_LDG(m.body_parentid + b), da = BT_LDG(m.jnt_dofadr + j);
@@ -312,8 +311,7 @@ struct BtEnv {
     const int rs = (int)br[15];
 #pragma unroll
     for (int k = 0; k < 3; k++) { pos[k] = xpos()[3 * b + k]; rp[k] = ref()[3 * rs + k]; }
-#pragma unroll
-    for (int k = 0; k < 4; k++) quat[k] = xquat()[4 * b + k];
+    bt_ld4(xquat() + 4 * b, quat);
     const int ld = (int)br[14];  // last dof on the chain root -> body: the body moves with it
     if (ld >= 0) {
       float r12[12];
@@ -413,10 +411,12 @@ struct BtEnv {
         const int w = BT_LDG(m.cmp_item + it);
         const int b = w & 0xfff, a = (w >> 12) & 0xfff;
         float pos[3] = {sp[3 * b], sp[3 * b + 1], sp[3 * b + 2]};
-        float quat[4] = {sq[4 * b], sq[4 * b + 1], sq[4 * b + 2], sq[4 * b + 3]};
+        float quat[4];
+        bt_ld4(sq + 4 * b, quat);
         if (!(w & (1 << 29))) {
           const float pa[3] = {sp[3 * a], sp[3 * a + 1], sp[3 * a + 2]};
-          const float qa[4] = {sq[4 * a], sq[4 * a + 1], sq[4 * a + 2], sq[4 * a + 3]};
+          float qa[4];
+          bt_ld4(sq + 4 * a, qa);
           float rr[3], q2[4];
           bt_rotate(pos, qa, rr);
           pos[0] = pa[0] + rr[0]; pos[1] = pa[1] + rr[1]; pos[2] = pa[2] + rr[2];
@@ -426,8 +426,7 @@ struct BtEnv {
         }
 #pragma unroll
         for (int k = 0; k < 3; k++) dp[3 * b + k] = pos[k];
-#pragma unroll
-        for (int k = 0; k < 4; k++) dq[4 * b + k] = quat[k];
+        bt_st4(dq + 4 * b, quat);
       }
       W::sync();
     }
@@ -970,10 +969,9 @@ struct BtEnv {
       }
       cdist[sl] = dist;
       const int rs = BT_LDG(m.con_ref + c);
-      float* cg = congeo() + 12 * c;
-      cg[0] = pos[0] - ref()[3 * rs]; cg[1] = pos[1] - ref()[3 * rs + 1]; cg[2] = pos[2] - ref()[3 * rs + 2];
-#pragma unroll
-      for (int k = 0; k < 9; k++) cg[3 + k] = fr[k];
+      const float off3[3] = {pos[0] - ref()[3 * rs], pos[1] - ref()[3 * rs + 1], pos[2] - ref()[3 * rs + 2]};
+      const float r6a[6] = {off3[0], off3[1], off3[2], fr[0], fr[1], fr[2]}, r6b[6] = {fr[3], fr[4], fr[5], fr[6], fr[7], fr[8]};
+      bt_st12(congeo() + 12 * c, r6a, r6b);
     }
     W::sync();
   }
@@ -991,7 +989,8 @@ struct BtEnv {
       float A[6] = {0, 0, 0, 0, 0, 0};
       if (cb2 >= 0) for (int k = 0; k < 6; k++) A[k] += cbs[6 * cb2 + k];
       if (cb1 >= 0) for (int k = 0; k < 6; k++) A[k] -= cbs[6 * cb1 + k];
-      const float* cg = congeo() + 12 * c;
+      float cg[12];  // contact record (offset 3, frame 9): three 128-bit loads (scalar loads at stride 12 are 4-way conflicts)
+      bt_ld12(congeo() + 12 * c, cg);
       float w[3];
       bt_cross(A, cg, w);
       w[0] += A[3]; w[1] += A[4]; w[2] += A[5];
@@ -1186,7 +1185,8 @@ struct BtEnv {
     for (int sl = 0; sl < CS; sl++) {
       const int c = lane + sl * G;
       if (c >= m.ncon) continue;
-      const float* cg = congeo() + 12 * c;
+      float cg[12];
+      bt_ld12(congeo() + 12 * c, cg);
       float F[3], tq[3];
 #pragma unroll
       for (int k = 0; k < 3; k++) F[k] = cg[3 + k] * fbase[sl][0] + cg[6 + k] * fbase[sl][1] + cg[9 + k] * fbase[sl][2];

@@ -165,6 +165,23 @@ BT_DEV void bt_ldg2(const float* p, float* o) {
   o[0] = p[0]; o[1] = p[1];
 #endif
 }
+// one 16-byte aligned quaternion (shared memory): a single 128-bit access instead of four stride-4 scalar ones (which are
+// 4-way bank conflicts when a warp walks consecutive bodies)
+BT_DEV void bt_ld4(const float* p, float* o) {
+#ifdef __CUDACC__
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+#else
+  for (int j = 0; j < 4; j++) o[j] = p[j];
+#endif
+}
+BT_DEV void bt_st4(float* p, const float* a) {
+#ifdef __CUDACC__
+  *reinterpret_cast<float4*>(p) = make_float4(a[0], a[1], a[2], a[3]);
+#else
+  for (int j = 0; j < 4; j++) p[j] = a[j];
+#endif
+}
 // 6 floats to a 16-byte aligned slot
 BT_DEV void bt_st6(float* p, const float* a) {
 #ifdef __CUDACC__

@@ -607,14 +607,17 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
         off += (-off) % 4
 
     R("qpos", nq); R("qvel", nv); R("act", max(na, 1)); R("ctrl", max(nu, 1)); R("warm", nv)
-    R("xpos", 3 * nbody); R("xquat", 4 * nbody)
+    R("xpos", 3 * nbody)
+    ALIGN4()   # quaternions move as one 128-bit access
+    R("xquat", 4 * nbody)
     ALIGN4()
     R("cdof", 12 * nv)   # per dof: S_k = cdof_k (6) | G_k = U_k / D_k (6); 16-byte aligned records
     R("crb", 10 * nbody); R("Dinv", nv); R("Dd", nv)
     R("cbJ", 18 * max(ncb, 1))   # three sets of per-contact-body chain sums (qvel, qacc_warmstart, qacc_smooth)
     # T region: cfrc (tree passes) -> the 6x6 reduced articulated inertia of every chain top (aba_factor)
     # -> contact geometry + wrenches + chain sums (solver)
-    R("T", max(7 * nbody, 6 * nv, 18 * ncon + 6 * max(ncb, 1)))   # 7 * nbody: second pose buffer of the composition
+    ALIGN4()   # the second pose buffer's quaternions (T + round4(3 * nbody)) are 128-bit accesses too
+    R("T", max(7 * nbody + 3, 6 * nv, 18 * ncon + 6 * max(ncb, 1)))   # 7 * nbody: second pose buffer of the composition
     R("ref", 3 * max(len(roots), 1))
     R("actdot", max(na, 1))
     # pvec (sweep state, 6/dof) and the solver vectors behind it are contiguous: together they hold cvel/cacc (12/dof)

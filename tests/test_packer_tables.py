@@ -114,3 +114,14 @@ def test_pose_composition_work_lists(name):
                 assert bool(w & (1 << 28)) == (new[b] == depth[b])
         dst[:] = new
     assert (buf[0][1:] == depth[1:]).all()
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_regions_with_128_bit_accesses_are_aligned(name):
+    m, cfg, clip, t = common.setup(name)
+    for k in ("o_cdof", "o_xquat", "o_T", "o_pvec"):          # dof records, quaternions (both pose buffers), cvel|cacc records
+        assert int(t[k][0]) % 4 == 0, k
+    assert int(t["smem_floats"][0]) % 4 == 0                   # every environment's block starts 16-byte aligned
+    need = ((3 * m.nbody + 3) & ~3) + 4 * m.nbody              # second pose buffer inside T
+    nxt = min(int(v[0]) for k, v in t.items() if k.startswith("o_") and int(v[0]) > int(t["o_T"][0]))
+    assert int(t["o_T"][0]) + need <= nxt

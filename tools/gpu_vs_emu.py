@@ -6,7 +6,7 @@ for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 import numpy as np
 import common, parity_cases as pc
-name = "rodent"
+name = sys.argv[2] if len(sys.argv) > 2 else "rodent"
 m, cfg, clip, tables = common.setup(name)
 N = 16
 st, ctrl = pc.random_states(m, N)
