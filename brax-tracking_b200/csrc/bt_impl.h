@@ -235,7 +235,10 @@ struct BtEnv {
         }
         bt_rotate(ja, q, axis);
         float* rec = cdof() + 12 * da;  // local axis / anchor, turned into cdof by joint_cdof()
-        rec[0] = axis[0]; rec[1] = axis[1]; rec[2] = axis[2]; rec[3] = anchor[0]; rec[4] = anchor[1]; rec[5] = anchor[2];
+        {
+          const float r6[6] = {axis[0], axis[1], axis[2], anchor[0], anchor[1], anchor[2]};
+          bt_st6(rec, r6);  // (scalar stores at the 12-float record stride are 4-way bank conflicts)
+        }
         const float ang = 0.5f * (qpos()[qa] - jr[10]);
         float sn, cs_;
 #ifdef __CUDACC__
@@ -278,18 +281,19 @@ struct BtEnv {
       const float off[3] = {rp[0] - xpos()[3 * b], rp[1] - xpos()[3 * b + 1], rp[2] - xpos()[3 * b + 2]};
 #pragma unroll
       for (int k = 0; k < 3; k++) {
-        float* c = cdof() + 12 * (da + k);
-        c[0] = c[1] = c[2] = c[3] = c[4] = c[5] = 0.f;
-        c[3 + k] = 1.f;
-        float* cr = cdof() + 12 * (da + 3 + k);
+        const float c6[6] = {0.f, 0.f, 0.f, k == 0 ? 1.f : 0.f, k == 1 ? 1.f : 0.f, k == 2 ? 1.f : 0.f};
+        bt_st6(cdof() + 12 * (da + k), c6);
         float ax[3] = {R[k], R[3 + k], R[6 + k]}, lin[3];
         bt_cross(ax, off, lin);
-        cr[0] = ax[0]; cr[1] = ax[1]; cr[2] = ax[2]; cr[3] = lin[0]; cr[4] = lin[1]; cr[5] = lin[2];
+        const float r6[6] = {ax[0], ax[1], ax[2], lin[0], lin[1], lin[2]};
+        bt_st6(cdof() + 12 * (da + 3 + k), r6);
       }
       return;
     }
     float* rec = cdof() + 12 * da;
-    float al[3] = {rec[0], rec[1], rec[2]}, nl[3] = {rec[3], rec[4], rec[5]}, ax[3], an[3], lin[3];
+    float l6[6];
+    bt_ld6(rec, l6);
+    float al[3] = {l6[0], l6[1], l6[2]}, nl[3] = {l6[3], l6[4], l6[5]}, ax[3], an[3], lin[3];
     if (p == 0) {
       ax[0] = al[0]; ax[1] = al[1]; ax[2] = al[2]; an[0] = nl[0]; an[1] = nl[1]; an[2] = nl[2];
     } else {
@@ -299,7 +303,8 @@ struct BtEnv {
     }
     const float off[3] = {rp[0] - an[0], rp[1] - an[1], rp[2] - an[2]};
     bt_cross(ax, off, lin);
-    rec[0] = ax[0]; rec[1] = ax[1]; rec[2] = ax[2]; rec[3] = lin[0]; rec[4] = lin[1]; rec[5] = lin[2];
+    const float r6[6] = {ax[0], ax[1], ax[2], lin[0], lin[1], lin[2]};
+    bt_st6(rec, r6);
   }
 
   BT_DEV void body_local(int b) {
