@@ -84,9 +84,11 @@ class RunningStatistics:
         var_upd = (diff * (b - mean)).sum(0)
         if world > 1:
             dist.all_reduce(var_upd)
-        self.summed_variance = self.summed_variance + var_upd
-        self.mean, self.count = mean, new_count
-        self.std = torch.sqrt(torch.clamp(self.summed_variance / new_count.to(torch.float32), min=0.0)).clamp(1e-6, 1e6)
+        # in place: captured CUDA graphs (rollout policy) keep reading these tensors
+        self.summed_variance.add_(var_upd)
+        self.mean.copy_(mean)
+        self.count.copy_(new_count)
+        self.std.copy_(torch.sqrt(torch.clamp(self.summed_variance / new_count.to(torch.float32), min=0.0)).clamp(1e-6, 1e6))
 
     def normalize(self, x):
         return (x - self.mean) / self.std
@@ -95,7 +97,8 @@ class RunningStatistics:
         return dict(count=self.count, mean=self.mean, summed_variance=self.summed_variance, std=self.std)
 
     def load_state_dict(self, d):
-        self.count, self.mean, self.summed_variance, self.std = d["count"], d["mean"], d["summed_variance"], d["std"]
+        for k in ("count", "mean", "summed_variance", "std"):
+            getattr(self, k).copy_(d[k])
 
 
 class NormalTanh:
@@ -149,11 +152,13 @@ def compute_gae(truncation, termination, rewards, values, bootstrap_value, lambd
 def compute_ppo_loss(policy, value, normalizer, data: Dict[str, torch.Tensor], noise, entropy_cost=1e-4, discounting=0.9,
                      reward_scaling=1.0, gae_lambda=0.95, clipping_epsilon=0.3, normalize_advantage=True):
     """brax compute_ppo_loss; ``data`` is batch-major [B, T, ...] as stored by the rollout."""
-    tm = {k: v.transpose(0, 1) for k, v in data.items()}  # time first
-    obs = normalizer(tm["observation"])
-    logits = policy(obs)
-    baseline = value(obs).squeeze(-1)
-    bootstrap = value(normalizer(tm["next_observation"][-1])).squeeze(-1)
+    tm = {k: v.transpose(0, 1) for k, v in data.items() if "observation" not in k}  # time first
+    # the networks act row by row: they are applied to the observation rows as stored (batch-major, contiguous: no transposed
+    # copy of the widest tensor of the update) and only their narrow outputs are viewed time-first
+    obs = normalizer(data["observation"])
+    logits = policy(obs).transpose(0, 1)
+    baseline = value(obs).squeeze(-1).transpose(0, 1)
+    bootstrap = value(normalizer(data["next_observation"][:, -1])).squeeze(-1)
     rewards = tm["reward"] * reward_scaling
     truncation = tm["truncation"]
     termination = (1.0 - tm["discount"]) * (1.0 - truncation)
@@ -181,17 +186,16 @@ class TrainingState:
     env_steps: int = 0
 
 
-def _flat_allreduce_mean(params, world):
-    """lax.pmean(grads, 'i'): one NCCL all-reduce on a flat buffer."""
-    grads = [p.grad for p in params]
-    flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat)
-    flat /= world
+def _bind_flat_grads(params) -> torch.Tensor:
+    """Every parameter's ``.grad`` becomes a view into ONE flat buffer (autograd accumulates into an existing ``.grad`` in
+    place), so that lax.pmean(grads, 'i') is a single NCCL all-reduce with no gather / scatter copies around it."""
+    flat = torch.zeros(sum(p.numel() for p in params), dtype=params[0].dtype, device=params[0].device)
     off = 0
-    for g in grads:
-        n = g.numel()
-        g.copy_(flat[off:off + n].view_as(g))
+    for p in params:
+        n = p.numel()
+        p.grad = flat[off:off + n].view_as(p)
         off += n
+    return flat
 
 
 def train(environment, num_timesteps: int, episode_length: int, action_repeat: int = 1, num_envs: int = 1,
@@ -233,6 +237,8 @@ def train(environment, num_timesteps: int, episode_length: int, action_repeat: i
     value = MLP([obs_size, *value_hidden_layer_sizes, 1], in_align=32).to(device)
     obs_pad = policy.in_padded
     params = list(policy.parameters()) + list(value.parameters())
+    flat_grad = _bind_flat_grads(params)
+    grad_ptrs = [p.grad.data_ptr() for p in params]
     opt = torch.optim.Adam(params, lr=learning_rate, eps=1e-8, capturable=device.type == "cuda")
     ts = TrainingState(policy, value, opt, RunningStatistics(obs_size, device))
     if restore_checkpoint_path is not None:
@@ -277,15 +283,16 @@ def train(environment, num_timesteps: int, episode_length: int, action_repeat: i
         # observations were normalised once for the whole batch (the statistics are fixed during the SGD epochs)
         loss, lm = compute_ppo_loss(policy, value, ident, mb_data, mb_noise, entropy_cost, discounting, reward_scaling, gae_lambda,
                                     clipping_epsilon, normalize_advantage)
-        opt.zero_grad(set_to_none=False)
+        flat_grad.zero_()
         loss.backward()
         if world > 1:
-            _flat_allreduce_mean(params, world)                              # lax.pmean(grads, 'i')
+            dist.all_reduce(flat_grad)                                       # lax.pmean(grads, 'i'): one all-reduce, in place
+            flat_grad.div_(world)
         opt.step()
         return lm
 
     def run_minibatch():
-        if not use_cuda_graph or world > 1 or device.type != "cuda":
+        if not use_cuda_graph or device.type != "cuda":
             return minibatch_update()
         if graph["g"] is None and not graph["tried"]:
             graph["tried"] = True
@@ -296,8 +303,11 @@ def train(environment, num_timesteps: int, episode_length: int, action_repeat: i
                     for _ in range(3):
                         minibatch_update()
                 torch.cuda.current_stream(device).wait_stream(side)
+                assert [p.grad.data_ptr() for p in params] == grad_ptrs, "autograd replaced a flat gradient view"
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                # the NCCL all-reduce is captured with the update (world > 1); thread-local capture mode because the process
+                # group's watchdog thread queries events while this thread captures
+                with torch.cuda.graph(g, capture_error_mode="thread_local" if world > 1 else "global"):
                     graph["lm"] = minibatch_update()
                 graph["g"] = g
                 g.replay()  # capture only records: this minibatch's update runs now
@@ -311,6 +321,54 @@ def train(environment, num_timesteps: int, episode_length: int, action_repeat: i
         graph["g"].replay()
         return graph["lm"]
 
+    # one unroll = T x (policy inference, sampling, fused env step, 7 transition records).  The env step is in place on static
+    # buffers and the C ABI only enqueues a kernel on the current stream, so the whole unroll replays as ONE CUDA graph
+    # writing a static [T, n_local, ...] staging record; only the sampling noise is drawn outside it.
+    ubuf = {k: torch.empty_like(v[0]) for k, v in buf.items()}
+    roll_noise = torch.zeros(T, n_local, nu, device=device)
+    rgraph = {"g": None, "tried": False}
+
+    def unroll_into(state, dst):
+        with torch.no_grad():
+            for t in range(T):
+                dst["observation"][t].copy_(state.obs)
+                logits = policy(norm(state.obs))
+                loc, scale = NormalTanh.params(logits)
+                raw = loc + scale * roll_noise[t]
+                dst["raw_action"][t].copy_(raw)
+                dst["log_prob"][t].copy_(NormalTanh.log_prob(logits, raw))
+                state = env.step(state, torch.tanh(raw).contiguous())
+                if t == T - 1:
+                    dst["next_observation"][0].copy_(state.obs)
+                dst["reward"][t].copy_(state.reward)
+                dst["discount"][t].copy_(1.0 - state.done)
+                dst["truncation"][t].copy_(state.info["truncation"])
+        return state
+
+    def run_unroll(state, u):
+        roll_noise.normal_(generator=gen)
+        dst_u = {k: v[u] for k, v in buf.items()}
+        if not use_cuda_graph or device.type != "cuda":
+            return unroll_into(state, dst_u)
+        if rgraph["g"] is None:
+            if rgraph["tried"]:
+                return unroll_into(state, dst_u)
+            rgraph["tried"] = True
+            state = unroll_into(state, dst_u)                                 # first unroll eagerly: cuBLAS handles, workspaces
+            try:
+                torch.cuda.synchronize(device)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, capture_error_mode="thread_local" if world > 1 else "global"):
+                    unroll_into(state, ubuf)                                  # records only: the env state is not advanced
+                rgraph["g"] = g
+            except Exception as e:  # pragma: no cover - capture is an optimisation, never a requirement
+                print(f"[ppo] CUDA graph capture of the unroll failed ({e!r}); running eagerly", flush=True)
+            return state
+        rgraph["g"].replay()
+        for k, v in dst_u.items():
+            v.copy_(ubuf[k])
+        return state
+
     metrics: Dict[str, float] = {}
     t_start = time.time()
     for it in range(num_evals_after_init):
@@ -318,19 +376,8 @@ def train(environment, num_timesteps: int, episode_length: int, action_repeat: i
         ep_reward = 0.0
         for _ in range(num_training_steps_per_epoch):
             # ---- rollout: acting.generate_unroll x n_unrolls (custom_ppo.py:296-314)
-            act = make_policy()
             for u in range(n_unrolls):
-                for t in range(T):
-                    buf["observation"][u, t].copy_(state.obs)
-                    action, raw, logits = act(state.obs)
-                    buf["raw_action"][u, t].copy_(raw)
-                    buf["log_prob"][u, t].copy_(NormalTanh.log_prob(logits, raw))
-                    state = env.step(state, action.contiguous())
-                    if t == T - 1:
-                        buf["next_observation"][u, 0].copy_(state.obs)
-                    buf["reward"][u, t].copy_(state.reward)
-                    buf["discount"][u, t].copy_(1.0 - state.done)
-                    buf["truncation"][u, t].copy_(state.info["truncation"])
+                state = run_unroll(state, u)
             ep_reward = float(buf["reward"].mean())
             # [n_unrolls, T, n, ...] -> [n_unrolls * n, T, ...]  (custom_ppo.py:316-320)
             for k, v in buf.items():

@@ -153,6 +153,19 @@ def test_ppo_loop_runs_on_the_fused_step(tmp_path):
     a, raw, logits = act(torch.zeros(3, env.observation_size, device="cuda"))
     assert a.shape == (3, env.action_size) and torch.isfinite(a).all() and float(a.abs().max()) <= 1.0
     assert float(params[0]["count"]) == 2 * 256 * 4 * 4
+    # the CUDA-graph replays (unroll, minibatch update) compute what the eager loop computes: same seed, same draws, ONE
+    # training step (the rollout runs on the initial policy in both; later steps amplify rounding through the contacts)
+    one = {}
+    for use_graph in (True, False):
+        e = envs.RodentSingleClip(clip, mj_model=m)
+        one[use_graph] = ppo.train(e, num_timesteps=256 * 4 * 4, episode_length=cfg["episode_length"], num_envs=256, num_evals=2,
+                                   learning_rate=3e-4, entropy_cost=1e-3, discounting=0.99, unroll_length=4, batch_size=256,
+                                   num_minibatches=4, num_updates_per_batch=2, normalize_observations=True, use_cuda_graph=use_graph)[2]
+    g_, e_ = one[True], one[False]
+    assert abs(g_["training/mean_step_reward"] - e_["training/mean_step_reward"]) < 1e-4 * abs(e_["training/mean_step_reward"]), (g_, e_)
+    # (parameters are not compared: the first Adam steps move every weight by ~lr whatever its gradient's size, so weights
+    # with near-zero gradients amplify rounding differences to the size of the update itself)
+    assert abs(g_["training/v_loss"] - e_["training/v_loss"]) < 0.05 * abs(e_["training/v_loss"]), (g_, e_)
     # evaluation rollout from frame 0 (main.py:136-258) + device FK for clip preprocessing (preprocess.py:144-204)
     tr = ppo.evaluate_rollout(env, act, common.jax_keys(4, seed=2), num_steps=10)
     assert tr["reward"].shape == (10, 4) and np.isfinite(tr["reward"]).all()
