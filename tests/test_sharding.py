@@ -23,6 +23,25 @@ def test_shard_keys_partition_the_split():
         parallel.shard_bounds(10, 0, 4)
 
 
+def _flat_grad_of_mean_loss(rank, world):
+    """Gradient of a mean loss over rank `rank`'s contiguous share of a fixed batch, through ppo._bind_flat_grads
+    (every .grad a view of one flat buffer that autograd accumulates into in place)."""
+    import torch
+    from brax_tracking_b200 import ppo
+    torch.manual_seed(5)
+    net = ppo.MLP([9, 8, 3], in_align=4)
+    x, y = torch.randn(12, 9), torch.randn(12, 3)
+    params = list(net.parameters())
+    flat = ppo._bind_flat_grads(params)
+    ptrs = [p.grad.data_ptr() for p in params]
+    lo, hi = parallel.shard_bounds(12, rank, world)
+    for _ in range(2):                                                       # a second pass reuses the same views
+        flat.zero_()
+        ((net(x[lo:hi]) - y[lo:hi]) ** 2).mean().backward()
+    assert [p.grad.data_ptr() for p in params] == ptrs and float(flat.abs().sum()) > 0
+    return flat
+
+
 def _worker(rank, world, port, n_envs, q):
     for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
         if p not in sys.path:
@@ -46,7 +65,8 @@ def _worker(rank, world, port, n_envs, q):
     gathered = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(gathered, mine)
     # the only collective of the whole job belongs to the learner: emulate the PPO gradient mean (custom_ppo.py:246-257)
-    grad = torch.full((4,), float(rank + 1))
+    # with the learner's own flat gradient buffer: each rank back-propagates its half of a batch, one in-place all-reduce
+    grad = _flat_grad_of_mean_loss(rank, world)
     dist.all_reduce(grad)
     grad /= world
     if rank == 0:
@@ -79,4 +99,4 @@ def test_two_rank_gloo_matches_single_process():
         b.step(st, out, first, fo, fi, acts[t])
     want = np.concatenate([st["qpos"], out["obs"], out["reward"][:, None], out["done"][:, None]], 1)
     assert np.array_equal(got, want)
-    np.testing.assert_allclose(grad, 1.5)
+    np.testing.assert_allclose(grad, _flat_grad_of_mean_loss(0, 1).numpy(), atol=1e-6)   # pmean of the shard gradients
