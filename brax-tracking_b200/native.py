@@ -13,7 +13,8 @@ from typing import Dict, Optional
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libbt_b200.so")
+# BT_B200_LIB: another build of the same library (compiler-flag experiments); no fallback either way
+LIB_PATH = os.environ.get("BT_B200_LIB") or os.path.join(_PKG, "libbt_b200.so")
 
 NUM_METRICS, NUM_INFO_F, NUM_INFO_I = 12, 5, 2
 METRIC_NAMES = ["pos_reward", "quat_reward", "joint_reward", "angvel_reward", "bodypos_reward", "endeff_reward",
