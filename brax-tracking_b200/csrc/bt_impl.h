@@ -221,7 +221,8 @@ struct BtEnv {
         p[0] = qpos()[qa]; p[1] = qpos()[qa + 1]; p[2] = qpos()[qa + 2];
         q[0] = qpos()[qa + 3]; q[1] = qpos()[qa + 4]; q[2] = qpos()[qa + 5]; q[3] = qpos()[qa + 6];
         const float nrm = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);  // x / norm(x), as mjx math.normalize
-        q[0] /= nrm; q[1] /= nrm; q[2] /= nrm; q[3] /= nrm;
+        const float inrm = bt_div(1.0f, nrm);
+        q[0] *= inrm; q[1] *= inrm; q[2] *= inrm; q[3] *= inrm;
         // MJX kinematics stores the normalised quaternion back into qpos
         qpos()[qa + 3] = q[0]; qpos()[qa + 4] = q[1]; qpos()[qa + 5] = q[2]; qpos()[qa + 6] = q[3];
       } else {
@@ -884,13 +885,13 @@ struct BtEnv {
     float da[3], db[3], am[3], bm[3], tr[3];
     for (int k = 0; k < 3; k++) { da[k] = a1[k] - a0[k]; db[k] = b1[k] - b0[k]; }
     const float la = sqrtf(bt_dot3(da, da)), lb = sqrtf(bt_dot3(db, db));
-    const float ia = la > 0.f ? 1.0f / la : 1.0f, ib = lb > 0.f ? 1.0f / lb : 1.0f;
+    const float ia = la > 0.f ? bt_div(1.0f, la) : 1.0f, ib = lb > 0.f ? bt_div(1.0f, lb) : 1.0f;
     for (int k = 0; k < 3; k++) { da[k] *= ia; db[k] *= ib; }
     const float ha = 0.5f * la, hb = 0.5f * lb;
     for (int k = 0; k < 3; k++) { am[k] = a0[k] + da[k] * ha; bm[k] = b0[k] + db[k] * hb; tr[k] = am[k] - bm[k]; }
     const float dab = bt_dot3(da, db), dat = bt_dot3(da, tr), dbt = bt_dot3(db, tr);
     const float den = 1.f - dab * dab;
-    const float ota = (-dat + dab * dbt) / (den + 1e-6f), otb = dbt + ota * dab;
+    const float ota = bt_div(-dat + dab * dbt, den + 1e-6f), otb = dbt + ota * dab;
     const float ta = bt_clampf(ota, -ha, ha), tb = bt_clampf(otb, -hb, hb);
     float ba[3], bb[3], na[3], nb[3], v[3];
     for (int k = 0; k < 3; k++) { ba[k] = am[k] + da[k] * ta; bb[k] = bm[k] + db[k] * tb; }
@@ -927,7 +928,7 @@ struct BtEnv {
           const bool usey = n[1] > -0.5f && n[1] < 0.5f;
           b[0] = usey ? R1[1] : R1[2]; b[1] = usey ? R1[4] : R1[5]; b[2] = usey ? R1[7] : R1[8];
         } else {
-          const float ib = 1.0f / bn;
+          const float ib = bt_div(1.0f, bn);
           b[0] *= ib; b[1] *= ib; b[2] *= ib;
         }
         fr[0] = n[0]; fr[1] = n[1]; fr[2] = n[2]; fr[3] = b[0]; fr[4] = b[1]; fr[5] = b[2];
@@ -967,7 +968,7 @@ struct BtEnv {
         float n[3] = {pb[0] - pa[0], pb[1] - pa[1], pb[2] - pa[2]};
         const float len = sqrtf(bt_dot3(n, n));
         if (len < BT_MINVAL) { n[0] = 1.f; n[1] = 0.f; n[2] = 0.f; }
-        else { const float il = 1.0f / len; n[0] *= il; n[1] *= il; n[2] *= il; }
+        else { const float il = bt_div(1.0f, len); n[0] *= il; n[1] *= il; n[2] *= il; }
         dist = len - (s10 + s20);
         for (int k = 0; k < 3; k++) pos[k] = pa[k] + n[k] * (s10 + 0.5f * dist);
         make_frame(n, fr);
@@ -1033,14 +1034,14 @@ struct BtEnv {
     if (width < BT_MINVAL) width = BT_MINVAL;
     mid = bt_clampf(mid, BT_MINIMP, BT_MAXIMP);
     if (power < 1.f) power = 1.f;
-    k = 1.f / (dmax * dmax * timeconst * timeconst * dampratio * dampratio);
-    b = 2.f / (dmax * timeconst);
-    if (sr0 <= 0.f) k = -sr0 / (dmax * dmax);
-    if (sr1 <= 0.f) b = -sr1 / dmax;
-    const float x = fabsf(pos) / width;
+    k = bt_div(1.f, dmax * dmax * timeconst * timeconst * dampratio * dampratio);
+    b = bt_div(2.f, dmax * timeconst);
+    if (sr0 <= 0.f) k = bt_div(-sr0, dmax * dmax);
+    if (sr1 <= 0.f) b = bt_div(-sr1, dmax);
+    const float x = bt_div(fabsf(pos), width);
     float y;
     if (power == 2.f) {  // MuJoCo default; the general case goes through the out-of-line helper (code size)
-      y = x < mid ? x * x / mid : 1.f - (1.f - x) * (1.f - x) / (1.f - mid);
+      y = x < mid ? bt_div(x * x, mid) : 1.f - bt_div((1.f - x) * (1.f - x), 1.f - mid);
     } else {
       y = bt_impedance_pow(x, mid, power);
     }
@@ -1066,30 +1067,30 @@ struct BtEnv {
       const float t = BT_LDG(m.con_invweight + c);
       const int dim = BT_LDG(m.con_dim + c);
       if (dim == 1) {
-        float R = t * (1.f - imp) / imp;
+        float R = bt_div(t * (1.f - imp), imp);
         R = R < BT_MINVAL ? BT_MINVAL : R;
-        e.D[sl][0] = 1.f / R;
+        e.D[sl][0] = bt_div(1.f, R);
         aref[sl][0] = -b * jv[sl][0] - k * imp * pos;
       } else if (m.cone == BT_CONE_PYRAMIDAL) {
 #pragma unroll
         for (int a = 0; a < 2; a++) {
           const float mu = BT_LDG(m.con_mu + 2 * c + a);
           e.mu[sl][a] = mu;
-          float R = (t + mu * mu * t) * 2.f * mu * mu / m.impratio * (1.f - imp) / imp;
+          float R = bt_div(bt_div((t + mu * mu * t) * 2.f * mu * mu, m.impratio) * (1.f - imp), imp);
           R = R < BT_MINVAL ? BT_MINVAL : R;
-          e.D[sl][2 * a] = e.D[sl][2 * a + 1] = 1.f / R;
+          e.D[sl][2 * a] = e.D[sl][2 * a + 1] = bt_div(1.f, R);
           aref[sl][2 * a] = -b * (jv[sl][0] + mu * jv[sl][1 + a]) - k * imp * pos;
           aref[sl][2 * a + 1] = -b * (jv[sl][0] - mu * jv[sl][1 + a]) - k * imp * pos;
         }
       } else {
         // elliptic: rows 0 (normal), 1, 2 (friction); friction rows: pos 0 in aref, impedance from the normal
         e.mu[sl][0] = BT_LDG(m.con_mu + 2 * c); e.mu[sl][1] = BT_LDG(m.con_mu + 2 * c + 1);
-        float R = t * (1.f - imp) / imp;
+        float R = bt_div(t * (1.f - imp), imp);
         R = R < BT_MINVAL ? BT_MINVAL : R;
-        e.D[sl][0] = 1.f / R;
-        float Rf = t / m.impratio * (1.f - imp) / imp;
+        e.D[sl][0] = bt_div(1.f, R);
+        float Rf = bt_div(bt_div(t, m.impratio) * (1.f - imp), imp);
         Rf = Rf < BT_MINVAL ? BT_MINVAL : Rf;
-        e.D[sl][1] = e.D[sl][2] = 1.f / Rf;
+        e.D[sl][1] = e.D[sl][2] = bt_div(1.f, Rf);
         aref[sl][0] = -b * jv[sl][0] - k * imp * pos;
         aref[sl][1] = -b * jv[sl][1];
         aref[sl][2] = -b * jv[sl][2];
@@ -1107,9 +1108,9 @@ struct BtEnv {
       const float sg = dlo < dhi ? 1.f : -1.f;
       float k, b, imp;
       kbi(BT_LDG(m.dof_solref + 2 * i), BT_LDG(m.dof_solref + 2 * i + 1), m.dof_solimp + 5 * i, pos, k, b, imp);
-      float R = BT_LDG(m.dof_invweight0 + i) * (1.f - imp) / imp;
+      float R = bt_div(BT_LDG(m.dof_invweight0 + i) * (1.f - imp), imp);
       R = R < BT_MINVAL ? BT_MINVAL : R;
-      e.lD[sl] = 1.f / R;
+      e.lD[sl] = bt_div(1.f, R);
       e.lsg[sl] = sg;
       laref[sl] = -b * sg * qvel()[i] - k * imp * pos;
     }
@@ -1450,7 +1451,7 @@ struct BtEnv {
       { float r3[3] = {pg_pMg, g_pMg, g_Mg}; if (G > 1) { W::template allsumN<3>(r3, lane); pg_pMg = r3[0]; g_pMg = r3[1]; g_Mg = r3[2]; } }
       float beta = 0.f;
       if (it > 0) {
-        beta = (g_Mg - g_pMg) / (pg_pMg > BT_MINVAL ? pg_pMg : BT_MINVAL);
+        beta = bt_div(g_Mg - g_pMg, pg_pMg > BT_MINVAL ? pg_pMg : BT_MINVAL);
         beta = beta < 0.f ? 0.f : beta;
       }
 #pragma unroll
@@ -1635,7 +1636,7 @@ struct BtEnv {
       const float w[3] = {v[3], v[4], v[5]};
       const float n = sqrtf(bt_dot3(w, w));
       float ax[3] = {0.f, 0.f, 0.f};
-      if (n > 0.f) { const float in = 1.0f / n; ax[0] = w[0] * in; ax[1] = w[1] * in; ax[2] = w[2] * in; }
+      if (n > 0.f) { const float in = bt_div(1.0f, n); ax[0] = w[0] * in; ax[1] = w[1] * in; ax[2] = w[2] * in; }
       const float ha = 0.5f * h * n;
       const float sn = sinf(ha), cs = cosf(ha);
       float qr[4] = {cs, ax[0] * sn, ax[1] * sn, ax[2] * sn}, q2[4];

@@ -129,6 +129,15 @@ BT_DEV float bt_rcp_pos(float x) {
   return 1.0f / x;
 #endif
 }
+// a / b where b is known to be a normal, non-zero number (impedances, regularisers, lengths behind a > 0 guard): a times the
+// refined reciprocal (<= 1 ulp of 1/b), without the range check and out-of-line slow path of an IEEE division
+BT_DEV float bt_div(float a, float b) {
+#ifdef __CUDACC__
+  return a * bt_rcp_pos(b);
+#else
+  return a / b;
+#endif
+}
 // 16-byte aligned 12-float record / its first 6 floats (shared memory): 128-bit loads on the device
 BT_DEV void bt_ld12(const float* p, float* o) {
 #ifdef __CUDACC__
