@@ -70,3 +70,22 @@ def test_ppo_loss_is_finite_and_has_gradients():
     loss.backward()
     assert torch.isfinite(loss) and all(p.grad is not None and torch.isfinite(p.grad).all() for p in pol.parameters())
     assert set(m) == {"total_loss", "policy_loss", "v_loss", "entropy_loss"}
+
+
+def test_linear_with_matvec_bias_gradient_matches_autograd():
+    torch.manual_seed(1)
+    net = ppo.MLP([9, 16, 4], in_align=4)
+    x = torch.randn(5, 7, 9)
+    tgt = torch.randn(5, 7, 4)
+    ((net(x) - tgt) ** 2).sum().backward()
+    got = [p.grad.clone() for p in net.parameters()]
+    for p in net.parameters():
+        p.grad = None
+    h = torch.nn.functional.pad(x, (0, net.in_padded - 9))
+    for i, l in enumerate(net.layers):                                       # the same network through nn.Linear's own backward
+        h = l(h)
+        if i + 1 < len(net.layers):
+            h = torch.nn.functional.silu(h)
+    ((h - tgt) ** 2).sum().backward()
+    for g, p in zip(got, net.parameters()):
+        np.testing.assert_allclose(g.numpy(), p.grad.numpy(), rtol=1e-5, atol=1e-5)
