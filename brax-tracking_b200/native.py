@@ -25,7 +25,8 @@ STATE_FIELDS = ("qpos", "qvel", "act", "qacc_warmstart", "time", "xpos")
 
 # exported symbols, exactly as declared in include/bt_api.h
 SYMBOLS = ["bt_model_create", "bt_model_destroy", "bt_model_dims", "bt_model_launch", "bt_reset", "bt_step",
-           "bt_physics_step", "bt_pipeline_init", "bt_reward_obs", "bt_forward_debug", "bt_last_error", "bt_launch_count"]
+           "bt_physics_step", "bt_pipeline_init", "bt_reward_obs", "bt_forward_debug", "bt_last_error", "bt_launch_count",
+           "bt_ppo_tanh_normal_fwd", "bt_ppo_tanh_normal_bwd"]
 
 
 class StatePtrs(C.Structure):
@@ -57,6 +58,39 @@ def _check(rc):
 
 def launch_count() -> int:
     return int(lib().bt_launch_count())
+
+
+def _bt_strides(t):
+    """(b, t) element strides of a [B, T, A] tensor whose innermost dim is contiguous."""
+    if t.dim() != 3 or (t.shape[2] > 1 and t.stride(2) != 1):
+        raise ValueError(f"expected a [B, T, A] tensor with a contiguous innermost dim, got strides {t.stride()}")
+    return C.c_int64(t.stride(0)), C.c_int64(t.stride(1))
+
+
+def ppo_tanh_normal(logits, raw, noise, grads=None):
+    """bt_ppo_tanh_normal_fwd (grads None): returns (log_prob, entropy_term) as [T, B]; bt_ppo_tanh_normal_bwd
+    (grads = (glp, gent), contiguous [T, B]): returns d/dlogits [B, T, 2A].  CUDA float32 tensors, current stream."""
+    import torch
+    B, T, A2 = logits.shape
+    A = A2 // 2
+    if not (logits.is_cuda and logits.is_contiguous() and logits.dtype == torch.float32 and raw.dtype == torch.float32
+            and noise.dtype == torch.float32 and tuple(raw.shape) == (B, T, A) and tuple(noise.shape) == (B, T, A)):
+        raise ValueError("ppo_tanh_normal: logits [B, T, 2A] contiguous float32 on CUDA, raw / noise [B, T, A] float32")
+    stream = C.c_void_p(torch.cuda.current_stream(logits.device).cuda_stream)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    osb, ost = C.c_int64(1), C.c_int64(B)                                    # outputs / output gradients are [T, B] contiguous
+    if grads is None:
+        lp, ent = torch.empty(T, B, device=logits.device), torch.empty(T, B, device=logits.device)
+        _check(lib().bt_ppo_tanh_normal_fwd(B, T, A, p(logits), p(raw), *_bt_strides(raw), p(noise), *_bt_strides(noise), p(lp), p(ent),
+                                            osb, ost, stream))
+        return lp, ent
+    glp, gent = grads
+    if not (glp.is_contiguous() and gent.is_contiguous() and tuple(glp.shape) == (T, B) and tuple(gent.shape) == (T, B)):
+        raise ValueError("ppo_tanh_normal: output gradients must be contiguous [T, B]")
+    out = torch.empty_like(logits)
+    _check(lib().bt_ppo_tanh_normal_bwd(B, T, A, p(logits), p(raw), *_bt_strides(raw), p(noise), *_bt_strides(noise), p(glp), p(gent),
+                                        osb, ost, p(out), stream))
+    return out
 
 
 class NativeModel:

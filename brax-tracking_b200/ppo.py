@@ -24,7 +24,7 @@ import torch.distributed as dist
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import envs as envs_mod, parallel, prng
+from . import envs as envs_mod, native, parallel, prng
 
 
 # ---------------------------------------------------------------------------------------------- networks
@@ -157,6 +157,21 @@ class NormalTanh:
         return (ent + NormalTanh.log_det_jac(loc + scale * noise)).sum(-1)
 
 
+class _TanhNormalTerms(torch.autograd.Function):
+    """(log_prob(raw), sampled-entropy term) of NormalTanh per row, time-major [T, B], from batch-major logits [B, T, 2A]:
+    one fused CUDA pass forward and one backward (csrc/bt_ppo.cu) instead of ~60 elementwise launches."""
+
+    @staticmethod
+    def forward(ctx, logits, raw, noise):
+        ctx.save_for_backward(logits, raw, noise)
+        return native.ppo_tanh_normal(logits, raw, noise)
+
+    @staticmethod
+    def backward(ctx, glp, gent):
+        logits, raw, noise = ctx.saved_tensors
+        return native.ppo_tanh_normal(logits, raw, noise, grads=(glp.contiguous(), gent.contiguous())), None, None
+
+
 # ---------------------------------------------------------------------------------------------- losses
 def compute_gae(truncation, termination, rewards, values, bootstrap_value, lambda_: float, discount: float):
     """brax.training.agents.ppo.losses.compute_gae; time-major [T, B]."""
@@ -181,13 +196,18 @@ def compute_ppo_loss(policy, value, normalizer, data: Dict[str, torch.Tensor], n
     # the networks act row by row: they are applied to the observation rows as stored (batch-major, contiguous: no transposed
     # copy of the widest tensor of the update) and only their narrow outputs are viewed time-first
     obs = normalizer(data["observation"])
-    logits = policy(obs).transpose(0, 1)
+    logits_bm = policy(obs)
+    logits = logits_bm.transpose(0, 1)
     baseline = value(obs).squeeze(-1).transpose(0, 1)
     bootstrap = value(normalizer(data["next_observation"][:, -1])).squeeze(-1)
     rewards = tm["reward"] * reward_scaling
     truncation = tm["truncation"]
     termination = (1.0 - tm["discount"]) * (1.0 - truncation)
-    target_lp = NormalTanh.log_prob(logits, tm["raw_action"])
+    fused = logits_bm.is_cuda and logits_bm.dtype == torch.float32 and logits_bm.dim() == 3
+    if fused:
+        target_lp, entropy_rows = _TanhNormalTerms.apply(logits_bm.contiguous(), data["raw_action"], noise.transpose(0, 1))
+    else:
+        target_lp, entropy_rows = NormalTanh.log_prob(logits, tm["raw_action"]), NormalTanh.entropy(logits, noise)
     vs, adv = compute_gae(truncation, termination, rewards, baseline, bootstrap, gae_lambda, discounting)
     if normalize_advantage:
         adv = (adv - adv.mean()) / (adv.std(unbiased=False) + 1e-8)
@@ -195,7 +215,7 @@ def compute_ppo_loss(policy, value, normalizer, data: Dict[str, torch.Tensor], n
     policy_loss = -torch.minimum(rho * adv, rho.clamp(1 - clipping_epsilon, 1 + clipping_epsilon) * adv).mean()
     v_err = vs - baseline
     v_loss = (v_err * v_err).mean() * 0.5 * 0.5
-    entropy = NormalTanh.entropy(logits, noise).mean()
+    entropy = entropy_rows.mean()
     total = policy_loss + v_loss - entropy_cost * entropy
     return total, dict(total_loss=total.detach(), policy_loss=policy_loss.detach(), v_loss=v_loss.detach(), entropy_loss=(-entropy_cost * entropy).detach())
 

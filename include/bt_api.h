@@ -18,6 +18,7 @@
  *   bt_physics_step   <- PipelineEnv.pipeline_step alone (envs/fruitfly.py:500; brax.mjx.pipeline.step)
  *   bt_pipeline_init  <- PipelineEnv.pipeline_init = mjx.forward (envs/fruitfly.py:477)
  *   bt_reward_obs     <- the part of env.step after pipeline_step (envs/fruitfly.py:502-596, _get_obs :598-646)
+ *   bt_ppo_tanh_normal_fwd / _bwd <- the policy terms of brax compute_ppo_loss (custom_brax/custom_ppo.py:250-284)
  *   bt_forward_debug  <- no reference counterpart: dumps on-chip intermediates for the parity tests
  */
 #ifndef BT_API_H_
@@ -81,6 +82,18 @@ int bt_reward_obs(BtModel* m, int n_envs, const float* action, BtStatePtrs state
    cdist [n, ncon], niter [n] */
 int bt_forward_debug(BtModel* m, int n_envs, const float* ctrl, BtStatePtrs state, int stop, float* scratch,
                      float* cdist, int32_t* niter, void* stream);
+
+/* Learner-side helper of the PPO loop that drives bt_step (custom_brax/custom_ppo.py:250-284 -> brax compute_ppo_loss with
+   NormalTanhDistribution, min_std 0.001): per (b, t) row of logits [B, T, 2A] (contiguous; loc | pre-softplus scale), the
+   log-probability of the stored raw action and the sampled-entropy term, summed over the A action dims, in one pass; and the
+   matching gradient w.r.t. the logits.  raw / noise [.., A] and the per-row outputs / output gradients are addressed as
+   b * sb + t * st (element strides), innermost dim contiguous. */
+int bt_ppo_tanh_normal_fwd(int B, int T, int A, const float* logits, const float* raw, int64_t raw_sb, int64_t raw_st,
+                           const float* noise, int64_t noise_sb, int64_t noise_st, float* lp, float* ent, int64_t out_sb,
+                           int64_t out_st, void* stream);
+int bt_ppo_tanh_normal_bwd(int B, int T, int A, const float* logits, const float* raw, int64_t raw_sb, int64_t raw_st,
+                           const float* noise, int64_t noise_sb, int64_t noise_st, const float* glp, const float* gent,
+                           int64_t out_sb, int64_t out_st, float* glogits, void* stream);
 
 const char* bt_last_error(void);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */

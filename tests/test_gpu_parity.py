@@ -177,6 +177,29 @@ def test_ppo_loop_runs_on_the_fused_step(tmp_path):
     np.testing.assert_allclose(c_dev.body_positions, c_host.body_positions, atol=2e-6)
 
 
+def test_fused_tanh_normal_terms_match_the_torch_formulas():
+    """csrc/bt_ppo.cu (log-prob + entropy term of brax's NormalTanhDistribution, forward and backward) against the
+    elementwise torch restatement that test_ppo.py checks on the CPU; fp32 tolerance 1e-4 relative."""
+    import torch
+    from brax_tracking_b200 import ppo
+    torch.manual_seed(0)
+    B, T, A = 37, 5, 38
+    logits = (torch.randn(B, T, 2 * A, device="cuda") * 1.5).requires_grad_(True)
+    raw = torch.randn(B, T, A, device="cuda") * 2
+    noise = torch.randn(T, B, A, device="cuda")                              # time-major, as the learner draws it
+    wl, we = torch.randn(T, B, device="cuda"), torch.randn(T, B, device="cuda")
+    lp, ent = ppo._TanhNormalTerms.apply(logits, raw, noise.transpose(0, 1))
+    ((lp * wl).sum() + (ent * we).sum()).backward()
+    g_fused, logits.grad = logits.grad.clone(), None
+    lt = logits.transpose(0, 1)
+    lp_ref, ent_ref = ppo.NormalTanh.log_prob(lt, raw.transpose(0, 1)), ppo.NormalTanh.entropy(lt, noise)
+    ((lp_ref * wl).sum() + (ent_ref * we).sum()).backward()
+    assert lp.shape == (T, B) and ent.shape == (T, B)
+    torch.testing.assert_close(lp, lp_ref, rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(ent, ent_ref, rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(g_fused, logits.grad, rtol=1e-4, atol=1e-4)
+
+
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()
