@@ -175,17 +175,19 @@ class _TanhNormalTerms(torch.autograd.Function):
 # ---------------------------------------------------------------------------------------------- losses
 def compute_gae(truncation, termination, rewards, values, bootstrap_value, lambda_: float, discount: float):
     """brax.training.agents.ppo.losses.compute_gae; time-major [T, B]."""
-    trunc_mask = 1.0 - truncation
-    values_tp1 = torch.cat([values[1:], bootstrap_value[None]], 0)
-    deltas = (rewards + discount * (1.0 - termination) * values_tp1 - values) * trunc_mask
-    acc = torch.zeros_like(bootstrap_value)
-    out = []
-    for t in range(values.shape[0] - 1, -1, -1):
-        acc = deltas[t] + discount * (1.0 - termination[t]) * trunc_mask[t] * lambda_ * acc
-        out.append(acc)
-    vs = torch.stack(out[::-1], 0) + values
-    vs_tp1 = torch.cat([vs[1:], bootstrap_value[None]], 0)
-    adv = (rewards + discount * (1.0 - termination) * vs_tp1 - values) * trunc_mask
+    with torch.no_grad():                                                    # targets only: nothing here is differentiated
+        trunc_mask = 1.0 - truncation
+        values_tp1 = torch.cat([values[1:], bootstrap_value[None]], 0)
+        deltas = (rewards + discount * (1.0 - termination) * values_tp1 - values) * trunc_mask
+        coef = discount * (1.0 - termination) * trunc_mask * lambda_         # one fused multiply-add per step of the scan
+        acc = torch.zeros_like(bootstrap_value)
+        out = []
+        for t in range(values.shape[0] - 1, -1, -1):
+            acc = torch.addcmul(deltas[t], coef[t], acc)
+            out.append(acc)
+        vs = torch.stack(out[::-1], 0) + values
+        vs_tp1 = torch.cat([vs[1:], bootstrap_value[None]], 0)
+        adv = (rewards + discount * (1.0 - termination) * vs_tp1 - values) * trunc_mask
     return vs.detach(), adv.detach()
 
 
