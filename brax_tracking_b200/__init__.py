@@ -1,8 +1,2 @@
-"""Import alias: the product package lives in ``brax-tracking_b200/`` (not a valid Python
-identifier), this shim makes it importable as ``brax_tracking_b200``."""
-import os as _os
-
-_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "brax-tracking_b200")
-__path__ = [_real]
-with open(_os.path.join(_real, "__init__.py")) as _f:
-    exec(compile(_f.read(), _os.path.join(_real, "__init__.py"), "exec"))
+"""B200-native batched physics + tracking-reward step for the rodent / fruit-fly imitation envs."""
+__version__ = "0.1.0"

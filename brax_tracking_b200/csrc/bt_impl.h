@@ -1785,6 +1785,7 @@ struct BtEnv {
     for (int i = lane; i < m.nv; i += G) nan |= (qvel()[i] != qvel()[i]) | (warm()[i] != warm()[i]);
     for (int i = lane; i < m.na; i += G) nan |= act()[i] != act()[i];
     for (int i = lane; i < 3 * m.nbody; i += G) nan |= xpos()[i] != xpos()[i];
+    nan |= cs != cs;  // data.ctrl = action is part of the flattened Data too: the sum of squares is NaN iff an action is
     nan = W::any(nan);
     done = fmaxf(done, nan ? 1.f : 0.f);
     r.reward = bt_nan_to_num(reward);

@@ -248,11 +248,13 @@ BT_DEV void bt_threefry2x32(unsigned k0, unsigned k1, unsigned& x0, unsigned& x1
     x1 += ks[(g + 2) % 3] + (unsigned)(g + 1);
   }
 }
-// element idx of threefry_2x32(key, iota(n)) with JAX's split-in-halves convention
+// element idx of threefry_2x32(key, iota(n)) with JAX's split-in-halves convention.  An odd-length counter array is padded
+// with a ZERO (jax/_src/prng.py threefry_2x32: concatenate([count, uint32([0])])), so the last element of the first half
+// pairs with counter 0, not n (known answer: uniform(PRNGKey(0), ()) = 0.41845703, tests/test_prng.py)
 BT_DEV unsigned bt_random_bits(unsigned k0, unsigned k1, int idx, int n) {
   int half = (n + 1) / 2;
   unsigned x0, x1;
-  if (idx < half) { x0 = (unsigned)idx; x1 = (unsigned)(half + idx); }
+  if (idx < half) { x0 = (unsigned)idx; x1 = half + idx < n ? (unsigned)(half + idx) : 0u; }
   else { x0 = (unsigned)(idx - half); x1 = (unsigned)idx; }
   bt_threefry2x32(k0, k1, x0, x1);
   return idx < half ? x0 : x1;

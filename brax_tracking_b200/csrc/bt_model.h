@@ -1,7 +1,7 @@
 // Device-side model description for the fused physics + tracking-reward step.
 //
 // All model constants are uploaded once by bt_model_create() as *named* tables: the X-macro lists below
-// name exactly the arrays produced by the host packer (brax-tracking_b200/model.py::pack).  Kernels take the
+// name exactly the arrays produced by the host packer (brax_tracking_b200/model.py::pack).  Kernels take the
 // struct by value (__grid_constant__) and read the tables through the read-only path; per-environment state
 // lives in shared memory for the duration of a control step ("data layout").
 #pragma once

@@ -9,7 +9,7 @@
 //
 // Build (on a machine with jaxlib):
 //   g++ -O2 -fPIC -shared -I$(python -c "import jax; print(jax.ffi.include_dir())") -Iinclude \
-//       brax-tracking_b200/csrc/xla_ffi_shim.cc -Lbrax-tracking_b200 -lbt_b200 -o libbt_xla_ffi.so
+//       brax_tracking_b200/csrc/xla_ffi_shim.cc -Lbrax_tracking_b200 -lbt_b200 -o libbt_xla_ffi.so
 // Register:  jax.ffi.register_ffi_target("bt_step", jax.ffi.pycapsule(lib.BtStepFfi), platform="CUDA")
 #if __has_include("xla/ffi/api/ffi.h")
 #include <cuda_runtime_api.h>

@@ -47,8 +47,11 @@ def threefry2x32(key, x0, x1):
 
 
 def _threefry_counts(key, n):
-    """threefry_2x32(key, iota(n)) with JAX's split-in-halves convention (odd n padded)."""
+    """threefry_2x32(key, iota(n)) with JAX's split-in-halves convention; an odd-length counter array is padded with a
+    ZERO (jax/_src/prng.py::threefry_2x32: ``concatenate([count.ravel(), np.uint32([0])])``), not with n."""
     cnt = np.arange(n + (n % 2), dtype=_U32)
+    if n % 2:
+        cnt[-1] = 0
     half = len(cnt) // 2
     y0, y1 = threefry2x32(key, cnt[:half], cnt[half:])
     return np.concatenate([y0, y1])[:n]
@@ -167,9 +170,10 @@ class EnvOracle:
         return 0.5 * np.arccos(dist)
 
     # -- reset: fruitfly.py:449-495 (+ rodent.py:154-159), EpisodeWrapper.reset, AutoReset.reset -----
-    def reset(self, keys, fixed_start_frame=-1):
+    def reset(self, keys, fixed_start_frame=-1, start_frames=None):
         """keys: [N,2] uint32 (one JAX key per env, as jax.random.split(key_env, num_envs)).
-        fixed_start_frame >= 0: RenderRolloutWrapperTracking.reset (custom_wrappers.py:85-125): split(rng, 3), that frame."""
+        fixed_start_frame >= 0: RenderRolloutWrapperTracking.reset (custom_wrappers.py:85-125): split(rng, 3), that frame.
+        start_frames (test-only): per-env start frames replacing the randint draw (late-clip cases)."""
         c, dt, m = self.c, self.dt, self.m
         N = keys.shape[0]
         qpos = np.zeros((N, m.nq), dtype=dt)
@@ -180,10 +184,13 @@ class EnvOracle:
             k = split((keys[e, 0], keys[e, 1]), 4 if fixed_start_frame < 0 else 3)
             rng, rng1, rng2 = (k[0, 0], k[0, 1]), (k[1, 0], k[1, 1]), (k[2, 0], k[2, 1])
             start[e] = randint(rng, 0, 44) if fixed_start_frame < 0 else fixed_start_frame
+            if start_frames is not None:
+                start[e] = start_frames[e]
             q0 = m.qpos0.astype(dt).copy()
             if c["seed_root_from_clip"] and fixed_start_frame < 0:
-                q0[:2] = self.clip["position"][start[e], :2]
-                q0[3:7] = self.clip["quaternion"][start[e]]
+                fs = min(max(int(start[e]), 0), self.T - 1)   # JAX gather clamps
+                q0[:2] = self.clip["position"][fs, :2]
+                q0[3:7] = self.clip["quaternion"][fs]
             qpos[e] = q0 + uniform(rng1, m.nq, lo, hi).astype(dt)
             qvel[e] = uniform(rng2, m.nv, lo, hi).astype(dt)
         st = dict(qpos=qpos, qvel=qvel, act=np.zeros((N, m.na), dtype=dt), qacc_warmstart=np.zeros((N, m.nv), dtype=dt),
@@ -274,6 +281,7 @@ class EnvOracle:
         nan = np.zeros(N, dtype=bool)
         for k in ("qpos", "qvel", "act", "qacc_warmstart", "xpos", "time"):
             nan |= np.isnan(ps[k].reshape(N, -1)).any(axis=1)
+        nan |= np.isnan(action.reshape(N, -1)).any(axis=1)   # data.ctrl = action is a leaf of the flattened mjx.Data (fruitfly.py:572)
         done = np.maximum(done, nan.astype(dt))
         metrics = dict(pos_reward=pos_reward, quat_reward=quat_reward, joint_reward=joint_reward,
                        angvel_reward=angvel_reward, bodypos_reward=bodypos_reward, endeff_reward=endeff_reward,

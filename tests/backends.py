@@ -41,6 +41,10 @@ class EmuBackend:
         self.e.reward_obs(st, out, action)
         return out
 
+    def pipeline_init(self, st):
+        self.e.physics_step(st, None, 0)
+        return st
+
     def forward_debug(self, st, ctrl, stop=0):
         return self.e.forward_debug(st, ctrl, stop)
 
@@ -93,6 +97,12 @@ class CudaBackend:
         self.nm.reward_obs(self._d(np.asarray(action, np.float32)), dst, dout)
         self._back(dout, out)
         return out
+
+    def pipeline_init(self, st):
+        dst = self._dst(st)
+        self.nm.pipeline_init(dst)
+        self._back(dst, st)
+        return st
 
     def forward_debug(self, st, ctrl, stop=0):
         sc, cd, ni = self.nm.forward_debug(None if ctrl is None else self._d(np.asarray(ctrl, np.float32)), self._dst(st), stop)

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 _SRC = os.path.join(_HERE, "host_emu", "bt_emu.cpp")
 _LIB = os.path.join(_HERE, "host_emu", "libbt_emu.so")
-_CSRC = os.path.join(_ROOT, "brax-tracking_b200", "csrc")
+_CSRC = os.path.join(_ROOT, "brax_tracking_b200", "csrc")
 
 
 class StatePtrs(C.Structure):

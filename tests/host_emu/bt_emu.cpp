@@ -1,6 +1,6 @@
 // HOST EMULATION -- TEST INFRASTRUCTURE ONLY (never loaded by the product package).
 //
-// Compiles the exact per-environment programs of the sm_100a kernels (brax-tracking_b200/csrc/bt_programs.h)
+// Compiles the exact per-environment programs of the sm_100a kernels (brax_tracking_b200/csrc/bt_programs.h)
 // with one lane per environment (G = 1), so the table logic, the tree-sparse factorisation, the matrix-free
 // Jacobian and the env layer can be checked against the oracle on the CPU-only box.  It exercises none of the
 // warp-level synchronisation; that is what the `-m gpu` tests and compute-sanitizer are for.
@@ -22,6 +22,9 @@ static char g_err[256];
 
 extern "C" {
 const char* emu_last_error(void) { return g_err; }
+
+// csrc/bt_math.h::bt_random_bits, element by element (tests/test_prng.py)
+uint32_t emu_random_bits(uint32_t k0, uint32_t k1, int idx, int n) { return bt_random_bits(k0, k1, idx, n); }
 
 int emu_model_create(int n, const char* const* names, const void* const* data, const int64_t* counts, const int* is_float,
                      EmuModel** out) {

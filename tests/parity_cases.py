@@ -114,18 +114,35 @@ def check_reset(backend, name, N=32, seed=3):
     return st, out, s0
 
 
-def check_teacher_forced(backend, name, N=16, T=100, seed=5, act_scale=0.3, episode_length=None):
+FLAG_METRICS = ("too_far", "bad_pose", "bad_quat", "fall")
+FLOAT_METRICS = ("pos_reward", "quat_reward", "joint_reward", "angvel_reward", "bodypos_reward", "endeff_reward", "reward_quadctrl",
+                 "reward_alive")
+INFO_FLOATS = ("summed_pos_distance", "quat_distance", "joint_distance")
+
+
+def _metric_scale(cfg, k):
+    """absolute scale of a reward-term metric = its weight (fruitfly.py:514-537: w * exp(-c * d)); 1 for the others"""
+    return max(abs(float(cfg.get(k + "_weight", 1.0))), 1.0) if k.endswith("_reward") else 1.0
+
+
+def check_teacher_forced(backend, name, N=16, T=100, seed=5, act_scale=0.3, episode_length=None, start_frames=None, require_done=True):
+    """Wrapped step (AutoReset o Episode o env.step), every control step started from the ORACLE's state.
+    `start_frames`: override the per-environment clip frame after the reset (late-clip cases: the `cur_frame + 1` window of
+    `_get_obs` clamps to `[T - ref_len, T)`, fruitfly.py:602-611, and `clip[cur_frame]` clamps to the last frame)."""
     m, cfg, clip, tables = common.setup(name, episode_length)
     o64, eo = common.oracles(name, np.float64, episode_length)
     o32 = oracle_mod.Oracle(m, np.float32)
     keys = common.jax_keys(N, seed=seed)
     acts = common.actions(T, N, m.nu, seed=seed + 2, scale=act_scale)
-    s = eo.reset(keys)
+    s = eo.reset(keys, start_frames=start_frames)
     first = state_from_oracle(s["info"]["first_pipeline_state"], N)
     first_obs = np.array(s["info"]["first_obs"], np.float32)
     first_ii = np.stack([s["info"]["first_cur_frame"], s["info"]["first_steps_taken_cur_frame"]], 1).astype(np.int32)
-    n_done = 0
-    eq, ev, oq, ov, er = [], [], [], [], []
+    n_done = n_live = 0
+    wmax = max(_metric_scale(cfg, k) for k in FLOAT_METRICS)   # reward terms scale with their weights (fly joint reward: 50)
+    eq, ev, oq, ov, er, eo_med, eo_max = [], [], [], [], [], [], []
+    em = {k: [] for k in FLOAT_METRICS + INFO_FLOATS}
+    max_frame = 0
     for t in range(T):
         st = state_from_oracle(s["pipeline_state"], N)
         out = backend.new_outputs(N)
@@ -135,6 +152,7 @@ def check_teacher_forced(backend, name, N=16, T=100, seed=5, act_scale=0.3, epis
         out["info_i"][:, 1] = s["info"]["steps_taken_cur_frame"]
         p32 = o32.pipeline_batch({k: np.array(v, np.float32) for k, v in s["pipeline_state"].items()}, acts[t], cfg["n_frames"])
         backend.step(st, out, first, first_obs, first_ii, acts[t])
+        s_prev = s
         s = eo.step(s, acts[t])
         # ---- bit-exact: done flags, frame counters, episode counters, reset selection
         assert np.array_equal(out["done"], s["done"]), f"done flags differ at step {t}"
@@ -142,27 +160,204 @@ def check_teacher_forced(backend, name, N=16, T=100, seed=5, act_scale=0.3, epis
         assert np.array_equal(out["info_i"][:, 1], s["info"]["steps_taken_cur_frame"])
         assert np.array_equal(out["info_f"][:, 3], s["info"]["steps"])
         assert np.array_equal(out["info_f"][:, 4], s["info"]["truncation"])
-        for k in ("too_far", "bad_pose", "bad_quat", "fall"):
+        for k in FLAG_METRICS:
             assert np.array_equal(out["metrics"][:, common_metric(k)], s["metrics"][k]), f"{k} differs at step {t}"
         d = s["done"] > 0
         n_done += int(d.sum())
         if d.any():  # auto-reset restored the cached first state exactly
-            assert np.array_equal(st["qpos"][d], first["qpos"][d]) and np.array_equal(out["obs"][d], first_obs[d])
+            for k in ("qpos", "qvel", "act", "qacc_warmstart", "time", "xpos"):
+                assert np.array_equal(st[k][d], first[k][d]), k
+            assert np.array_equal(out["obs"][d], first_obs[d])
         nd = ~d
+        n_live += int(nd.sum())
         ref = s["pipeline_state"]
         eq.append(np.abs(st["qpos"] - ref["qpos"])[nd].max(1)); ev.append(np.abs(st["qvel"] - ref["qvel"])[nd].max(1))
         oq.append(np.abs(p32["qpos"] - ref["qpos"])[nd].max(1)); ov.append(np.abs(p32["qvel"] - ref["qvel"])[nd].max(1))
         er.append(np.abs(out["reward"] - s["reward"]))
-    assert n_done > 0, "the trajectory never exercised the auto-reset path"
-    eq, ev, oq, ov, er = (np.concatenate(x) for x in (eq, ev, oq, ov, er))
+        # ---- env layer of every LIVE environment, every step, at fp32 rounding level: the oracle's reward / obs functions
+        #      evaluated on the PRODUCT's post-step physics state (so the one-step physics departure does not blur it):
+        #      post-step observation (fruitfly.py:554 -> :598-646: the window clip[cur_frame + 1 : cur_frame + 1 + ref_len] AFTER
+        #      the frame counter advanced), the 8 float metrics, the 3 info floats (fruitfly.py:530,548-549,579-592), the reward
+        if nd.any():
+            over = {k: (st[k].reshape(N, m.nbody, 3) if k == "xpos" else st[k]) for k in st}
+            with np.errstate(all="ignore"):
+                chk = eo.step(s_prev, acts[t], physics_override=over)
+            np.testing.assert_allclose(out["obs"][nd], chk["obs"][nd], atol=2e-5, rtol=1e-6, err_msg=f"obs at step {t}")
+            np.testing.assert_allclose(out["reward"][nd], chk["reward"][nd], atol=1e-4 * wmax, err_msg=f"reward at step {t}")
+            for k in FLOAT_METRICS:
+                np.testing.assert_allclose(out["metrics"][nd, common_metric(k)], chk["metrics"][k][nd], atol=1e-4 * _metric_scale(cfg, k),
+                                           err_msg=f"{k} at step {t}")
+            for i, k in enumerate(INFO_FLOATS):
+                np.testing.assert_allclose(out["info_f"][nd, i], chk["info"][k][nd], atol=1e-5, rtol=1e-4, err_msg=f"{k} at step {t}")
+            # ... and against the oracle's own physics: bounded by the one-step state departure
+            eobs = np.abs(out["obs"][nd] - s["obs"][nd])
+            eo_med.append(np.median(eobs, 1)); eo_max.append(eobs.max(1))
+        # terminal-step values of every environment (the auto-reset does not touch metrics / info floats): bulk only
+        for k in FLOAT_METRICS:
+            em[k].append(np.abs(out["metrics"][:, common_metric(k)] - s["metrics"][k]) / _metric_scale(cfg, k))
+        for i, k in enumerate(INFO_FLOATS):
+            em[k].append(np.abs(out["info_f"][:, i] - s["info"][k]) / np.maximum(1.0, np.abs(s["info"][k])))
+        max_frame = max(max_frame, int(s["info"]["cur_frame"].max()))
+    assert n_done > 0 or not require_done, "the trajectory never exercised the auto-reset path"
+    assert n_live > 0, "no live environment was ever compared"
+    eq, ev, oq, ov, er, eo_med, eo_max = (np.concatenate(x) for x in (eq, ev, oq, ov, er, eo_med, eo_max))
     # ---- fp32 tolerance after ONE control step (n_frames substeps) from identical inputs:
     #      absolute bounds on the bulk, and no worse than 3x (bulk) / 10x (extreme tail) the float32 oracle's own departure from float64
     assert np.median(eq) < 1e-4 and np.median(ev) < 2e-2, (np.median(eq), np.median(ev))
     for p, k in ((50, 3), (90, 3), (99, 10), (100, 10)):   # the extreme tail of a few hundred samples is itself noisy
         assert np.percentile(eq, p) <= k * np.percentile(oq, p) + 1e-5, (p, np.percentile(eq, p), np.percentile(oq, p))
         assert np.percentile(ev, p) <= k * np.percentile(ov, p) + 1e-3, (p, np.percentile(ev, p), np.percentile(ov, p))
-    assert np.median(er) < 1e-4 and er.max() < 2e-2, (np.median(er), er.max())
-    return dict(n_done=n_done, qpos_med=float(np.median(eq)), qpos_max=float(eq.max()), qvel_med=float(np.median(ev)))
+    # reward / reward terms: |err| relative to the term's weight
+    assert np.median(er) < 1e-4 * wmax and er.max() < 2e-2 * wmax, (np.median(er), er.max())
+    # observation rows: typical element at fp32 rounding, worst element bounded by the one-step qvel tolerance
+    assert np.median(eo_med) < 1e-4 and eo_max.max() < max(2e-2, 1.5 * ev.max()), (np.median(eo_med), eo_max.max(), ev.max())
+    res = dict(n_done=n_done, n_live=n_live, max_frame=max_frame, qpos_med=float(np.median(eq)), qpos_max=float(eq.max()),
+               qvel_med=float(np.median(ev)), qvel_max=float(ev.max()), reward_med=float(np.median(er)), reward_max=float(er.max()),
+               obs_med=float(np.median(eo_med)), obs_max=float(eo_max.max()))
+    for k, v in em.items():
+        v = np.concatenate(v)
+        assert np.isfinite(v).all(), k
+        assert np.median(v) < 1e-4, (k, np.median(v), v.max(), res)
+        res[k + "_max"] = float(v.max())
+    return res
+
+
+def check_late_clip(backend, name, N=16, T=24, episode_length=None):
+    """Clip-end clamps: start frames T-14 .. T+1 so that within the run `cur_frame + 1 + ref_len` passes the end of the clip
+    (dynamic_slice clamps the window start, fruitfly.py:602-611) and `cur_frame` itself passes T - 1 (gather clamps)."""
+    m, cfg, clip, tables = common.setup(name, episode_length)
+    Tc = int(np.asarray(clip["joints"]).shape[0])
+    start = (Tc - 14 + np.arange(N) % 16).astype(np.int32)
+    r = check_teacher_forced(backend, name, N=N, T=T, seed=9, episode_length=episode_length, start_frames=start, require_done=False)
+    assert r["max_frame"] >= Tc, "the run never indexed past the end of the clip"
+    return r
+
+
+def check_unwrapped_step(backend, name, N=8, T=12, seed=13):
+    """The bare env (no wrappers): `pipeline_init` (fruitfly.py:477), `env.step` = `pipeline_step` + reward / obs
+    (fruitfly.py:497-596) through bt_pipeline_init / bt_physics_step / bt_reward_obs, teacher-forced against the oracle."""
+    m, cfg, clip, tables = common.setup(name)
+    o64, eo = common.oracles(name)
+    keys = common.jax_keys(N, seed=seed)
+    acts = common.actions(T, N, m.nu, seed=seed + 1, scale=0.3)
+    s = eo.reset(keys, fixed_start_frame=0)         # RenderRolloutWrapperTracking.reset: frame 0
+    # ---- pipeline_init = mjx.forward on (qpos, qvel): xpos and the warm start it leaves behind
+    st = state_from_oracle(s["pipeline_state"], N)
+    st["xpos"][:] = 0; st["qacc_warmstart"][:] = 0
+    backend.pipeline_init(st)
+    np.testing.assert_allclose(st["xpos"], s["pipeline_state"]["xpos"].reshape(N, -1), atol=2e-6)
+    sw = np.abs(s["pipeline_state"]["qacc_warmstart"]).max()
+    np.testing.assert_allclose(st["qacc_warmstart"], s["pipeline_state"]["qacc_warmstart"], atol=1e-3 * sw)
+    wmax = max(_metric_scale(cfg, k) for k in FLOAT_METRICS)
+    o32 = oracle_mod.Oracle(m, np.float32)
+    eq, oq = [], []
+    for t in range(T):
+        st = state_from_oracle(s["pipeline_state"], N)
+        out = backend.new_outputs(N)
+        out["info_i"][:, 0] = s["info"]["cur_frame"]
+        out["info_i"][:, 1] = s["info"]["steps_taken_cur_frame"]
+        p32 = o32.pipeline_batch({k: np.array(v, np.float32) for k, v in s["pipeline_state"].items()}, acts[t], cfg["n_frames"])
+        backend.physics_step(st, acts[t], cfg["n_frames"])
+        backend.reward_obs(st, out, acts[t])
+        # the env layer on the product's own physics state, at fp32 rounding level (see check_teacher_forced)
+        over = {k: (st[k].reshape(N, m.nbody, 3) if k == "xpos" else st[k]) for k in st}
+        chk = eo.reward_obs(s, over, acts[t])
+        s = eo.env_step(s, acts[t])
+        assert np.array_equal(out["done"], s["done"]), f"done differs at step {t}"
+        assert np.array_equal(out["info_i"][:, 0], s["info"]["cur_frame"]) and np.array_equal(out["info_i"][:, 1], s["info"]["steps_taken_cur_frame"])
+        for k in FLAG_METRICS:
+            assert np.array_equal(out["metrics"][:, common_metric(k)], s["metrics"][k]), k
+        np.testing.assert_allclose(out["obs"], chk["obs"], atol=2e-5, rtol=1e-6, err_msg=f"obs at step {t}")
+        np.testing.assert_allclose(out["reward"], chk["reward"], atol=1e-4 * wmax)
+        for k in FLOAT_METRICS:
+            np.testing.assert_allclose(out["metrics"][:, common_metric(k)], chk["metrics"][k], atol=1e-4 * _metric_scale(cfg, k), err_msg=k)
+        for i, k in enumerate(INFO_FLOATS):
+            np.testing.assert_allclose(out["info_f"][:, i], chk["info"][k], atol=1e-5, rtol=1e-4, err_msg=k)
+        eq.append(np.abs(st["qpos"] - s["pipeline_state"]["qpos"]).max(1)); oq.append(np.abs(p32["qpos"] - s["pipeline_state"]["qpos"]).max(1))
+        assert np.abs(out["reward"] - s["reward"]).max() < 2e-2 * wmax
+    eq, oq = np.concatenate(eq), np.concatenate(oq)
+    # physics of the unwrapped step: as in check_teacher_forced, relative to the float32 oracle's own one-step departure
+    assert np.median(eq) < 1e-4 and eq.max() <= 10 * oq.max() + 1e-5, (np.median(eq), eq.max(), oq.max())
+    stats = dict(qpos_med=float(np.median(eq)), qpos_max=float(eq.max()), o32_qpos_max=float(oq.max()))
+    assert int(s["info"]["cur_frame"].max()) == T // 2      # two control steps per mocap frame, from frame 0
+    return stats
+
+
+def check_nan_guard(backend, name, N=12, seed=17):
+    """NaN guard (fruitfly.py:569-577): a NaN anywhere in the pipeline state => done = 1 with nan_to_num'ed reward / obs; the
+    auto-reset wrapper then restores the cached first state, and the next step is clean.  Also the element-wise nan_to_num
+    of the observation row (NaN -> 0, +-inf -> +-FLT_MAX) on the unwrapped path, where no reset replaces the row."""
+    m, cfg, clip, tables = common.setup(name)
+    o64, eo = common.oracles(name)
+    keys = common.jax_keys(N, seed=seed)
+    acts = common.actions(3, N, m.nu, seed=seed + 1, scale=0.3)
+    s = eo.reset(keys)
+    first = state_from_oracle(s["info"]["first_pipeline_state"], N)
+    first_obs = np.array(s["info"]["first_obs"], np.float32)
+    first_ii = np.stack([s["info"]["first_cur_frame"], s["info"]["first_steps_taken_cur_frame"]], 1).astype(np.int32)
+    s = eo.step(s, acts[0])                                  # one clean step first
+    free = m.jnt_type[0] == 0
+    ps = {k: np.array(v, copy=True) for k, v in s["pipeline_state"].items()}
+    a1 = acts[1].copy()
+    hinge0 = 7 if free else 0
+    ps["qpos"][0, hinge0 + 3] = np.nan                       # a joint angle
+    ps["qvel"][1, m.nv - 1] = np.nan                         # a leaf joint velocity
+    if free:
+        ps["qpos"][2, 4] = np.nan                            # root quaternion component
+    if m.na:
+        ps["act"][3, 0] = np.nan                             # actuator activation
+    a1[4, 1] = np.nan                                        # the action itself (data.ctrl is part of the flattened Data)
+    ps["qacc_warmstart"][5, 2] = np.nan                      # warm start only: `warm.cost < smooth.cost` is False -> qacc_smooth, no NaN survives
+    poisoned = np.zeros(N, bool); poisoned[[0, 1, 4]] = True
+    if free: poisoned[2] = True
+    if m.na: poisoned[3] = True
+    s["pipeline_state"] = ps
+    st = state_from_oracle(ps, N)
+    out = backend.new_outputs(N)
+    out["done"][:] = s["done"]; out["info_f"][:, 3] = s["info"]["steps"]
+    out["info_i"][:, 0] = s["info"]["cur_frame"]; out["info_i"][:, 1] = s["info"]["steps_taken_cur_frame"]
+    backend.step(st, out, first, first_obs, first_ii, a1)
+    with np.errstate(all="ignore"):
+        s = eo.step(s, a1)
+    assert (s["done"][poisoned] == 1).all(), "the oracle itself did not flag the poisoned environments"
+    assert np.array_equal(out["done"], s["done"]), (out["done"], s["done"])
+    assert s["done"][5] == 0 and np.isfinite(st["qpos"][5]).all()                 # NaN warm start alone is harmless
+    assert np.isfinite(out["reward"]).all() and np.isfinite(out["obs"]).all()
+    # nan_to_num(reward): a NaN reward reads 0 in both
+    np.testing.assert_array_equal(out["reward"][poisoned] == 0.0, s["reward"][poisoned] == 0.0)
+    assert (out["reward"][[0, 4]] == 0.0).all()               # joint / ctrl sums contain the NaN for certain
+    for k in ("qpos", "qvel", "act", "qacc_warmstart", "time", "xpos"):          # restored from the cached first state
+        assert np.array_equal(st[k][poisoned], first[k][poisoned]), k
+        assert np.isfinite(st[k]).all(), k
+    assert np.array_equal(out["obs"][poisoned], first_obs[poisoned])
+    assert np.array_equal(out["info_i"][poisoned, 0], first_ii[poisoned, 0])
+    live = s["done"] == 0
+    np.testing.assert_allclose(out["reward"][live], s["reward"][live], atol=2e-2 * max(_metric_scale(cfg, k) for k in FLOAT_METRICS))
+    # ---- the step after: every environment is clean again and tracks the oracle
+    st = state_from_oracle(s["pipeline_state"], N)
+    out["done"][:] = s["done"]; out["info_f"][:, 3] = s["info"]["steps"]
+    out["info_i"][:, 0] = s["info"]["cur_frame"]; out["info_i"][:, 1] = s["info"]["steps_taken_cur_frame"]
+    backend.step(st, out, first, first_obs, first_ii, acts[2])
+    s = eo.step(s, acts[2])
+    assert np.array_equal(out["done"], s["done"]) and np.array_equal(out["info_f"][:, 3], s["info"]["steps"])
+    assert (out["info_f"][poisoned, 3] == 1).all()            # episode counter restarted (custom_wrappers.py:55-58)
+    dq = np.abs(st["qpos"] - s["pipeline_state"]["qpos"])      # one control step in contact: bulk at fp32 rounding (check_teacher_forced has the distribution test)
+    assert np.median(dq) < 1e-5 and dq.max() < 2e-3, (np.median(dq), dq.max())
+    # ---- unwrapped: element-wise nan_to_num of the observation row and of the reward
+    ps = {k: np.array(v, copy=True) for k, v in s["pipeline_state"].items()}
+    ps["qvel"][0, 3] = np.nan; ps["qvel"][1, 5] = np.inf; ps["qvel"][2, 6] = -np.inf; ps["xpos"].reshape(N, -1)[3, 3 * 5 + 1] = np.nan
+    st = state_from_oracle(ps, N)
+    o2 = backend.new_outputs(N)
+    o2["info_i"][:, 0] = s["info"]["cur_frame"]; o2["info_i"][:, 1] = s["info"]["steps_taken_cur_frame"]
+    backend.reward_obs(st, o2, acts[2])
+    with np.errstate(all="ignore"):
+        ref = eo.reward_obs(dict(s), {k: np.asarray(v, np.float32) for k, v in ps.items()}, acts[2])
+    assert np.isfinite(o2["obs"]).all() and np.isfinite(o2["reward"]).all()
+    assert np.array_equal(o2["done"], ref["done"]) and o2["done"][0] == 1 and o2["done"][3] == 1 and o2["done"][1] == ref["done"][1]
+    fmax = np.finfo(np.float32).max
+    assert o2["obs"][0, m.nq + 3] == 0.0 and o2["obs"][1, m.nq + 5] == fmax and o2["obs"][2, m.nq + 6] == -fmax
+    np.testing.assert_allclose(o2["obs"], ref["obs"], atol=2e-5, rtol=1e-6)
+    return dict(poisoned=int(poisoned.sum()))
 
 
 def common_metric(name):

@@ -46,7 +46,7 @@ def test_error_path_without_gpu():
 
 
 def test_product_never_imports_the_oracle():
-    pkg = os.path.join(ROOT, "brax-tracking_b200")
+    pkg = os.path.join(ROOT, "brax_tracking_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
             if f.endswith((".py", ".h", ".cu", ".inc", ".cc")):

@@ -30,6 +30,19 @@ def test_teacher_forced_wrapped_step(rodent_emu):
     assert r["n_done"] > 0
 
 
+def test_late_clip_window_clamps(rodent_emu):
+    r = pc.check_late_clip(rodent_emu, "rodent", N=16, T=24)
+    assert r["n_live"] > 0
+
+
+def test_unwrapped_env_step_and_pipeline_init(rodent_emu):
+    pc.check_unwrapped_step(rodent_emu, "rodent", N=4, T=8)
+
+
+def test_nan_guard(rodent_emu):
+    pc.check_nan_guard(rodent_emu, "rodent")
+
+
 def test_physics_1_10_100(rodent_emu):
     pc.check_physics_1_10_100(rodent_emu, "rodent", N=4)
 
@@ -40,7 +53,7 @@ def test_fly_elliptic_cone(name):
     b = EmuBackend(common.setup(name)[3])
     pc.check_forward_intermediates(b, name, N=4)
     pc.check_reset(b, name, N=8)
-    pc.check_physics_1_10_100(b, name, N=4)
+    pc.check_physics_1_10_100(b, name, N=16)      # medians over environments: 4 are too few for a chaotic free fall
     bt = EmuBackend(common.setup(name, FLY_EPISODE)[3])
     r = pc.check_teacher_forced(bt, name, N=8, T=30, episode_length=FLY_EPISODE)
     assert r["n_done"] > 0

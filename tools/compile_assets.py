@@ -1,4 +1,4 @@
-"""Generating script for brax-tracking_b200/assets/*.npz: compiles the reference's MJCF assets with the
+"""Generating script for brax_tracking_b200/assets/*.npz: compiles the reference's MJCF assets with the
 in-repo mini-compiler (mjcf.py), with exactly the options the reference env constructors apply
 (/root/reference/envs/rodent.py:51-73, /root/reference/envs/fruitfly.py:380-413).  Needs the reference checkout."""
 import os
@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from brax_tracking_b200 import assets, mjcf  # noqa: E402
 
 REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
-OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "brax-tracking_b200", "assets")
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "brax_tracking_b200", "assets")
 OPT = dict(iterations=4, ls_iterations=4)  # configs/dataset/*.yaml env_args
 
 rodent = mjcf.compile_mjcf(os.path.join(REF, "assets/rodent.xml"), scale_factor=0.9, overrides=OPT)

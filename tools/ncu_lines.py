@@ -45,7 +45,7 @@ srcs = {}
 for (k, v) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
     if k and k[0] not in srcs:
         try:
-            srcs[k[0]] = open("/root/repo/brax-tracking_b200/csrc/" + k[0]).read().splitlines()
+            srcs[k[0]] = open("/root/repo/brax_tracking_b200/csrc/" + k[0]).read().splitlines()
         except Exception:
             srcs[k[0]] = []
     text = srcs[k[0]][k[1] - 1].strip()[:90] if k and len(srcs.get(k[0], [])) >= k[1] else ""

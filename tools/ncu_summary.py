@@ -15,7 +15,7 @@ tag = sys.argv[1]
 model = sys.argv[2] if len(sys.argv) > 2 else "rodent"
 variant = sys.argv[3] if len(sys.argv) > 3 else "3_1"
 rep = os.path.join(ROOT, "gpurun_out", f"prof_{tag}.ncu-rep")
-obj = os.path.join(ROOT, "brax-tracking_b200", "build", f"tu_step_{variant}.o")
+obj = os.path.join(ROOT, "brax_tracking_b200", "build", f"tu_step_{variant}.o")
 tmp = "/tmp/bt_cubin"
 os.makedirs(tmp, exist_ok=True)
 subprocess.run(["cuobjdump", "-xelf", "all", obj], cwd=tmp, check=True, capture_output=True)

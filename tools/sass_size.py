@@ -1,7 +1,7 @@
 """Static SASS instruction count per inlined source function (needs -lineinfo): python tools/sass_size.py <cubin>"""
 import collections, re, subprocess, sys
 dis = subprocess.run(["nvdisasm", "-g", "-c", sys.argv[1]], capture_output=True, text=True).stdout
-impl = open("/root/repo/brax-tracking_b200/csrc/bt_impl.h").read().splitlines()
+impl = open("/root/repo/brax_tracking_b200/csrc/bt_impl.h").read().splitlines()
 funcs = []
 for n, l in enumerate(impl, 1):
     mm = re.match(r"  (?:static )?(?:template <[^>]*>\s*)?BT_DEV\s+[\w:<>\*&\s]+?\s+(\w+)\(", l)
