@@ -59,6 +59,25 @@ struct BtModel {
     }                                                                                           \
   } while (0)
 
+// Every entry point that touches the GPU runs with the model's device current and restores the caller's device on exit
+// (the stream handed in must belong to that device; cudaErrorInvalidResourceHandle otherwise, reported by BT_LAUNCHED).
+struct BtDeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  cudaError_t err = cudaSuccess;
+  explicit BtDeviceGuard(int device) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != device) { err = cudaSetDevice(device); switched = err == cudaSuccess; }
+  }
+  ~BtDeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+#define BT_ON_DEVICE(m)                                                                                          \
+  BtDeviceGuard guard_((m)->device);                                                                             \
+  if (guard_.err != cudaSuccess) {                                                                               \
+    snprintf(g_err, sizeof(g_err), "cudaSetDevice(%d) failed: %s", (m)->device, cudaGetErrorString(guard_.err)); \
+    return BT_E_CUDA;                                                                                            \
+  }
+
 static inline BtLaunchCfg cfg_for(const BtModel* m, int n_envs, void* stream) {
   int ctas = (n_envs + m->warps - 1) / m->warps;
   if (ctas > m->max_ctas) ctas = m->max_ctas;
@@ -81,7 +100,8 @@ int64_t bt_launch_count(void) { return g_launches.load(); }
 int bt_model_create(int n, const char* const* names, const void* const* data, const int64_t* counts, const int* is_float,
                     int device, BtModel** out) {
   if (!names || !data || !counts || !is_float || !out || n <= 0) { snprintf(g_err, sizeof(g_err), "null argument"); return BT_E_ARG; }
-  BT_CUDA(cudaSetDevice(device));
+  BtDeviceGuard guard(device);
+  if (guard.err != cudaSuccess) { snprintf(g_err, sizeof(g_err), "cudaSetDevice(%d) failed: %s", device, cudaGetErrorString(guard.err)); return BT_E_CUDA; }
   // one blob, every table 256-byte aligned
   std::vector<size_t> off(n);
   size_t total = 0;
@@ -92,32 +112,35 @@ int bt_model_create(int n, const char* const* names, const void* const* data, co
   }
   std::vector<char> host(total, 0);
   for (int i = 0; i < n; i++) memcpy(host.data() + off[i], data[i], (size_t)counts[i] * 4);
-  void* blob = nullptr;
-  BT_CUDA(cudaMalloc(&blob, total));
-  cudaError_t e = cudaMemcpy(blob, host.data(), total, cudaMemcpyHostToDevice);
-  if (e != cudaSuccess) { cudaFree(blob); snprintf(g_err, sizeof(g_err), "upload failed: %s", cudaGetErrorString(e)); return BT_E_CUDA; }
-  std::vector<const void*> bound(n);
-  for (int i = 0; i < n; i++) bound[i] = (const char*)blob + off[i];
   BtModel* m = new BtModel();
-  m->blob = blob;
+  m->blob = nullptr;
   m->device = device;
-  if (bt_bind(&m->dev, n, names, data, bound.data(), counts, is_float, g_err, sizeof(g_err))) { cudaFree(blob); delete m; return BT_E_ARG; }
+  // every error path below goes through fail(): frees the blob and the handle (the guard restores the caller's device)
+  auto fail = [&](int code) { if (m->blob) cudaFree(m->blob); delete m; return code; };
+  cudaError_t e = cudaMalloc(&m->blob, total);
+  if (e != cudaSuccess) { m->blob = nullptr; snprintf(g_err, sizeof(g_err), "cudaMalloc(%zu) failed: %s", total, cudaGetErrorString(e)); return fail(BT_E_CUDA); }
+  e = cudaMemcpy(m->blob, host.data(), total, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { snprintf(g_err, sizeof(g_err), "upload failed: %s", cudaGetErrorString(e)); return fail(BT_E_CUDA); }
+  std::vector<const void*> bound(n);
+  for (int i = 0; i < n; i++) bound[i] = (const char*)m->blob + off[i];
+  if (bt_bind(&m->dev, n, names, data, bound.data(), counts, is_float, g_err, sizeof(g_err))) return fail(BT_E_ARG);
   const int need_ds = (m->dev.nv + 31) / 32, need_cs = m->dev.ncon > 0 ? (m->dev.ncon + 31) / 32 : 1;
   m->ops = nullptr;
   for (const BtVariantOps& v : kVariants)
     if (v.ds >= need_ds && v.cs >= need_cs) { m->ops = &v; break; }
   if (!m->ops) {
     snprintf(g_err, sizeof(g_err), "model (nv=%d, ncon=%d) exceeds the compiled kernel variants", m->dev.nv, m->dev.ncon);
-    cudaFree(blob); delete m; return BT_E_UNSUPPORTED;
+    return fail(BT_E_UNSUPPORTED);
   }
   cudaDeviceProp prop;
-  BT_CUDA(cudaGetDeviceProperties(&prop, device));
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) { snprintf(g_err, sizeof(g_err), "cudaGetDeviceProperties failed: %s", cudaGetErrorString(e)); return fail(BT_E_CUDA); }
   const size_t per_env = (size_t)m->dev.smem_floats * 4;
   int warps = (int)(prop.sharedMemPerBlockOptin / per_env);
   if (warps > m->ops->max_warps) warps = m->ops->max_warps;
   if (warps < 1) {
     snprintf(g_err, sizeof(g_err), "per-environment scratch (%zu B) exceeds shared memory", per_env);
-    cudaFree(blob); delete m; return BT_E_UNSUPPORTED;
+    return fail(BT_E_UNSUPPORTED);
   }
   if (const char* w = getenv("BT_WARPS")) { int v = atoi(w); if (v >= 1 && v <= warps) warps = v; }
   m->warps = warps;
@@ -132,7 +155,7 @@ int bt_model_create(int n, const char* const* names, const void* const* data, co
     if (pe == cudaSuccess) pe = o->prepare_debug(m->smem_bytes);
     if (pe != cudaSuccess) {
       snprintf(g_err, sizeof(g_err), "cudaFuncSetAttribute(%d B dynamic smem) failed: %s", m->smem_bytes, cudaGetErrorString(pe));
-      cudaFree(blob); delete m; return BT_E_CUDA;
+      return fail(BT_E_CUDA);
     }
   }
   *out = m;
@@ -141,6 +164,7 @@ int bt_model_create(int n, const char* const* names, const void* const* data, co
 
 void bt_model_destroy(BtModel* m) {
   if (!m) return;
+  BtDeviceGuard guard(m->device);
   cudaFree(m->blob);
   delete m;
 }
@@ -171,6 +195,7 @@ int bt_reset(BtModel* m, int n_envs, const uint32_t* keys, int fixed_start_frame
   if (!m || n_envs < 0 || !keys || !obs || !reward || !done || !metrics || !info_f || !info_i) { snprintf(g_err, sizeof(g_err), "bad argument"); return BT_E_ARG; }
   if (check_state(m, state, true)) return BT_E_ARG;
   if (n_envs == 0) return BT_OK;
+  BT_ON_DEVICE(m);
   if (fixed_start_frame >= m->dev.clip_len) { snprintf(g_err, sizeof(g_err), "fixed_start_frame beyond the clip"); return BT_E_ARG; }
   BtResetArgs a = {keys, fixed_start_frame, state, obs, reward, done, metrics, info_f, info_i};
   m->ops->reset(cfg_for(m, n_envs, stream), m->dev, n_envs, m->warps, a);
@@ -187,6 +212,7 @@ int bt_step(BtModel* m, int n_envs, const float* action, BtStatePtrs state, BtSt
   }
   if (check_state(m, state, true) || check_state(m, first, true)) return BT_E_ARG;
   if (n_envs == 0) return BT_OK;
+  BT_ON_DEVICE(m);
   BtStepArgs a = {action, state, first, first_obs, first_info_i, obs, reward, done, metrics, info_f, info_i};
   m->ops->step(cfg_for(m, n_envs, stream), m->dev, n_envs, m->warps, a);
   BT_LAUNCHED();
@@ -197,6 +223,7 @@ int bt_physics_step(BtModel* m, int n_envs, const float* ctrl, BtStatePtrs state
   if (!m || n_envs < 0 || n_substeps < 1 || (m->dev.nu > 0 && !ctrl)) { snprintf(g_err, sizeof(g_err), "bad argument"); return BT_E_ARG; }
   if (check_state(m, state, false)) return BT_E_ARG;
   if (n_envs == 0) return BT_OK;
+  BT_ON_DEVICE(m);
   m->ops->physics(cfg_for(m, n_envs, stream), m->dev, n_envs, m->warps, ctrl, state, n_substeps);
   BT_LAUNCHED();
   return BT_OK;
@@ -206,6 +233,7 @@ int bt_pipeline_init(BtModel* m, int n_envs, BtStatePtrs state, void* stream) {
   if (!m || n_envs < 0) { snprintf(g_err, sizeof(g_err), "bad argument"); return BT_E_ARG; }
   if (check_state(m, state, false)) return BT_E_ARG;
   if (n_envs == 0) return BT_OK;
+  BT_ON_DEVICE(m);
   m->ops->physics(cfg_for(m, n_envs, stream), m->dev, n_envs, m->warps, nullptr, state, 0);
   BT_LAUNCHED();
   return BT_OK;
@@ -216,6 +244,7 @@ int bt_reward_obs(BtModel* m, int n_envs, const float* action, BtStatePtrs state
   if (!m || n_envs < 0 || !action || !info_i || !obs || !reward || !done || !metrics || !info_f) { snprintf(g_err, sizeof(g_err), "bad argument"); return BT_E_ARG; }
   if (check_state(m, state, true)) return BT_E_ARG;
   if (n_envs == 0) return BT_OK;
+  BT_ON_DEVICE(m);
   BtRewardArgs a = {action, state, info_i, obs, reward, done, metrics, info_f};
   m->ops->reward(cfg_for(m, n_envs, stream), m->dev, n_envs, m->warps, a);
   BT_LAUNCHED();
@@ -227,6 +256,7 @@ int bt_forward_debug(BtModel* m, int n_envs, const float* ctrl, BtStatePtrs stat
   if (!m || n_envs < 0 || !scratch || !cdist || !niter) { snprintf(g_err, sizeof(g_err), "bad argument"); return BT_E_ARG; }
   if (check_state(m, state, false)) return BT_E_ARG;
   if (n_envs == 0) return BT_OK;
+  BT_ON_DEVICE(m);
   m->ops->debug(cfg_for(m, n_envs, stream), m->dev, n_envs, m->warps, ctrl, state, stop, scratch, cdist, niter);
   BT_LAUNCHED();
   return BT_OK;

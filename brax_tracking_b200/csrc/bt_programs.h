@@ -124,8 +124,9 @@ BT_DEV void bt_prog_reset(const BtDev& m, float* s, int lane, int env, bool live
   for (int i = lane; i < m.nq; i += G) {
     float q0 = BT_LDG(m.qpos0 + i);
     if (m.seed_root_from_clip && a.fixed_start_frame < 0) {  // the render-rollout reset starts from qpos0 (custom_wrappers.py:99-103)
-      if (i < 2) q0 = BT_LDG(m.clip_position + 3 * start + i);
-      else if (i >= 3 && i < 7) q0 = BT_LDG(m.clip_quaternion + 4 * start + i - 3);
+      const int fs = start > m.clip_len - 1 ? m.clip_len - 1 : start;  // JAX gather clamps (a clip shorter than the start-frame range)
+      if (i < 2) q0 = BT_LDG(m.clip_position + 3 * fs + i);
+      else if (i >= 3 && i < 7) q0 = BT_LDG(m.clip_quaternion + 4 * fs + i - 3);
     }
     E.qpos()[i] = q0 + bt_bits_to_uniform(bt_random_bits(sk[2], sk[3], i, m.nq), lo, hi);
   }

@@ -224,8 +224,8 @@ class Oracle:
                     d.act[:na] = out["act"][e]
                 d.qacc_warmstart[:] = out["qacc_warmstart"][e]
                 d.time[0] = out["time"][e]
-                if nu and ctrl is not None:
-                    d.ctrl[:nu] = ctrl[e]
+                if nu:   # pipeline_init runs mjx.forward on a fresh mjx.make_data: ctrl = 0 (the pooled buffers keep the last call's)
+                    d.ctrl[:nu] = ctrl[e] if ctrl is not None else 0
                 if forward_only:
                     self.lib.o_forward(C.byref(self.om.struct), C.byref(d.struct))
                 else:

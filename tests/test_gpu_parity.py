@@ -27,6 +27,86 @@ def test_teacher_forced_wrapped_step_100(rodent_cuda):
     print(r)
 
 
+def test_late_clip_window_clamps(rodent_cuda):
+    """`cur_frame + 1` window clamp of _get_obs (fruitfly.py:602-611) and the clip[cur_frame] gather clamp, past the clip end."""
+    print(pc.check_late_clip(rodent_cuda, "rodent", N=16, T=24))
+
+
+def test_nan_guard(rodent_cuda):
+    """fruitfly.py:569-577: NaN in qpos / qvel / act / action => done, finite reward / obs, restore from the cached first state."""
+    print(pc.check_nan_guard(rodent_cuda, "rodent"))
+
+
+def test_unwrapped_env_step_and_pipeline_init(rodent_cuda):
+    """bt_pipeline_init, bt_physics_step + bt_reward_obs (the bare env.step, fruitfly.py:497-596) against the oracle."""
+    print(pc.check_unwrapped_step(rodent_cuda, "rodent", N=8, T=12))
+
+
+def test_env_classes_against_the_oracle():
+    """The host-side mirror of the reference classes on CUDA: TrackingEnv.reset / .step / .pipeline_init,
+    RenderRolloutWrapperTracking (custom_wrappers.py:82-125) and ppo.evaluate_rollout (main.py:136-258) traces."""
+    import torch
+    from brax_tracking_b200 import envs, native, ppo
+    m, cfg, clip, _ = common.setup("rodent")
+    _, eo = common.oracles("rodent")
+    n, T = 8, 10
+    keys = common.jax_keys(n, seed=31)
+    acts = common.actions(T, n, m.nu, seed=32, scale=0.3)
+    env = envs.RodentSingleClip(clip, mj_model=m)
+    # ---- bare env: reset draws the training start frames; step = pipeline_step + reward / obs, no wrappers
+    s = eo.reset(keys)
+    state = env.reset(keys)
+    assert np.array_equal(state.info["cur_frame"].cpu().numpy(), s["info"]["cur_frame"])
+    np.testing.assert_allclose(state.obs.cpu().numpy(), s["obs"], atol=2e-5)
+    assert "steps" not in state.info and "first_obs" not in state.info            # those belong to the wrappers
+    for t in range(3):
+        # teacher forcing: the oracle's state goes in, one env.step comes out
+        for k in native.STATE_FIELDS:
+            state.pipeline_state[k].copy_(torch.from_numpy(np.asarray(s["pipeline_state"][k], np.float32).reshape(state.pipeline_state[k].shape)))
+        state._raw["info_i"][:, 0].copy_(torch.from_numpy(s["info"]["cur_frame"])); state._raw["info_i"][:, 1].copy_(torch.from_numpy(s["info"]["steps_taken_cur_frame"]))
+        state = env.step(state, torch.from_numpy(acts[t]).cuda())
+        # the oracle's env layer on the product's own post-step physics state: fp32 rounding level (parity_cases.check_teacher_forced)
+        over = {k: state.pipeline_state[k].cpu().numpy() for k in native.STATE_FIELDS}
+        over["xpos"] = over["xpos"].reshape(n, m.nbody, 3)
+        chk = eo.reward_obs(s, over, acts[t])
+        s = eo.env_step(s, acts[t])
+        assert np.array_equal(state.done.cpu().numpy(), s["done"])
+        assert np.array_equal(state.info["cur_frame"].cpu().numpy(), s["info"]["cur_frame"])
+        np.testing.assert_allclose(state.obs.cpu().numpy(), chk["obs"], atol=2e-5, rtol=1e-6)
+        np.testing.assert_allclose(state.reward.cpu().numpy(), chk["reward"], atol=1e-4)
+        for k in pc.FLOAT_METRICS:
+            np.testing.assert_allclose(state.metrics[k].cpu().numpy(), chk["metrics"][k], atol=1e-4, err_msg=k)
+        for k in pc.INFO_FLOATS:
+            np.testing.assert_allclose(state.info[k].cpu().numpy(), chk["info"][k], atol=1e-5, rtol=1e-4, err_msg=k)
+        assert np.median(np.abs(state.obs.cpu().numpy() - s["obs"])) < 1e-4      # and the bulk against the oracle's own physics
+        np.testing.assert_allclose(state.reward.cpu().numpy(), s["reward"], atol=2e-2)
+    # ---- pipeline_init (fruitfly.py:477)
+    ps = env.pipeline_init(torch.from_numpy(np.asarray(s["pipeline_state"]["qpos"], np.float32)).cuda(),
+                           torch.from_numpy(np.asarray(s["pipeline_state"]["qvel"], np.float32)).cuda())
+    o64, _ = common.oracles("rodent")
+    fwd = o64.pipeline_batch(dict(s["pipeline_state"], act=np.zeros_like(s["pipeline_state"]["act"]),
+                                  qacc_warmstart=np.zeros_like(s["pipeline_state"]["qacc_warmstart"])), None, 0, forward_only=True)
+    np.testing.assert_allclose(ps["xpos"].cpu().numpy(), np.asarray(fwd["xpos"]).reshape(n, -1), atol=2e-6)
+    # ---- render-rollout wrapper: frame 0, split(rng, 3), qpos0 + noise, bare steps
+    renv = envs.RenderRolloutWrapperTracking(env)
+    rs = renv.reset(keys)
+    s0 = eo.reset(keys, fixed_start_frame=0)
+    assert not rs.info["cur_frame"].any().item()
+    assert np.array_equal(rs.pipeline_state["qvel"].cpu().numpy(), s0["pipeline_state"]["qvel"])
+    np.testing.assert_allclose(rs.obs.cpu().numpy(), s0["obs"], atol=2e-5)
+    # ---- evaluation rollout traces with an open-loop "policy" (free-running: the first steps stay within the 1-step bounds)
+    it = iter(range(T))
+    tr = ppo.evaluate_rollout(env, lambda obs: (torch.from_numpy(acts[next(it)]).cuda(),), keys, num_steps=T)
+    so, ref_rew, ref_cur, ref_h = s0, [], [], []
+    for t in range(T):
+        so = eo.env_step(so, acts[t])
+        ref_rew.append(so["reward"]); ref_cur.append(so["info"]["cur_frame"]); ref_h.append(so["pipeline_state"]["xpos"][:, cfg["torso_idx"], 2])
+    assert np.array_equal(tr["cur_frame"], np.array(ref_cur))                      # frame index trace: exact, all steps
+    np.testing.assert_allclose(tr["reward"][:2], np.array(ref_rew)[:2], atol=2e-2)
+    np.testing.assert_allclose(tr["torso_height"][:2], np.array(ref_h)[:2], atol=1e-4)
+    assert np.isfinite(tr["reward"]).all() and tr["pos_reward"].shape == (T, n)
+
+
 def test_physics_1_10_100(rodent_cuda):
     print(pc.check_physics_1_10_100(rodent_cuda, "rodent", N=8))
 
@@ -38,9 +118,13 @@ def test_fly_elliptic_cone(name):
     b = CudaBackend(common.setup(name)[3])
     pc.check_forward_intermediates(b, name, N=16)
     pc.check_reset(b, name, N=64)
-    pc.check_physics_1_10_100(b, name, N=8)
+    print(pc.check_physics_1_10_100(b, name, N=16))
+    pc.check_unwrapped_step(b, name, N=8, T=8)
+    pc.check_nan_guard(b, name)
     bt = CudaBackend(common.setup(name, 12)[3])
     print(pc.check_teacher_forced(bt, name, N=16, T=40, episode_length=12))
+    if name == "fly_tethered":   # (the free fly is not seeded from the clip: at a late start frame it is `too_far` at every step)
+        print(pc.check_late_clip(bt, name, N=16, T=24, episode_length=12))
 
 
 @pytest.mark.parametrize("name", ["rodent", "fly_free", "fly_tethered"])
