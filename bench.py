@@ -32,9 +32,9 @@ UNIT = "env-steps/s"
 # algorithmic HBM bytes per env-step (SURVEY.md section 8d / BASELINE.md section 2):
 #   read  qpos + qvel + act + qacc_warmstart + time + action + 2 ints
 #   write qpos + qvel + act + qacc_warmstart + time + obs + reward, done + 12 metrics + 3 info floats + 2 info ints
-ALGO_BYTES = dict(rodent=4776, fly_free=6472, fly_tethered=6128, rodent_pair=7580)
+ALGO_BYTES = dict(rodent=4776, fly_free=6472, fly_tethered=6128, rodent_pair=9268)
 MODEL_XML = dict(rodent="rodent", fly_free="fruitfly_force_fast (free root)", fly_tethered="fruitfly_force_fast (tethered)",
-                 rodent_pair="2 x rodent in one world")
+                 rodent_pair="rodent_pair")
 
 
 def algo_bytes(nq, nv, na, nu, obs):

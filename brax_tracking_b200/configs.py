@@ -40,6 +40,21 @@ RODENT_ENV_ARGS = dict(
 )
 
 
+# BASELINE.json configs[3]: assets/rodent_pair.xml (two replicas of the animal in one world) with the rodent env semantics per
+# animal; SURVEY.md Appendix C.3 variant (i), DESIGN.md "config 4".  `inter_animal_pairs`: the opened capsule-capsule pairs
+# (geom names without the `_collision-k` suffix; animal 0's geom first) -- declared deviation: the file as committed lets the
+# animals collide with the floor only (rodent_pair.xml:31-40).
+_FORE, _HIND = ("humerus_L", "humerus_R"), ("upper_leg_L0", "upper_leg_R0")
+RODENT_PAIR_ENV_ARGS = dict(
+    RODENT_ENV_ARGS, animal_suffixes=["-0", "-1"],
+    inter_animal_pairs=([(a, b) for a in _FORE for b in _FORE] + [(a, b) for a in _HIND for b in _HIND]
+                        + [(_FORE[i], _HIND[i]) for i in range(2)] + [(_HIND[i], _FORE[i]) for i in range(2)]))
+
+
+def pair_geom_names(env_args):
+    return [(f"{a}_collision-0", f"{b}_collision-1") for a, b in env_args["inter_animal_pairs"]]
+
+
 def _fly_names():
     bodies = ["thorax", "head", "rostrum", "haustellum", "labrum_left", "labrum_right", "antenna_left", "antenna_right",
               "wing_left", "wing_right", "abdomen"] + [f"abdomen_{k}" for k in range(2, 8)] + ["haltere_left", "haltere_right"]
@@ -87,8 +102,35 @@ def resolve(m: mjcf.Model, env_args: dict) -> Dict:
     cfg["steps_for_cur_frame"] = steps_for_cur_frame
     # main.py:86
     cfg["episode_length"] = int((env_args["clip_length"] - 50 - env_args["ref_traj_length"]) * steps_for_cur_frame)
-    cfg["torso_idx"] = m.name2id("body", env_args["center_of_mass"])
-    cfg["joint_idxs"] = [m.name2id("joint", n) for n in env_args["joint_names"]]
-    cfg["body_idxs"] = [m.name2id("body", n) for n in env_args["body_names"]]
-    cfg["endeff_idxs"] = [m.name2id("body", n) for n in env_args["end_eff_names"]]
+    # one record per tracked animal = per free root (the tethered fly: one pseudo-animal spanning all of qpos).  Every reference
+    # env has exactly one; the two-rodent model of BASELINE.json configs[3] has two, whose names carry the replicate suffixes
+    # of assets/rodent_pair.xml:163 (`-0`, `-1`).  Joint ids are taken relative to the animal's root joint, so that each animal
+    # reproduces the single-animal indexing, quirks included (ids used as columns of `qpos[7:]`).
+    roots = [j for j in range(m.njnt) if m.jnt_type[j] == mjcf.JNT_FREE] if env_args["free_jnt"] else []
+    suffixes = env_args.get("animal_suffixes") or [""]
+    if roots and len(suffixes) != len(roots):
+        raise ValueError(f"the model has {len(roots)} free roots but the env names {len(suffixes)} animals")
+    animals, jbase = [], 0
+    for k, sfx in enumerate(suffixes):
+        if roots:
+            j0 = roots[k]
+            j1 = roots[k + 1] if k + 1 < len(roots) else m.njnt
+            qadr, dadr, nj = int(m.jnt_qposadr[j0]), int(m.jnt_dofadr[j0]), j1 - j0 - 1
+            if any(m.jnt_type[j] != mjcf.JNT_HINGE for j in range(j0 + 1, j1)):
+                raise NotImplementedError("animals are a free root followed by hinges")
+        else:
+            j0, qadr, dadr, nj = 0, 0, 0, m.nq
+
+        def jid(n):
+            i = m.name2id("joint", n + sfx)
+            return i - j0 if i >= 0 else -1
+        animals.append(dict(
+            qadr=qadr, dadr=dadr, nj=nj, jbase=jbase, torso_idx=m.name2id("body", env_args["center_of_mass"] + sfx),
+            joint_idxs=[jid(n) for n in env_args["joint_names"]],
+            body_idxs=[m.name2id("body", n + sfx) for n in env_args["body_names"]],
+            endeff_idxs=[m.name2id("body", n + sfx) for n in env_args["end_eff_names"]]))
+        jbase += nj
+    cfg["animals"] = animals
+    for k in ("torso_idx", "joint_idxs", "body_idxs", "endeff_idxs"):   # the env attributes other layers read: animal 0's
+        cfg[k] = animals[0][k]
     return cfg

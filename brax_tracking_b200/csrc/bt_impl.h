@@ -190,8 +190,8 @@ struct BtEnv {
   BT_DEV float* ctop(int c) const { return pvec() + 8 * c; }
   // T-region views during the constraint phase
   BT_DEV float* congeo() const { return T(); }                          // [ncon][12] off(3) frame(9)
-  BT_DEV float* wrench() const { return T() + 12 * m.ncon; }            // [ncon][6]
-  BT_DEV float* cbA() const { return T() + 18 * m.ncon; }               // [ncb][6]
+  BT_DEV float* wrench() const { return s + m.o_wrench; }               // [ncon + ncross][6]; over Dd | cbJ when they fit (model.py)
+  BT_DEV float* cbA() const { return s + m.o_cbA; }                     // [ncb][6]
 
   // ================================================================== P1: forward tree pass
   // (MJX: smooth.kinematics, com_pos, com_vel, rne forward half, passive fluid), in five parts so that
@@ -992,14 +992,28 @@ struct BtEnv {
       out[sl][0] = out[sl][1] = out[sl][2] = 0.f;
       if (c >= m.ncon) continue;
       const int cb1 = BT_LDG(m.con_cb1 + c), cb2 = BT_LDG(m.con_cb2 + c);
-      float A[6] = {0, 0, 0, 0, 0, 0};
-      if (cb2 >= 0) for (int k = 0; k < 6; k++) A[k] += cbs[6 * cb2 + k];
-      if (cb1 >= 0) for (int k = 0; k < 6; k++) A[k] -= cbs[6 * cb1 + k];
       float cg[12];  // contact record (offset 3, frame 9): three 128-bit loads (scalar loads at stride 12 are 4-way conflicts)
       bt_ld12(congeo() + 12 * c, cg);
       float w[3];
-      bt_cross(A, cg, w);
-      w[0] += A[3]; w[1] += A[4]; w[2] += A[5];
+      const int xr = m.ncross > 0 ? BT_LDG(m.con_xref + c) : -1;
+      if (xr >= 0) {
+        // contact between two kinematic trees: each chain sum is about its own tree's reference point, so the point velocity
+        // of body 1 uses the offset from ITS reference: off1 = off + ref[tree of body 2] - ref[tree of body 1]
+        const int r2 = BT_LDG(m.con_ref + c);
+        const float off1[3] = {cg[0] + (ref()[3 * r2] - ref()[3 * xr]), cg[1] + (ref()[3 * r2 + 1] - ref()[3 * xr + 1]),
+                               cg[2] + (ref()[3 * r2 + 2] - ref()[3 * xr + 2])};
+        float w1[3];
+        bt_cross(cbs + 6 * cb2, cg, w);
+        bt_cross(cbs + 6 * cb1, off1, w1);
+#pragma unroll
+        for (int k = 0; k < 3; k++) w[k] = (w[k] + cbs[6 * cb2 + 3 + k]) - (w1[k] + cbs[6 * cb1 + 3 + k]);
+      } else {
+        float A[6] = {0, 0, 0, 0, 0, 0};
+        if (cb2 >= 0) for (int k = 0; k < 6; k++) A[k] += cbs[6 * cb2 + k];
+        if (cb1 >= 0) for (int k = 0; k < 6; k++) A[k] -= cbs[6 * cb1 + k];
+        bt_cross(A, cg, w);
+        w[0] += A[3]; w[1] += A[4]; w[2] += A[5];
+      }
       out[sl][0] = bt_dot3(cg + 3, w); out[sl][1] = bt_dot3(cg + 6, w); out[sl][2] = bt_dot3(cg + 9, w);
     }
   }
@@ -1199,6 +1213,20 @@ struct BtEnv {
       bt_cross(cg, F, tq);
       float* w = wrench() + 6 * c;
       w[0] = tq[0]; w[1] = tq[1]; w[2] = tq[2]; w[3] = F[0]; w[4] = F[1]; w[5] = F[2];
+      if (m.ncross > 0) {
+        const int xr = BT_LDG(m.con_xref + c);
+        if (xr >= 0) {
+          // the same force on body 1's tree, as a wrench about THAT tree's reference point, in the contact's second slot
+          // (model.py: con_xslot; the contact-body sums of body 1 read it with a minus sign)
+          const int r2 = BT_LDG(m.con_ref + c);
+          const float off1[3] = {cg[0] + (ref()[3 * r2] - ref()[3 * xr]), cg[1] + (ref()[3 * r2 + 1] - ref()[3 * xr + 1]),
+                                 cg[2] + (ref()[3 * r2 + 2] - ref()[3 * xr + 2])};
+          float t1[3];
+          bt_cross(off1, F, t1);
+          float* w1 = wrench() + 6 * BT_LDG(m.con_xslot + c);
+          w1[0] = t1[0]; w1[1] = t1[1]; w1[2] = t1[2]; w1[3] = F[0]; w1[4] = F[1]; w1[5] = F[2];
+        }
+      }
     }
     W::sync();
     // wrench per contact BODY (8 for the rodent instead of 30 contacts), then one gather per dof over the contact bodies
@@ -1647,6 +1675,15 @@ struct BtEnv {
     W::sync();
   }
 
+  // initcheck substitute (compute-sanitizer is closed on the pool): with the table scalar `poison` set, every program starts
+  // by filling its scratch slice with NaN, so a read of anything the program did not write itself shows up in the outputs
+  // (tests/test_gpu_parity.py::test_poisoned_scratch_and_scheduling_invariance requires bit-identical results)
+  BT_DEV void poison_scratch() {
+    if (!m.poison) return;
+    for (int i = lane; i < m.smem_floats; i += G) s[i] = NAN;
+    W::sync();
+  }
+
   // ================================================================== state I/O ([n_envs, dim] rows, coalesced per env)
   BT_DEV void load_state(const BtState& st, int env) {
     for (int i = lane; i < m.nq; i += G) qpos()[i] = st.qpos[(size_t)env * m.nq + i];
@@ -1665,49 +1702,64 @@ struct BtEnv {
   // ================================================================== env layer
   BT_DEV float* obsbuf() const { return s + m.o_crb; }  // staged observation row (crb/LD/T are dead by then)
 
-  // _get_obs (fruitfly.py:598-646 free root; :271-319 tethered) into obsbuf, nan_to_num applied
+  // per-animal constants of the env layer (model.py: animal_rec = qadr dadr nj jbase torso 0 0 0): one record per tracked
+  // free root.  Every reference env has ONE animal; the two-rodent stress model (BASELINE.json configs[3]) has two, each
+  // tracking its own copy of the clip (DESIGN.md "config 4").  The tethered fly is one animal with qadr = 0 and nj = nq.
+  struct Animal { int qadr, dadr, nj, jbase, torso; };
+  BT_DEV Animal animal(int a) const {
+    const int* r = m.animal_rec + 8 * a;
+    return Animal{BT_LDG(r), BT_LDG(r + 1), BT_LDG(r + 2), BT_LDG(r + 3), BT_LDG(r + 4)};
+  }
+
+  // _get_obs (fruitfly.py:598-646 free root; :271-319 tethered) into obsbuf, nan_to_num applied.
+  // Layout: qpos | qvel | per animal: track_pos_local (3 L) | quat_dist (4 L) | joint_dist (n_joint_idxs L) | body_pos_dist_local (3 n_body_idxs L)
   BT_DEV void build_obs(int cur_frame) {
     float* o = obsbuf();
-    const int L = m.ref_len, nq = m.nq, nv = m.nv;
+    const int L = m.ref_len, nq = m.nq, nv = m.nv, NA = m.n_animals;
     int start = cur_frame + 1;
     start = start < 0 ? 0 : (start > m.clip_len - L ? m.clip_len - L : start);  // dynamic_slice clamps the start
     for (int i = lane; i < nq; i += G) o[i] = bt_nan_to_num(qpos()[i]);
     for (int i = lane; i < nv; i += G) o[nq + i] = bt_nan_to_num(qvel()[i]);
     int base = nq + nv;
-    const float rq[4] = {qpos()[3], qpos()[4], qpos()[5], qpos()[6]};  // tethered quirk: four joint angles (fruitfly.py:305)
     const int nj = m.clip_nj;
-    if (m.free_jnt) {
-      for (int l = lane; l < L; l += G) {
-        const float* cp = m.clip_position + 3 * (start + l);
-        float d[3] = {BT_LDG(cp) - qpos()[0], BT_LDG(cp + 1) - qpos()[1], BT_LDG(cp + 2) - qpos()[2]}, r[3];
-        bt_rotate(d, rq, r);
-        o[base + 3 * l] = bt_nan_to_num(r[0]); o[base + 3 * l + 1] = bt_nan_to_num(r[1]); o[base + 3 * l + 2] = bt_nan_to_num(r[2]);
-        const float* cq = m.clip_quaternion + 4 * (start + l);
-        const float tq[4] = {BT_LDG(cq), BT_LDG(cq + 1), BT_LDG(cq + 2), BT_LDG(cq + 3)};
-        const float inv[4] = {rq[0], -rq[1], -rq[2], -rq[3]};
-        float rel[4];
-        bt_quat_mul(tq, inv, rel);  // relative_quat(q_root, q_ref) = q_ref * conj(q_root)
+    for (int a = 0; a < NA; a++) {
+      const Animal an = animal(a);
+      const float* qa = qpos() + an.qadr;
+      const float rq[4] = {qa[3], qa[4], qa[5], qa[6]};  // tethered quirk: four joint angles (fruitfly.py:305)
+      if (m.free_jnt) {
+        for (int l = lane; l < L; l += G) {
+          const float* cp = m.clip_position + 3 * ((start + l) * NA + a);
+          float d[3] = {BT_LDG(cp) - qa[0], BT_LDG(cp + 1) - qa[1], BT_LDG(cp + 2) - qa[2]}, r[3];
+          bt_rotate(d, rq, r);
+          o[base + 3 * l] = bt_nan_to_num(r[0]); o[base + 3 * l + 1] = bt_nan_to_num(r[1]); o[base + 3 * l + 2] = bt_nan_to_num(r[2]);
+          const float* cq = m.clip_quaternion + 4 * ((start + l) * NA + a);
+          const float tq[4] = {BT_LDG(cq), BT_LDG(cq + 1), BT_LDG(cq + 2), BT_LDG(cq + 3)};
+          const float inv[4] = {rq[0], -rq[1], -rq[2], -rq[3]};
+          float rel[4];
+          bt_quat_mul(tq, inv, rel);  // relative_quat(q_root, q_ref) = q_ref * conj(q_root)
 #pragma unroll
-        for (int k = 0; k < 4; k++) o[base + 3 * L + 4 * l + k] = bt_nan_to_num(rel[k]);
+          for (int k = 0; k < 4; k++) o[base + 3 * L + 4 * l + k] = bt_nan_to_num(rel[k]);
+        }
+        base += 7 * L;
       }
-      base += 7 * L;
-    }
-    const int qoff = m.free_jnt ? 7 : 0;
-    const int nji = m.n_joint_idxs;
-    for (int it = lane; it < L * nji; it += G) {
-      const int l = it / nji, k = it - l * nji;
-      const int col = BT_LDG(m.joint_idxs + k);
-      o[base + it] = bt_nan_to_num(BT_LDG(m.clip_joints + (size_t)(start + l) * nj + col) - qpos()[qoff + col]);
-    }
-    base += L * nji;
-    const int nbi = m.n_body_idxs;
-    for (int it = lane; it < L * nbi; it += G) {
-      const int l = it / nbi, k = it - l * nbi;
-      const int b = BT_LDG(m.body_idxs + k);
-      const float* cb = m.clip_body_positions + ((size_t)(start + l) * m.nbody + b) * 3;
-      float d[3] = {BT_LDG(cb) - xpos()[3 * b], BT_LDG(cb + 1) - xpos()[3 * b + 1], BT_LDG(cb + 2) - xpos()[3 * b + 2]}, r[3];
-      bt_rotate(d, rq, r);
-      o[base + 3 * it] = bt_nan_to_num(r[0]); o[base + 3 * it + 1] = bt_nan_to_num(r[1]); o[base + 3 * it + 2] = bt_nan_to_num(r[2]);
+      const int qoff = an.qadr + (m.free_jnt ? 7 : 0);
+      const int j0 = BT_LDG(m.jidx_adr + a), nji = BT_LDG(m.jidx_adr + a + 1) - j0;
+      for (int it = lane; it < L * nji; it += G) {
+        const int l = it / nji, k = it - l * nji;
+        const int col = BT_LDG(m.joint_idxs + j0 + k);
+        o[base + it] = bt_nan_to_num(BT_LDG(m.clip_joints + (size_t)(start + l) * nj + an.jbase + col) - qpos()[qoff + col]);
+      }
+      base += L * nji;
+      const int b0 = BT_LDG(m.bidx_adr + a), nbi = BT_LDG(m.bidx_adr + a + 1) - b0;
+      for (int it = lane; it < L * nbi; it += G) {
+        const int l = it / nbi, k = it - l * nbi;
+        const int b = BT_LDG(m.body_idxs + b0 + k);
+        const float* cb = m.clip_body_positions + ((size_t)(start + l) * m.nbody + b) * 3;
+        float d[3] = {BT_LDG(cb) - xpos()[3 * b], BT_LDG(cb + 1) - xpos()[3 * b + 1], BT_LDG(cb + 2) - xpos()[3 * b + 2]}, r[3];
+        bt_rotate(d, rq, r);
+        o[base + 3 * it] = bt_nan_to_num(r[0]); o[base + 3 * it + 1] = bt_nan_to_num(r[1]); o[base + 3 * it + 2] = bt_nan_to_num(r[2]);
+      }
+      base += 3 * L * nbi;
     }
     W::sync();
   }
@@ -1725,59 +1777,78 @@ struct BtEnv {
     stc = stc * (hit ? 0 : 1);
     r.cur_frame = cur; r.steps_taken = stc;
     const int fi = cur < 0 ? 0 : (cur > m.clip_len - 1 ? m.clip_len - 1 : cur);  // JAX gather clamps
-    float pd[3] = {0.f, 0.f, 0.f}, quat_d = 0.f, pos_r = 0.f, quat_r = 0.f;
-    const int qoff = m.free_jnt ? 7 : 0;
-    if (m.free_jnt) {
-      const float* cp = m.clip_position + 3 * fi;
-      pd[0] = qpos()[0] - BT_LDG(cp); pd[1] = qpos()[1] - BT_LDG(cp + 1); pd[2] = qpos()[2] - BT_LDG(cp + 2);
-      const float sp = (pd[0] + pd[1]) + pd[2];
-      pos_r = m.pos_reward_weight * expf(-400.f * (sp * sp));
-      const float* cq = m.clip_quaternion + 4 * fi;
-      float a[4] = {qpos()[3], qpos()[4], qpos()[5], qpos()[6]}, b[4] = {BT_LDG(cq), BT_LDG(cq + 1), BT_LDG(cq + 2), BT_LDG(cq + 3)};
-      const float na = sqrtf(a[0] * a[0] + a[1] * a[1] + a[2] * a[2] + a[3] * a[3]);
-      const float nb = sqrtf(b[0] * b[0] + b[1] * b[1] + b[2] * b[2] + b[3] * b[3]);
-      float dt = 0.f;
+    // Per-animal terms (fruitfly.py:514-552), combined over the animals of the model: reward terms ADD, termination flags and
+    // the three tracking distances take the MAX (any animal off its clip ends the episode).  With one animal (every
+    // reference env) this is the reference expression, operation for operation.
+    const int NA = m.n_animals;
+    float pos_r = 0.f, quat_r = 0.f, joint_r = 0.f, angvel_r = 0.f, bodypos_r = 0.f, endeff_r = 0.f, healthy_r = 0.f;
+    float too_far = 0.f, bad_pose = 0.f, bad_quat = 0.f, fall = 0.f, summed = 0.f, quat_d = 0.f, joint_d = 0.f;
+    for (int a = 0; a < NA; a++) {
+      const Animal an = animal(a);
+      const float* qa = qpos() + an.qadr;
+      float pd[3] = {0.f, 0.f, 0.f}, qd = 0.f, pr = 0.f, qr = 0.f;
+      const int qoff = an.qadr + (m.free_jnt ? 7 : 0);
+      if (m.free_jnt) {
+        const float* cp = m.clip_position + 3 * (fi * NA + a);
+        pd[0] = qa[0] - BT_LDG(cp); pd[1] = qa[1] - BT_LDG(cp + 1); pd[2] = qa[2] - BT_LDG(cp + 2);
+        const float sp = (pd[0] + pd[1]) + pd[2];
+        pr = m.pos_reward_weight * expf(-400.f * (sp * sp));
+        const float* cq = m.clip_quaternion + 4 * (fi * NA + a);
+        float qa4[4] = {qa[3], qa[4], qa[5], qa[6]}, b[4] = {BT_LDG(cq), BT_LDG(cq + 1), BT_LDG(cq + 2), BT_LDG(cq + 3)};
+        const float na = sqrtf(qa4[0] * qa4[0] + qa4[1] * qa4[1] + qa4[2] * qa4[2] + qa4[3] * qa4[3]);
+        const float nb = sqrtf(b[0] * b[0] + b[1] * b[1] + b[2] * b[2] + b[3] * b[3]);
+        float dt = 0.f;
 #pragma unroll
-      for (int k = 0; k < 4; k++) dt += (a[k] / na) * (b[k] / nb);
-      float dd = 2.f * dt * dt - 1.f;
-      dd = dd > 1.f ? 1.f : dd;
-      const float ang = 0.5f * acosf(dd);
-      quat_d = ang * ang;
-      quat_r = m.quat_reward_weight * expf(-4.0f * quat_d);
+        for (int k = 0; k < 4; k++) dt += (qa4[k] / na) * (b[k] / nb);
+        float dd = 2.f * dt * dt - 1.f;
+        dd = dd > 1.f ? 1.f : dd;
+        const float ang = 0.5f * acosf(dd);
+        qd = ang * ang;
+        qr = m.quat_reward_weight * expf(-4.0f * qd);
+      }
+      float js = 0.f;
+      for (int k = lane; k < an.nj; k += G) js += qpos()[qoff + k] - BT_LDG(m.clip_joints + (size_t)fi * m.clip_nj + an.jbase + k);
+      js = W::allsum(js);
+      const float jd = js * js;
+      const float* ca = m.clip_angular_velocity + 3 * (fi * NA + a);
+      const float* va = qvel() + an.dadr;
+      const float av = ((va[3] - BT_LDG(ca)) + (va[4] - BT_LDG(ca + 1))) + (va[5] - BT_LDG(ca + 2));
+      float bs = 0.f, es = 0.f;
+      for (int it = 3 * BT_LDG(m.bidx_adr + a) + lane, i1 = 3 * BT_LDG(m.bidx_adr + a + 1); it < i1; it += G) {
+        const int b = BT_LDG(m.body_idxs + it / 3), k = it % 3;
+        bs += xpos()[3 * b + k] - BT_LDG(m.clip_body_positions + ((size_t)fi * m.nbody + b) * 3 + k);
+      }
+      for (int it = 3 * BT_LDG(m.eidx_adr + a) + lane, i1 = 3 * BT_LDG(m.eidx_adr + a + 1); it < i1; it += G) {
+        const int b = BT_LDG(m.endeff_idxs + it / 3), k = it % 3;
+        es += xpos()[3 * b + k] - BT_LDG(m.clip_body_positions + ((size_t)fi * m.nbody + b) * 3 + k);
+      }
+      bs = W::allsum(bs); es = W::allsum(es);
+      const float z = xpos()[3 * an.torso + 2];
+      float healthy = z < m.healthy_z_min ? 0.f : 1.f;
+      healthy = z > m.healthy_z_max ? 0.f : healthy;
+      const float w0 = pd[0], w1 = pd[1], w2 = pd[2] * 0.2f;
+      const float sm = (w0 * w0 + w1 * w1) + w2 * w2;
+      pos_r += pr; quat_r += qr;
+      joint_r += m.joint_reward_weight * expf(-0.5f * jd);
+      angvel_r += m.angvel_reward_weight * expf(-0.5f * (av * av));
+      bodypos_r += m.bodypos_reward_weight * expf(-6.0f * (bs * bs));
+      endeff_r += m.endeff_reward_weight * expf(-0.75f * (es * es));
+      healthy_r += m.terminate_when_unhealthy ? m.healthy_reward : m.healthy_reward * healthy;
+      // max over the animals; a NaN distance propagates (comparisons with NaN are false in fmaxf, so select by hand)
+      summed = a == 0 ? sm : (sm > summed || sm != sm ? sm : summed);
+      quat_d = a == 0 ? qd : (qd > quat_d || qd != qd ? qd : quat_d);
+      joint_d = a == 0 ? jd : (jd > joint_d || jd != jd ? jd : joint_d);
+      too_far = fmaxf(too_far, sm > m.too_far_dist ? 1.f : 0.f);
+      bad_pose = fmaxf(bad_pose, jd > m.bad_pose_dist ? 1.f : 0.f);
+      bad_quat = fmaxf(bad_quat, qd > m.bad_quat_dist ? 1.f : 0.f);
+      fall = fmaxf(fall, 1.f - healthy);
     }
-    float js = 0.f;
-    for (int k = lane; k < m.clip_nj; k += G) js += qpos()[qoff + k] - BT_LDG(m.clip_joints + (size_t)fi * m.clip_nj + k);
-    js = W::allsum(js);
-    const float joint_d = js * js;
-    const float joint_r = m.joint_reward_weight * expf(-0.5f * joint_d);
-    const float* ca = m.clip_angular_velocity + 3 * fi;
-    const float av = ((qvel()[3] - BT_LDG(ca)) + (qvel()[4] - BT_LDG(ca + 1))) + (qvel()[5] - BT_LDG(ca + 2));
-    const float angvel_r = m.angvel_reward_weight * expf(-0.5f * (av * av));
-    float bs = 0.f, es = 0.f, cs = 0.f;
-    for (int it = lane; it < 3 * m.n_body_idxs; it += G) {
-      const int b = BT_LDG(m.body_idxs + it / 3), k = it % 3;
-      bs += xpos()[3 * b + k] - BT_LDG(m.clip_body_positions + ((size_t)fi * m.nbody + b) * 3 + k);
-    }
-    for (int it = lane; it < 3 * m.n_endeff_idxs; it += G) {
-      const int b = BT_LDG(m.endeff_idxs + it / 3), k = it % 3;
-      es += xpos()[3 * b + k] - BT_LDG(m.clip_body_positions + ((size_t)fi * m.nbody + b) * 3 + k);
-    }
+    float cs = 0.f;
     for (int u = lane; u < m.nu; u += G) cs += action[u] * action[u];
-    bs = W::allsum(bs); es = W::allsum(es); cs = W::allsum(cs);
-    const float bodypos_r = m.bodypos_reward_weight * expf(-6.0f * (bs * bs));
-    const float endeff_r = m.endeff_reward_weight * expf(-0.75f * (es * es));
-    const float z = xpos()[3 * m.torso_idx + 2];
-    float healthy = z < m.healthy_z_min ? 0.f : 1.f;
-    healthy = z > m.healthy_z_max ? 0.f : healthy;
-    const float healthy_r = m.terminate_when_unhealthy ? m.healthy_reward : m.healthy_reward * healthy;
-    const float w0 = pd[0], w1 = pd[1], w2 = pd[2] * 0.2f;
-    const float summed = (w0 * w0 + w1 * w1) + w2 * w2;
-    const float too_far = summed > m.too_far_dist ? 1.f : 0.f;
-    const float bad_pose = joint_d > m.bad_pose_dist ? 1.f : 0.f;
-    const float bad_quat = quat_d > m.bad_quat_dist ? 1.f : 0.f;
+    cs = W::allsum(cs);
     const float ctrl_cost = m.ctrl_cost_weight * cs;
     float reward = joint_r + pos_r + quat_r + angvel_r + bodypos_r + endeff_r + healthy_r - ctrl_cost;
-    float done = m.terminate_when_unhealthy ? 1.f - healthy : 0.f;
+    float done = m.terminate_when_unhealthy ? fall : 0.f;
     done = fmaxf(fmaxf(done, too_far), fmaxf(bad_pose, bad_quat));
     // NaN guard (fruitfly.py:569-577): any NaN in the pipeline state => done
     int nan = 0;
@@ -1793,7 +1864,7 @@ struct BtEnv {
     r.metrics[BT_M_POS] = pos_r; r.metrics[BT_M_QUAT] = quat_r; r.metrics[BT_M_JOINT] = joint_r;
     r.metrics[BT_M_ANGVEL] = angvel_r; r.metrics[BT_M_BODYPOS] = bodypos_r; r.metrics[BT_M_ENDEFF] = endeff_r;
     r.metrics[BT_M_QUADCTRL] = -ctrl_cost; r.metrics[BT_M_ALIVE] = healthy_r; r.metrics[BT_M_TOO_FAR] = too_far;
-    r.metrics[BT_M_BAD_POSE] = bad_pose; r.metrics[BT_M_BAD_QUAT] = bad_quat; r.metrics[BT_M_FALL] = 1.f - healthy;
+    r.metrics[BT_M_BAD_POSE] = bad_pose; r.metrics[BT_M_BAD_QUAT] = bad_quat; r.metrics[BT_M_FALL] = fall;
     r.summed_pos = summed; r.quat_d = quat_d; r.joint_d = joint_d;
   }
 };

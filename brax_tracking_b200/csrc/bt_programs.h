@@ -35,6 +35,7 @@ BT_DEV void bt_prog_step(const BtDev& m, float* s, int lane, int env, bool live,
     stc_in = a.info_i[(size_t)env * BT_NINFOI + BT_II_STEPS_TAKEN];
     time = a.state.time[env];
     W::sync();  // all lanes have read done / info before lane 0 overwrites them below
+    E.poison_scratch();
     E.load_state(a.state, env);
     const float* act_row = a.action + (size_t)env * m.nu;
     for (int u = lane; u < m.nu; u += G) E.ctrl()[u] = act_row[u];
@@ -102,6 +103,7 @@ BT_DEV void bt_prog_reset(const BtDev& m, float* s, int lane, int env, bool live
   typedef BtLanes<G> W;
   BtEnv<G, DS, CS> E(m, s, lane, live);
   if (!live) { E.forward(); return; }
+  E.poison_scratch();
   const unsigned k0 = a.keys[2 * (size_t)env], k1 = a.keys[2 * (size_t)env + 1];
   // training: rng, rng1, rng2, rng_pos = split(rng, 4);  render rollout: rng, rng1, rng2 = split(rng, 3)
   const int nsplit = a.fixed_start_frame < 0 ? 8 : 6;
@@ -125,8 +127,11 @@ BT_DEV void bt_prog_reset(const BtDev& m, float* s, int lane, int env, bool live
     float q0 = BT_LDG(m.qpos0 + i);
     if (m.seed_root_from_clip && a.fixed_start_frame < 0) {  // the render-rollout reset starts from qpos0 (custom_wrappers.py:99-103)
       const int fs = start > m.clip_len - 1 ? m.clip_len - 1 : start;  // JAX gather clamps (a clip shorter than the start-frame range)
-      if (i < 2) q0 = BT_LDG(m.clip_position + 3 * fs + i);
-      else if (i >= 3 && i < 7) q0 = BT_LDG(m.clip_quaternion + 4 * fs + i - 3);
+      for (int an = 0; an < m.n_animals; an++) {   // every animal's root x, y and orientation from its own copy of the clip
+        const int rel = i - BT_LDG(m.animal_rec + 8 * an);
+        if (rel >= 0 && rel < 2) q0 = BT_LDG(m.clip_position + 3 * (fs * m.n_animals + an) + rel);
+        else if (rel >= 3 && rel < 7) q0 = BT_LDG(m.clip_quaternion + 4 * (fs * m.n_animals + an) + rel - 3);
+      }
     }
     E.qpos()[i] = q0 + bt_bits_to_uniform(bt_random_bits(sk[2], sk[3], i, m.nq), lo, hi);
   }
@@ -162,6 +167,7 @@ BT_DEV void bt_prog_physics(const BtDev& m, float* s, int lane, int env, bool li
   if (live) {
     time = st.time[env];
     W::sync();
+    E.poison_scratch();
     E.load_state(st, env);
     for (int u = lane; u < m.nu; u += G) E.ctrl()[u] = ctrl ? ctrl[(size_t)env * m.nu + u] : 0.f;
     W::sync();
@@ -191,6 +197,7 @@ BT_DEV void bt_prog_reward(const BtDev& m, float* s, int lane, int env, bool liv
   const int cur_in = a.info_i[(size_t)env * BT_NINFOI + BT_II_CUR_FRAME];
   const int stc_in = a.info_i[(size_t)env * BT_NINFOI + BT_II_STEPS_TAKEN];
   W::sync();
+  E.poison_scratch();
   E.load_state(a.state, env);
   for (int i = lane; i < 3 * m.nbody; i += G) E.xpos()[i] = a.state.xpos[(size_t)env * 3 * m.nbody + i];
   for (int u = lane; u < m.nu; u += G) E.ctrl()[u] = a.action[(size_t)env * m.nu + u];

@@ -27,7 +27,7 @@ import copy
 import os
 import xml.etree.ElementTree as ET
 from dataclasses import dataclass, field
-from typing import Dict, List, Optional
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 
@@ -351,8 +351,18 @@ def _rescale_subtree(elem: ET.Element, pos_factor: float, size_factor: float):
             _rescale_subtree(child, pos_factor, size_factor)
 
 
-def _expand_replicate(elem: ET.Element):
-    """<replicate count sep offset euler>: expand children `count` times with name suffixes."""
+def _expand_replicate(elem: ET.Element) -> List[Tuple[str, int]]:
+    """``<replicate count sep offset euler>``: the children are instantiated ``count`` times with ``sep + k`` appended to every
+    name; copy k sits in frame ``T_k = T_{k-1} o (offset, euler)`` (``T_0`` = identity), which is FOLDED into the pose of each
+    direct child (MuJoCo frames are not bodies).  ``euler`` is in the compiler's angle unit like every other angle: with
+    ``<compiler angle="radian"/>`` the ``euler="0 0 180"`` of assets/rodent_pair.xml:163 is 180 rad (= 233.2 deg), not 180 deg.
+    Returns [(sep, count)] of the replicates met."""
+    found = []
+    comp = {}
+    for c in elem.findall("compiler"):
+        comp.update(c.attrib)
+    degree = comp.get("angle", "degree") == "degree"
+    eulerseq = comp.get("eulerseq", "xyz")
     changed = True
     while changed:
         changed = False
@@ -362,68 +372,48 @@ def _expand_replicate(elem: ET.Element):
                     continue
                 count = int(child.get("count", "1"))
                 sep = child.get("sep", "")
-                offset = _vec(child.get("offset"), default=[0, 0, 0]) if child.get("offset") else np.zeros(3)
-                euler = _vec(child.get("euler")) if child.get("euler") else np.zeros(3)
+                offset = _vec(child.get("offset")) if child.get("offset") else np.zeros(3)
+                dq = _orientation(child.attrib, eulerseq, degree)
                 parent.remove(child)
+                found.append((sep, count))
                 ins = idx
+                fpos, fquat = np.zeros(3), np.array([1.0, 0.0, 0.0, 0.0])
                 for k in range(count):
-                    frame = ET.Element("body")  # a jointless, massless frame body keeps semantics simple
-                    frame.set("name", f"__replicate_frame{sep}{k}")
-                    frame.set("pos", " ".join(repr(float(x)) for x in offset * k))
-                    frame.set("euler", " ".join(repr(float(x)) for x in euler * k))
+                    if k > 0:
+                        fpos = fpos + rotate(offset, fquat)
+                        fquat = quat_mul(fquat, dq)
                     for sub in child:
                         c = copy.deepcopy(sub)
                         for e in c.iter():
                             if e.get("name") is not None:
                                 e.set("name", f"{e.get('name')}{sep}{k}")
-                        frame.append(c)
-                    parent.insert(ins, frame)
-                    ins += 1
+                        if c.tag in ("body", "geom", "site", "camera", "light"):
+                            if c.get("fromto") is not None:
+                                raise NotImplementedError("fromto on a direct child of <replicate>")
+                            pos = fpos + rotate(_vec(c.get("pos"), default=[0, 0, 0]), fquat)
+                            quat = quat_mul(fquat, _orientation(c.attrib, eulerseq, degree))
+                            for k_ in ("euler", "axisangle", "xyaxes", "zaxis"):
+                                if k_ in c.attrib:
+                                    del c.attrib[k_]
+                            c.set("pos", " ".join(repr(float(x)) for x in pos))
+                            c.set("quat", " ".join(repr(float(x)) for x in quat))
+                        parent.insert(ins, c)
+                        ins += 1
                 changed = True
                 break
             if changed:
                 break
-
-
-def _duplicate_animal(root: ET.Element, count: int, offset) -> None:
-    """Stress-model helper (variant ii): `count` copies of every top-level moving body of the
-    worldbody in ONE world, names suffixed `-k`, copy k translated by k * offset; excludes / tendons / actuators are
-    duplicated with the suffixed references.  Copy 0 keeps the original names (so the env's name lists still resolve)."""
-    wb = root.find("worldbody")
-    tops = [b for b in wb if b.tag == "body"]
-
-    def suffixed(elem, k, attrs=("name", "joint", "tendon", "body1", "body2", "joint1", "joint2", "site", "objname")):
-        c = copy.deepcopy(elem)
-        for e in c.iter():
-            for a in attrs:
-                if e.get(a) is not None:
-                    e.set(a, f"{e.get(a)}-{k}")
-        return c
-
-    for k in range(1, count):
-        for b in tops:
-            c = suffixed(b, k)
-            pos = _vec(c.get("pos"), default=[0, 0, 0]) + np.asarray(offset, dtype=np.float64) * k
-            c.set("pos", " ".join(repr(float(x)) for x in pos))
-            wb.append(c)
-        for sec in ("contact", "tendon", "actuator"):
-            node = root.find(sec)
-            if node is not None:
-                for e in list(node):
-                    node.append(suffixed(e, k))
-    sens = root.find("sensor")
-    if sens is not None:
-        root.remove(sens)
+    return found
 
 
 def compile_mjcf(
     path: str,
     scale_factor: Optional[float] = None,
-    duplicate: Optional[tuple] = None,
     delete_free_joint_of: Optional[str] = None,
     overrides: Optional[dict] = None,
     missing_mesh: str = "error",
-    actuator_name_suffix_fix: bool = False,
+    replicate_actuators: bool = False,
+    extra_pairs: Optional[List[Tuple[str, str]]] = None,
 ) -> Model:
     """Compile an MJCF file.
 
@@ -434,15 +424,18 @@ def compile_mjcf(
     missing_mesh: 'error' | 'skip' -- what to do with mesh files absent from the checkout
         (six fly meshes).  'skip' treats the geom as massless unless it has explicit
         mass, in which case a sphere-equivalent inertia is used (declared deviation).
+    replicate_actuators: assets/rodent_pair.xml replicates the animal (``sep="-"``) but its ``<actuator>`` block still
+        names the un-suffixed joints, so MuJoCo itself rejects the file.  With this flag an actuator whose joint
+        only exists with the replicate suffixes is instantiated once per copy (``name-k`` on ``joint-k``), copy 0 first.
+    extra_pairs: explicit contact pairs by geom name, as ``<contact><pair geom1 geom2/>`` would add them (they bypass the
+        contype / conaffinity filter; unspecified parameters follow the geoms with the rules of dynamic pairs).
     """
     tree = ET.parse(path)
     root = tree.getroot()
     basedir = os.path.dirname(os.path.abspath(path))
-    _expand_replicate(root)
+    replicates = _expand_replicate(root)
     if scale_factor is not None:
         _rescale_subtree(root, scale_factor, scale_factor)
-    if duplicate is not None:
-        _duplicate_animal(root, int(duplicate[0]), duplicate[1])
 
     comp = {}
     for c in root.findall("compiler"):
@@ -876,6 +869,15 @@ def compile_mjcf(
             if a["geom_type"][i] > a["geom_type"][j]:
                 i, j = j, i
             pairs.append((i, j))
+    for n1, n2 in (extra_pairs or []):
+        i, j = m.name2id("geom", n1), m.name2id("geom", n2)
+        if i < 0 or j < 0:
+            raise ValueError(f"extra pair ({n1}, {n2}): geom not found")
+        if a["geom_type"][i] > a["geom_type"][j]:
+            i, j = j, i
+        if (i, j) in pairs or (j, i) in pairs:
+            raise ValueError(f"extra pair ({n1}, {n2}) is already a dynamic pair")
+        pairs.append((i, j))
     P = len(pairs)
     pair_geom = np.array(pairs, dtype=np.int32).reshape(-1, 2)
     pair_condim = np.zeros(P, dtype=np.int32)
@@ -951,15 +953,27 @@ def compile_mjcf(
     # ---- actuators
     acts = []
     act_root = root.find("actuator")
+    act_elems = []   # (element, name suffix)
     if act_root is not None:
-        for e in act_root:
+        plain = list(act_root)
+        if replicate_actuators and replicates:
+            sep, count = replicates[0]
+            for k in range(count):
+                for e in plain:
+                    jn = e.get("joint")
+                    if jn is not None and m.name2id("joint", jn) < 0 and m.name2id("joint", f"{jn}{sep}{k}") >= 0:
+                        act_elems.append((e, f"{sep}{k}"))
+                    elif k == 0:
+                        act_elems.append((e, ""))
+        else:
+            act_elems = [(e, "") for e in plain]
+    if True:
+        for e, sfx in act_elems:
             at = defaults.resolve(e.tag, e, None)
-            u = {"name": at.get("name", "")}
+            u = {"name": at.get("name", "") + sfx}
             if "joint" in at:
-                jname = at["joint"]
+                jname = at["joint"] + sfx
                 jid = m.name2id("joint", jname)
-                if jid < 0 and actuator_name_suffix_fix:
-                    jid = -2  # resolved by the caller (pair config)
                 if jid < 0:
                     raise ValueError(f"actuator joint {jname} not found")
                 u["trntype"], u["trnid"] = TRN_JOINT, jid

@@ -436,14 +436,21 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
     t["con_solimp"] = _f([c["solimp"] for c in con]) if con else Z(5, np.float32)
     t["con_includemargin"] = _f([c["includemargin"] for c in con]) if con else Z(1, np.float32)
     t["con_invweight"] = _f([c["invw"] for c in con]) if con else Z(1, np.float32)
-    # two trees in one contact need both reference points to coincide for the shared wrench; with one ref per
-    # tree the wrench is re-expressed per tree in the kernel (con_ref is the tree of body2; body1's tree uses
-    # its own ref).  All selected models have a single moving tree per contact or both bodies in one tree.
+    # A contact between two kinematic trees (BASELINE.json configs[3]: the opened inter-animal pairs): each tree's spatial
+    # quantities are about its own reference point, so body 1's side of such a contact uses the offset from ITS reference
+    # (con_xref = tree of body 1, -1 for ordinary contacts) and, in J' f, a second wrench slot behind the ncon regular ones
+    # (con_xslot) holding the same force as a wrench about that point.  con_ref stays the tree of body 2.
+    con_xref, con_xslot, ncross = [], [], 0
     for c in con:
         m1 = a["body_lastdof"][c["b1"]] >= 0
         m2 = a["body_lastdof"][c["b2"]] >= 0
         if m1 and m2 and body_ref[c["b1"]] != body_ref[c["b2"]]:
-            raise NotImplementedError("contacts between two different kinematic trees need per-tree wrenches")
+            con_xref.append(int(body_ref[c["b1"]])); con_xslot.append(ncon + ncross); ncross += 1
+        else:
+            con_xref.append(-1); con_xslot.append(-1)
+    S("ncross", ncross)
+    t["con_xref"] = _i(con_xref) if con else Z(1, np.int32)
+    t["con_xslot"] = _i(con_xslot) if con else Z(1, np.int32)
     # J' f in two gathers: contact -> contact body (sign +1 when the body is geom2's, -1 when it is geom1's), then
     # contact body -> every dof on its ancestor chain (common ancestors of a two-body contact cancel in the sum)
     cbcon = [[] for _ in range(max(ncb, 1))]
@@ -451,7 +458,7 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
         if c["b2"] in cb_slot:
             cbcon[cb_slot[c["b2"]]].append((ci, 1.0))
         if c["b1"] in cb_slot:
-            cbcon[cb_slot[c["b1"]]].append((ci, -1.0))
+            cbcon[cb_slot[c["b1"]]].append((con_xslot[ci] if con_xslot[ci] >= 0 else ci, -1.0))
     cbcon_adr, cbcon_c, cbcon_s = [0], [], []
     for k in range(ncb):
         for ci, sg in cbcon[k]:
@@ -557,6 +564,8 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
     # the CTA, 32 / 64 / 128 = only within a contiguous half / equal parity / equal (index mod 4); 2..16 = extra barrier
     # points; 0 = none.  Measured (rodent, 8192 envs): 0: 1.39 M (r1q), 1: 2.756 M, 32: 2.777 M, 64: 2.781 M, 128: 2.61 M.
     S("sync_mode", int(os.environ.get("BT_SYNC", "64")))
+    # initcheck substitute: fill the scratch slice with NaN before every program (csrc/bt_impl.h::poison_scratch)
+    S("poison", int(os.environ.get("BT_POISON", "0")))
     SF("timestep", m.timestep)
     SF("grav_x", m.gravity[0]); SF("grav_y", m.gravity[1]); SF("grav_z", m.gravity[2])
     SF("density", m.density); SF("viscosity", m.viscosity); SF("impratio", m.impratio)
@@ -567,9 +576,21 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
     nj = int(np.asarray(clip["joints"]).shape[1])
     S("free_jnt", int(cfg["free_jnt"])); S("seed_root_from_clip", int(cfg["seed_root_from_clip"]))
     S("ref_len", cfg["ref_len"]); S("clip_len", T); S("clip_nj", nj)
-    jidx = _gather_idx(cfg["joint_idxs"], nj)
-    bidx = _gather_idx(cfg["body_idxs"], nbody)
-    eidx = _gather_idx(cfg["endeff_idxs"], nbody)
+    # per-animal index lists (configs.resolve: cfg["animals"]); joint ids index the ANIMAL's own joint columns
+    animals = cfg.get("animals") or [dict(qadr=0, dadr=0, nj=nj, jbase=0, torso_idx=cfg["torso_idx"], joint_idxs=cfg["joint_idxs"],
+                                          body_idxs=cfg["body_idxs"], endeff_idxs=cfg["endeff_idxs"])]
+    NA = len(animals)
+    S("n_animals", NA)
+    jidx, bidx, eidx, jadr, badr, eadr = [], [], [], [0], [0], [0]
+    arec = np.zeros((NA, 8), dtype=np.int32)
+    for k, an in enumerate(animals):
+        jidx.extend(_gather_idx(an["joint_idxs"], an["nj"])); jadr.append(len(jidx))
+        bidx.extend(_gather_idx(an["body_idxs"], nbody)); badr.append(len(bidx))
+        eidx.extend(_gather_idx(an["endeff_idxs"], nbody)); eadr.append(len(eidx))
+        arec[k, :5] = [an["qadr"], an["dadr"], an["nj"], an["jbase"], int(an["torso_idx"]) % nbody]
+    jidx, bidx, eidx = _i(jidx), _i(bidx), _i(eidx)
+    t["animal_rec"] = arec.reshape(-1); t["jidx_adr"] = _i(jadr); t["bidx_adr"] = _i(badr); t["eidx_adr"] = _i(eadr)
+    assert sum(an["nj"] for an in animals) == nj, "the clip's joint columns are the animals' joints side by side"
     S("n_joint_idxs", len(jidx)); S("n_body_idxs", len(bidx)); S("n_endeff_idxs", len(eidx))
     t["joint_idxs"] = jidx; t["body_idxs"] = bidx; t["endeff_idxs"] = eidx if len(eidx) else Z(1, np.int32)
     S("torso_idx", int(cfg["torso_idx"]) % nbody)  # negative ids index from the end, as in JAX
@@ -585,14 +606,16 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
     SF("healthy_z_min", cfg["healthy_z_range"][0]); SF("healthy_z_max", cfg["healthy_z_range"][1])
     L = int(cfg["ref_len"])
     if cfg["free_jnt"]:
-        obs_size = nq + nv + 3 * L + 4 * L + len(jidx) * L + 3 * len(bidx) * L
+        obs_size = nq + nv + NA * (3 * L + 4 * L) + len(jidx) * L + 3 * len(bidx) * L
     else:
         obs_size = nq + nv + len(jidx) * L + 3 * len(bidx) * L
     S("obs_size", obs_size)
     for k in CLIP_FIELDS:
         t["clip_" + k] = _f(clip[k])
     assert np.asarray(clip["body_positions"]).shape[1:] == (nbody, 3)
-    assert nj == (nq - 7 if cfg["free_jnt"] else nq), (nj, nq)
+    assert nj == (nq - 7 * NA if cfg["free_jnt"] else nq), (nj, nq)
+    for k, w in (("position", 3), ("quaternion", 4), ("angular_velocity", 3)):
+        assert np.asarray(clip[k]).reshape(T, -1).shape[1] == w * NA, (k, np.asarray(clip[k]).shape, NA)
 
     # ------------------------------------------------------------------ per-environment scratch layout (floats)
     lay, off = {}, 0
@@ -617,7 +640,12 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
     # T region: cfrc (tree passes) -> the 6x6 reduced articulated inertia of every chain top (aba_factor)
     # -> contact geometry + wrenches + chain sums (solver)
     ALIGN4()   # the second pose buffer's quaternions (T + round4(3 * nbody)) are 128-bit accesses too
-    R("T", max(7 * nbody + 3, 6 * nv, 18 * ncon + 6 * max(ncb, 1)))   # 7 * nbody: second pose buffer of the composition
+    # The per-contact wrenches of J' f (6 per contact, + 6 per inter-tree contact) live only inside the CG loop, where the pivots
+    # Dd (used by M v before the solve) and the three cbJ chain-sum sets (consumed by the warm-start selection) are dead: when
+    # they fit, the wrenches take that space instead of lengthening T (two-rodent model: 6 instead of 5 environments per SM)
+    wrench_floats = 6 * (ncon + ncross)
+    wrench_alias = wrench_floats <= nv + 18 * max(ncb, 1)
+    R("T", max(7 * nbody + 3, 6 * nv, 12 * ncon + (0 if wrench_alias else wrench_floats) + 6 * max(ncb, 1)))   # 7 * nbody: second pose buffer
     R("ref", 3 * max(len(roots), 1))
     R("actdot", max(na, 1))
     # pvec (sweep state, 6/dof) and the solver vectors behind it are contiguous: together they hold cvel/cacc (12/dof)
@@ -630,6 +658,9 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
     R("x", max(nv, nu))
     if off - w12 < 12 * nv:    # inclusive cvel / cacc per dof during the velocity sweep
         off = w12 + 12 * nv
+    assert lay["cbJ"] == lay["Dd"] + nv
+    lay["wrench"] = lay["Dd"] if wrench_alias else lay["T"] + 12 * ncon
+    lay["cbA"] = lay["T"] + 12 * ncon + (0 if wrench_alias else wrench_floats)
     lay["aforce"] = lay["x"]            # actuator forces live only inside smooth_forces()
     lay["tmpv"] = lay["qacc_smooth"]    # solve() temp (g_k): qacc_smooth is consumed (into registers) before the first CG solve
     for k, v in lay.items():

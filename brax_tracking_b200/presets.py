@@ -7,8 +7,8 @@ import functools
 from . import assets, clips, configs
 
 ENV_ARGS = dict(rodent=configs.RODENT_ENV_ARGS, fly_free=configs.FLY_FREEJNT_ENV_ARGS, fly_tethered=configs.FLY_ENV_ARGS,
-                # two-rodent stress model (BASELINE.json configs[3]): the env layer of animal 0 (names resolve to the un-suffixed copy)
-                rodent_pair=configs.RODENT_ENV_ARGS)
+                # BASELINE.json configs[3]: rodent_pair.xml, both animals tracked, 12 opened inter-animal capsule pairs
+                rodent_pair=configs.RODENT_PAIR_ENV_ARGS)
 
 
 @functools.lru_cache(maxsize=None)

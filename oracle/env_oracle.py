@@ -136,6 +136,14 @@ class EnvOracle:
         self.c = dict(cfg)
         self.T = self.clip["joints"].shape[0]
 
+    def animals(self):
+        """Per-animal constants (brax_tracking_b200.configs.resolve): every reference env has one animal; the two-rodent
+        model of BASELINE.json configs[3] applies the single-animal expressions to each animal's own slices."""
+        c = self.c
+        nj = self.clip["joints"].shape[1]
+        return c.get("animals") or [dict(qadr=0, dadr=0, nj=nj, jbase=0, torso_idx=c["torso_idx"], joint_idxs=c["joint_idxs"],
+                                         body_idxs=c["body_idxs"], endeff_idxs=c["endeff_idxs"])]
+
     # -- fruitfly.py:598-646 ---------------------------------------------------------------------
     def get_obs(self, qpos, qvel, xpos, cur_frame):
         c, dt = self.c, self.dt
@@ -145,20 +153,25 @@ class EnvOracle:
         win = start[:, None] + np.arange(L)[None, :]   # [N, L]
         parts = [qpos, qvel]
         free = c["free_jnt"]
-        nj = self.clip["joints"].shape[1]
-        if free:
-            quat = qpos[:, 3:7]
-            parts.append(rotate(self.clip["position"][win] - qpos[:, None, :3], quat[:, None, :]).reshape(N, -1))
-            parts.append(relative_quat(quat[:, None, :], self.clip["quaternion"][win]).reshape(N, -1))
-            jd = self.clip["joints"][win] - qpos[:, None, 7:]
-        else:
-            # tethered: fruitfly.py:271-319 -- no pos/quat terms, full qpos joints, offsets rotated by qpos[3:7]
-            quat = qpos[:, 3:7]
-            jd = self.clip["joints"][win] - qpos[:, None, :]
-        parts.append(jd[:, :, _gather_idx(c["joint_idxs"], nj)].reshape(N, -1))
-        bidx = _gather_idx(c["body_idxs"], self.m.nbody)
-        bd = (self.clip["body_positions"][win] - xpos[:, None, :, :])[:, :, bidx]  # [N,L,nb,3]
-        parts.append(rotate(bd, quat[:, None, None, :]).reshape(N, -1))
+        ans = self.animals()
+        NA = len(ans)
+        cpos = self.clip["position"].reshape(self.T, NA, 3)
+        cquat = self.clip["quaternion"].reshape(self.T, NA, 4)
+        for a, an in enumerate(ans):
+            qa = an["qadr"]
+            # tethered: fruitfly.py:271-319 -- no pos/quat terms, full qpos joints, offsets rotated by qpos[3:7] (joint angles!)
+            quat = qpos[:, qa + 3:qa + 7]
+            if free:
+                parts.append(rotate(cpos[win, a] - qpos[:, None, qa:qa + 3], quat[:, None, :]).reshape(N, -1))
+                parts.append(relative_quat(quat[:, None, :], cquat[win, a]).reshape(N, -1))
+                q0 = qa + 7
+            else:
+                q0 = qa
+            jd = self.clip["joints"][win][:, :, an["jbase"]:an["jbase"] + an["nj"]] - qpos[:, None, q0:q0 + an["nj"]]
+            parts.append(jd[:, :, _gather_idx(an["joint_idxs"], an["nj"])].reshape(N, -1))
+            bidx = _gather_idx(an["body_idxs"], self.m.nbody)
+            bd = (self.clip["body_positions"][win] - xpos[:, None, :, :])[:, :, bidx]  # [N,L,nb,3]
+            parts.append(rotate(bd, quat[:, None, None, :]).reshape(N, -1))
         return np.concatenate(parts, axis=1).astype(dt)
 
     @staticmethod
@@ -189,8 +202,11 @@ class EnvOracle:
             q0 = m.qpos0.astype(dt).copy()
             if c["seed_root_from_clip"] and fixed_start_frame < 0:
                 fs = min(max(int(start[e]), 0), self.T - 1)   # JAX gather clamps
-                q0[:2] = self.clip["position"][fs, :2]
-                q0[3:7] = self.clip["quaternion"][fs]
+                ans = self.animals()
+                for a, an in enumerate(ans):                  # every animal from its own copy of the clip
+                    qa = an["qadr"]
+                    q0[qa:qa + 2] = self.clip["position"].reshape(self.T, len(ans), 3)[fs, a, :2]
+                    q0[qa + 3:qa + 7] = self.clip["quaternion"].reshape(self.T, len(ans), 4)[fs, a]
             qpos[e] = q0 + uniform(rng1, m.nq, lo, hi).astype(dt)
             qvel[e] = uniform(rng2, m.nv, lo, hi).astype(dt)
         st = dict(qpos=qpos, qvel=qvel, act=np.zeros((N, m.na), dtype=dt), qacc_warmstart=np.zeros((N, m.nv), dtype=dt),
@@ -235,46 +251,72 @@ class EnvOracle:
         fi = np.clip(cur, 0, self.T - 1)  # JAX gather clamps
         qpos, qvel, xpos = ps["qpos"], ps["qvel"], ps["xpos"]
         free = c["free_jnt"]
-        if free:
-            pos_distance = qpos[:, :3] - self.clip["position"][fi]
-            pos_reward = f32(c["pos_reward_weight"]) * np.exp(f32(-400) * np.sum(pos_distance, -1) ** 2)
-            quat_distance = self.bounded_quat_dist(qpos[:, 3:7], self.clip["quaternion"][fi]) ** 2
-            quat_reward = f32(c["quat_reward_weight"]) * np.exp(f32(-4.0) * quat_distance)
-            joint_distance = np.sum(qpos[:, 7:] - self.clip["joints"][fi], -1) ** 2
-        else:
-            pos_distance = np.zeros((N, 3), dtype=dt)
-            quat_distance = np.zeros(N, dtype=dt)
-            pos_reward = np.zeros(N, dtype=dt)
-            quat_reward = np.zeros(N, dtype=dt)
-            joint_distance = np.sum(qpos - self.clip["joints"][fi], -1) ** 2
-        joint_reward = f32(c["joint_reward_weight"]) * np.exp(f32(-0.5) * joint_distance)
-        info["joint_distance"] = joint_distance.astype(dt)
-        angvel_reward = f32(c["angvel_reward_weight"]) * np.exp(f32(-0.5) * np.sum(qvel[:, 3:6] - self.clip["angular_velocity"][fi], -1) ** 2)
-        bidx = _gather_idx(c["body_idxs"], self.m.nbody)
-        eidx = _gather_idx(c["endeff_idxs"], self.m.nbody)
-        tb = self.clip["body_positions"][fi]
-        bodypos_reward = f32(c["bodypos_reward_weight"]) * np.exp(f32(-6.0) * np.sum((xpos[:, bidx] - tb[:, bidx]).reshape(N, -1), -1) ** 2)
-        endeff_reward = f32(c["endeff_reward_weight"]) * np.exp(f32(-0.75) * np.sum((xpos[:, eidx] - tb[:, eidx]).reshape(N, -1), -1) ** 2)
+        ans = self.animals()
+        NA = len(ans)
+        cpos = self.clip["position"].reshape(self.T, NA, 3)
+        cquat = self.clip["quaternion"].reshape(self.T, NA, 4)
+        cang = self.clip["angular_velocity"].reshape(self.T, NA, 3)
         min_z, max_z = c["healthy_z_range"]
-        z = xpos[:, c["torso_idx"], 2]
-        is_healthy = np.where(z < f32(min_z), f32(0), f32(1))
-        is_healthy = np.where(z > f32(max_z), f32(0), is_healthy)
-        if c["terminate_when_unhealthy"]:
-            healthy_reward = np.full(N, c["healthy_reward"], dtype=dt)
-        else:
-            healthy_reward = f32(c["healthy_reward"]) * is_healthy
-        summed_pos_distance = np.sum((pos_distance * np.array([1.0, 1.0, 0.2], dtype=dt)) ** 2, -1)
-        too_far = np.where(summed_pos_distance > f32(c["too_far_dist"]), f32(1), f32(0))
-        info["summed_pos_distance"] = summed_pos_distance.astype(dt)
-        info["quat_distance"] = quat_distance.astype(dt)
-        bad_pose = np.where(joint_distance > f32(c["bad_pose_dist"]), f32(1), f32(0))
-        bad_quat = np.where(quat_distance > f32(c["bad_quat_dist"]), f32(1), f32(0))
+        z32 = lambda: np.zeros(N, dtype=dt)
+        tot = {k: z32() for k in ("pos", "quat", "joint", "angvel", "bodypos", "endeff", "healthy")}
+        flags = {k: z32() for k in ("too_far", "bad_pose", "bad_quat", "fall")}
+        dist = {}
+        with np.errstate(invalid="ignore"):
+            for a, an in enumerate(ans):
+                # ---- the single-animal expressions of fruitfly.py:514-552 on this animal's slices
+                qa, da = an["qadr"], an["dadr"]
+                if free:
+                    pos_distance = qpos[:, qa:qa + 3] - cpos[fi, a]
+                    pos_reward = f32(c["pos_reward_weight"]) * np.exp(f32(-400) * np.sum(pos_distance, -1) ** 2)
+                    quat_distance = self.bounded_quat_dist(qpos[:, qa + 3:qa + 7], cquat[fi, a]) ** 2
+                    quat_reward = f32(c["quat_reward_weight"]) * np.exp(f32(-4.0) * quat_distance)
+                    q0 = qa + 7
+                else:
+                    pos_distance = np.zeros((N, 3), dtype=dt)
+                    quat_distance = z32()
+                    pos_reward = z32()
+                    quat_reward = z32()
+                    q0 = qa
+                joint_distance = np.sum(qpos[:, q0:q0 + an["nj"]] - self.clip["joints"][fi][:, an["jbase"]:an["jbase"] + an["nj"]], -1) ** 2
+                joint_reward = f32(c["joint_reward_weight"]) * np.exp(f32(-0.5) * joint_distance)
+                angvel_reward = f32(c["angvel_reward_weight"]) * np.exp(f32(-0.5) * np.sum(qvel[:, da + 3:da + 6] - cang[fi, a], -1) ** 2)
+                bidx = _gather_idx(an["body_idxs"], self.m.nbody)
+                eidx = _gather_idx(an["endeff_idxs"], self.m.nbody)
+                tb = self.clip["body_positions"][fi]
+                bodypos_reward = f32(c["bodypos_reward_weight"]) * np.exp(f32(-6.0) * np.sum((xpos[:, bidx] - tb[:, bidx]).reshape(N, -1), -1) ** 2)
+                endeff_reward = f32(c["endeff_reward_weight"]) * np.exp(f32(-0.75) * np.sum((xpos[:, eidx] - tb[:, eidx]).reshape(N, -1), -1) ** 2)
+                z = xpos[:, an["torso_idx"], 2]
+                is_healthy = np.where(z < f32(min_z), f32(0), f32(1))
+                is_healthy = np.where(z > f32(max_z), f32(0), is_healthy)
+                if c["terminate_when_unhealthy"]:
+                    healthy_reward = np.full(N, c["healthy_reward"], dtype=dt)
+                else:
+                    healthy_reward = f32(c["healthy_reward"]) * is_healthy
+                summed_pos_distance = np.sum((pos_distance * np.array([1.0, 1.0, 0.2], dtype=dt)) ** 2, -1)
+                # ---- combination over animals (DESIGN.md "config 4"): reward terms add, flags and distances take the max
+                for k, v in (("pos", pos_reward), ("quat", quat_reward), ("joint", joint_reward), ("angvel", angvel_reward),
+                             ("bodypos", bodypos_reward), ("endeff", endeff_reward), ("healthy", healthy_reward)):
+                    tot[k] = (tot[k] + v).astype(dt)
+                for k, v in (("too_far", np.where(summed_pos_distance > f32(c["too_far_dist"]), f32(1), f32(0))),
+                             ("bad_pose", np.where(joint_distance > f32(c["bad_pose_dist"]), f32(1), f32(0))),
+                             ("bad_quat", np.where(quat_distance > f32(c["bad_quat_dist"]), f32(1), f32(0))),
+                             ("fall", f32(1) - is_healthy)):
+                    flags[k] = np.maximum(flags[k], v).astype(dt)
+                for k, v in (("summed_pos_distance", summed_pos_distance), ("quat_distance", quat_distance), ("joint_distance", joint_distance)):
+                    v = v.astype(dt)
+                    dist[k] = v if a == 0 else np.where((v > dist[k]) | np.isnan(v), v, dist[k])   # max; NaN propagates
+        pos_reward, quat_reward, joint_reward, angvel_reward = tot["pos"], tot["quat"], tot["joint"], tot["angvel"]
+        bodypos_reward, endeff_reward, healthy_reward = tot["bodypos"], tot["endeff"], tot["healthy"]
+        too_far, bad_pose, bad_quat, fall = flags["too_far"], flags["bad_pose"], flags["bad_quat"], flags["fall"]
+        info["joint_distance"] = dist["joint_distance"]
+        info["summed_pos_distance"] = dist["summed_pos_distance"]
+        info["quat_distance"] = dist["quat_distance"]
         action = np.asarray(action, dtype=dt)
         ctrl_cost = f32(c["ctrl_cost_weight"]) * np.sum(np.square(action), -1)
         obs = self.get_obs(qpos, qvel, xpos, cur)
         reward = (joint_reward + pos_reward + quat_reward + angvel_reward + bodypos_reward + endeff_reward
                   + healthy_reward - ctrl_cost)
-        done = (f32(1) - is_healthy) if c["terminate_when_unhealthy"] else np.zeros(N, dtype=dt)
+        done = fall if c["terminate_when_unhealthy"] else np.zeros(N, dtype=dt)
         done = np.max(np.stack([done, too_far, bad_pose, bad_quat]), axis=0)
         reward = np.nan_to_num(reward)
         obs = np.nan_to_num(obs)
@@ -286,7 +328,7 @@ class EnvOracle:
         metrics = dict(pos_reward=pos_reward, quat_reward=quat_reward, joint_reward=joint_reward,
                        angvel_reward=angvel_reward, bodypos_reward=bodypos_reward, endeff_reward=endeff_reward,
                        reward_quadctrl=-ctrl_cost, reward_alive=healthy_reward, too_far=too_far, bad_pose=bad_pose,
-                       bad_quat=bad_quat, fall=f32(1) - is_healthy)
+                       bad_quat=bad_quat, fall=fall)
         metrics = {k: np.asarray(v, dtype=dt) for k, v in metrics.items()}
         return dict(pipeline_state=ps, obs=obs.astype(dt), reward=reward.astype(dt), done=done.astype(dt),
                     metrics=metrics, info=info)

@@ -20,15 +20,19 @@ def random_states(m, N, seed=0):
     rng = np.random.default_rng(seed)
     st = dict(qpos=np.zeros((N, m.nq), np.float32), qvel=np.zeros((N, m.nv), np.float32), act=np.zeros((N, m.na), np.float32),
               qacc_warmstart=np.zeros((N, m.nv), np.float32), time=np.zeros(N, np.float32), xpos=np.zeros((N, 3 * m.nbody), np.float32))
-    free = m.jnt_type[0] == 0
+    roots = [int(m.jnt_qposadr[j]) for j in range(m.njnt) if m.jnt_type[j] == 0]
+    hinge = np.ones(m.nq, bool)
+    for qa in roots:
+        hinge[qa:qa + 7] = False
     for e in range(N):
         q = m.qpos0.copy()
-        hinge = slice(7, None) if free else slice(0, None)
-        q[hinge] += rng.uniform(-0.2, 0.2, q[hinge].shape)
-        if free:
-            q[2] += rng.uniform(-0.01, 0.02)
-            quat = np.array([1.0, 0, 0, 0]) + rng.uniform(-0.2, 0.2, 4)
-            q[3:7] = quat / np.linalg.norm(quat)
+        q[hinge] += rng.uniform(-0.2, 0.2, int(hinge.sum()))
+        for k, qa in enumerate(roots):
+            q[qa + 2] += rng.uniform(-0.01, 0.02)
+            quat = q[qa + 3:qa + 7] + rng.uniform(-0.2, 0.2, 4)
+            q[qa + 3:qa + 7] = quat / np.linalg.norm(quat)
+            if k > 0:     # further animals stand beside the first one (0.3 m apart: no inter-animal contact)
+                q[qa:qa + 2] += [0.0, 0.3 * k]
         st["qpos"][e] = q
         st["qvel"][e] = rng.uniform(-1, 1, m.nv)
         st["act"][e] = rng.uniform(-0.5, 0.5, m.na)
@@ -37,12 +41,50 @@ def random_states(m, N, seed=0):
     return st, ctrl
 
 
-def check_forward_intermediates(backend, name, N=8):
+def touching_states(name, N, seed=0, min_active=1):
+    """States of a two-animal model in which inter-animal contacts are ACTIVE (penetrating): the second root is placed beside the
+    first by rejection sampling against the oracle's collision pass."""
+    m, cfg, clip, tables = common.setup(name)
+    o, _ = common.oracles(name)
+    rng = np.random.default_rng(seed)
+    roots = [int(m.jnt_qposadr[j]) for j in range(m.njnt) if m.jnt_type[j] == 0]
+    assert len(roots) == 2
+    cross = np.asarray(tables["con_xref"]) >= 0
+    base, ctrl = random_states(m, 1, seed=seed + 100)
+    out = {k: np.repeat(np.zeros_like(v), N, 0) for k, v in base.items()}
+    ctrls = np.zeros((N, m.nu), np.float32)
+    found = tries = 0
+    while found < N:
+        tries += 1
+        assert tries < 4000, "no touching configuration found"
+        st1, c1 = random_states(m, 1, seed=int(rng.integers(1 << 30)))
+        q = st1["qpos"][0].astype(np.float64)
+        q0, q1 = roots
+        yaw = rng.uniform(-np.pi, np.pi)
+        q[q1:q1 + 2] = q[q0:q0 + 2] + rng.uniform(-0.07, 0.07, 2)
+        q[q1 + 2] = q[q0 + 2] + rng.uniform(-0.005, 0.005)
+        q[q1 + 3:q1 + 7] = [np.cos(yaw / 2), 0, 0, np.sin(yaw / 2)]
+        o.set_state(q, st1["qvel"][0].astype(np.float64), st1["act"][0].astype(np.float64), st1["qacc_warmstart"][0].astype(np.float64),
+                    c1[0].astype(np.float64))
+        o.forward()
+        d = np.asarray(o.d.con_dist)
+        # penetrating but not absurdly deep (a few mm at most: the regime a simulation can reach)
+        act = cross & (d < 0)
+        if act.sum() >= min_active and d[cross].min() > -0.004:
+            for k in out:
+                out[k][found] = st1[k][0]
+            out["qpos"][found] = q.astype(np.float32)
+            ctrls[found] = c1[0]
+            found += 1
+    return out, ctrls
+
+
+def check_forward_intermediates(backend, name, N=8, states=None):
     """kinematics / smooth forces / tree-sparse factor+solve / collision / CG vs the dense float64 oracle."""
     m, cfg, clip, tables = common.setup(name)
     o, _ = common.oracles(name)
     o32 = oracle_mod.Oracle(m, np.float32)
-    st, ctrl = random_states(m, N)
+    st, ctrl = random_states(m, N) if states is None else states
     full, cdist, niter = backend.forward_debug(st, ctrl, 0)
     at5, _, _ = backend.forward_debug(st, ctrl, 5)
     R = lambda s, e, nm, size: common.region(tables, s[e], nm, size).astype(np.float64)

@@ -59,11 +59,17 @@ def test_fly_elliptic_cone(name):
     assert r["n_done"] > 0
 
 
-def test_two_rodent_stress_model():
-    """configs[3]: two rodents in one world (nv 146, 60 floor contacts, two kinematic trees); SURVEY Appendix C.3 (ii)."""
+def test_two_rodent_model_with_inter_animal_contacts():
+    """configs[3]: assets/rodent_pair.xml -- two animals in one world (nv 146, 114 floor contacts + 12 opened inter-animal capsule
+    pairs, two kinematic trees), both tracked (obs 1234); SURVEY Appendix C.3 (i), DESIGN.md "config 4"."""
     name = "rodent_pair"
-    b = EmuBackend(common.setup(name)[3])
+    m, cfg, clip, tables = common.setup(name)
+    assert (m.nq, m.nv, m.nu, m.na, m.nbody) == (148, 146, 60, 60, 133) and int(tables["obs_size"][0]) == 1234
+    assert int(tables["ncon"][0]) == 126 and int(tables["ncross"][0]) == 12 and int(tables["n_animals"][0]) == 2
+    b = EmuBackend(tables)
     pc.check_forward_intermediates(b, name, N=2)
+    # the animals actually touching: active (penetrating) contacts between the two kinematic trees
+    pc.check_forward_intermediates(b, name, N=4, states=pc.touching_states(name, 4, seed=1))
     pc.check_reset(b, name, N=4)
     pc.check_physics_1_10_100(b, name, N=2)
     bt = EmuBackend(common.setup(name, FLY_EPISODE)[3])

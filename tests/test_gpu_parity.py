@@ -208,16 +208,64 @@ def test_host_bound_observations():
         assert np.array_equal(sd.reward.cpu().numpy(), sh.reward.cpu().numpy())
 
 
-def test_two_rodent_stress_model():
-    """configs[3]: 4096-env kernel variant (5 dof slots, 4 contact slots per lane)."""
+def test_two_rodent_model_with_inter_animal_contacts():
+    """configs[3]: rodent_pair.xml, 4096-env kernel variant (5 dof slots, 4 contact slots per lane): two kinematic trees with
+    contacts BETWEEN them (per-tree reference points in J v / J' f), both animals tracked."""
     from backends import CudaBackend
     name = "rodent_pair"
-    b = CudaBackend(common.setup(name)[3])
+    m, cfg, clip, tables = common.setup(name)
+    assert int(tables["obs_size"][0]) == 1234 and int(tables["ncross"][0]) == 12
+    b = CudaBackend(tables)
     pc.check_forward_intermediates(b, name, N=8)
+    pc.check_forward_intermediates(b, name, N=16, states=pc.touching_states(name, 16, seed=1))   # animals touching
     pc.check_reset(b, name, N=32)
-    pc.check_physics_1_10_100(b, name, N=4)
+    print(pc.check_physics_1_10_100(b, name, N=8))
+    pc.check_unwrapped_step(b, name, N=8, T=8)
+    pc.check_nan_guard(b, name)
     bt = CudaBackend(common.setup(name, 12)[3])
-    print(pc.check_teacher_forced(bt, name, N=8, T=30, episode_length=12))
+    print(pc.check_teacher_forced(bt, name, N=16, T=30, episode_length=12))
+
+
+def test_poisoned_scratch_and_scheduling_invariance():
+    """compute-sanitizer is closed on this pool (profiles/r2a_sanitizer.txt); what stands in for initcheck / racecheck:
+      * `poison`: every program first fills its shared-memory slice with NaN -- a read of anything it did not write itself would
+        surface in the outputs; they must be bit-identical to the unpoisoned run;
+      * scheduling: warps per CTA (which warps share an SM / a barrier), barrier placement (BT_SYNC) and the position of an
+        environment in the batch change every inter-warp timing; outputs must not change by a single bit."""
+    import os
+    from backends import CudaBackend
+    from brax_tracking_b200 import model as model_mod
+    for name, n in (("rodent", 96), ("fly_free", 64), ("rodent_pair", 24)):
+        m, cfg, clip, tables = common.setup(name, 12)
+        keys = common.jax_keys(n, seed=41)
+        acts = common.actions(6, n, m.nu, seed=42, scale=0.5)
+
+        def rollout(tb, env=None):
+            old = {k: os.environ.get(k) for k in (env or {})}
+            os.environ.update(env or {})
+            try:
+                b = CudaBackend(tb)
+            finally:
+                for k, v in old.items():
+                    os.environ.pop(k, None) if v is None else os.environ.__setitem__(k, v)
+            st, out = b.reset(keys)
+            first = {k: v.copy() for k, v in st.items()}
+            fo, fi = out["obs"].copy(), out["info_i"].copy()
+            for t in range(acts.shape[0]):
+                b.step(st, out, first, fo, fi, acts[t])
+            return st, out
+
+        ref_st, ref_out = rollout(tables)
+        variants = {"poison": (dict(tables, poison=np.array([1], np.int32)), None),
+                    "sync=1": (dict(tables, sync_mode=np.array([1], np.int32)), None),
+                    "sync=0": (dict(tables, sync_mode=np.array([0], np.int32)), None),
+                    "warps=3": (tables, {"BT_WARPS": "3"}), "warps=1": (tables, {"BT_WARPS": "1"})}
+        for label, (tb, env) in variants.items():
+            st, out = rollout(tb, env)
+            for k in ref_st:
+                assert np.array_equal(ref_st[k], st[k]), (name, label, k)
+            for k in ref_out:
+                assert np.array_equal(ref_out[k], out[k], equal_nan=True), (name, label, k)
 
 
 def test_ppo_loop_runs_on_the_fused_step(tmp_path):

@@ -20,9 +20,13 @@ ff = mjcf.compile_mjcf(fly, overrides=OPT, missing_mesh="skip")
 assets.save_model(ff, os.path.join(OUT, "fly_free.npz"))
 ft = mjcf.compile_mjcf(fly, delete_free_joint_of="thorax", overrides=OPT, missing_mesh="skip")
 assets.save_model(ft, os.path.join(OUT, "fly_tethered.npz"))
-# two-rodent stress model (BASELINE.json configs[3]; SURVEY Appendix C.3 variant ii): `rodent_pair.xml` does not compile
-# as committed, so the pair is two copies of rodent.xml in one world, 0.3 m apart
-pair = mjcf.compile_mjcf(os.path.join(REF, "assets/rodent.xml"), scale_factor=0.9, duplicate=(2, (0.0, 0.3, 0.0)), overrides=OPT)
+# BASELINE.json configs[3] / SURVEY Appendix C.3 variant (i): the geometry of assets/rodent_pair.xml (two replicas of the animal,
+# 114 floor contacts, 30 joint actuators per animal, no tendons) with the rodent env's rescale and solver options; the file's
+# actuator block is instantiated per replica (it names un-suffixed joints and is rejected by MuJoCo as committed) and
+# the stated list of inter-animal capsule-capsule pairs is opened (configs.RODENT_PAIR_ENV_ARGS)
+from brax_tracking_b200 import configs  # noqa: E402
+pair = mjcf.compile_mjcf(os.path.join(REF, "assets/rodent_pair.xml"), scale_factor=0.9, overrides=OPT, replicate_actuators=True,
+                         extra_pairs=configs.pair_geom_names(configs.RODENT_PAIR_ENV_ARGS))
 assets.save_model(pair, os.path.join(OUT, "rodent_pair.npz"))
 for n, m in (("rodent", rodent), ("fly_free", ff), ("fly_tethered", ft), ("rodent_pair", pair)):
     print(n, dict(nq=m.nq, nv=m.nv, nu=m.nu, na=m.na, nbody=m.nbody, ncon=int(m.pair_ncon.sum()), nM=m.nM, cone=m.cone,
