@@ -130,17 +130,26 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     n_envs = 64 * cores if args.ref_envs is None else args.ref_envs
-    # every "step" is a bounded sample: one control step over n_envs envs on all host threads
-    for _ in range(args.warmup):
-        cpu_port_run(args.model, min(n_envs, 2 * cores), 1, cores)
-    v, dt = cpu_port_run(args.model, n_envs, args.steps, cores)
-    sample = f"{n_envs} envs x {args.steps} control steps, oracle port (C, float32), {cores} threads"
+    # the real MJX env on the JAX CPU backend when it is importable (baseline/_ref) ...
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import run_cpu_baseline as rcb
+    real = rcb.run_mjx(min(n_envs, 1024), args.steps) if args.model == "rodent" else None
+    if real is not None:
+        v, dt, kind, sample, cores = real["value"], real["wall_s"], "reference", real["sample"], real["cores"]
+    else:
+        # ... else the oracle port.  Every "step" is a bounded sample: one control step over n_envs envs on all host threads
+        for _ in range(args.warmup):
+            cpu_port_run(args.model, min(n_envs, 2 * cores), 1, cores)
+        v, dt = cpu_port_run(args.model, n_envs, args.steps, cores)
+        kind = "port"
+        sample = f"{n_envs} envs x {args.steps} control steps, oracle port (C, float32), {cores} threads"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.model, args.envs), "sample": sample},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": workload_name(args.model, args.envs), "sample": sample,
+                   "same_config": False, "note": "a bounded sample of the per-environment-linear CPU path, not all 8192 environments"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
