@@ -241,6 +241,47 @@ def run_gpu(args):
         tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_dev, t_e2e = float(tt[0]), float(tt[1])
+    # ---------------- the two measurements that involve the learner / a fixed global batch, same JSON line:
+    #   strong: the SAME 8192 environments split over the N ranks (step only, no collective: per-rank launches shrink)
+    #   train : custom_ppo.train on 8192 envs per GPU with the train_fly.yaml hyper-parameters; NCCL gradient all-reduce per minibatch
+    strong = train_blk = None
+    if not args.no_extra:
+        del state, h_obs
+        gn = 8192
+        if gn % world == 0:
+            ns = gn // world
+            st2 = env.reset(parallel.shard_keys(prng.PRNGKey(0), gn, rank, world))
+            a2 = torch.from_numpy(np.tanh(rng.standard_normal((n_act, ns, m.nu))).astype(np.float32)).to(dev)
+            for i in range(Wm):
+                st2 = env.step(st2, a2[i % n_act])
+            ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+            barrier()
+            for i in range(K):
+                flush.zero_()
+                ev2[i][0].record()
+                st2 = env.step(st2, a2[i % n_act])
+                ev2[i][1].record()
+            barrier()
+            ts_ = torch.tensor([sum(a.elapsed_time(b) for a, b in ev2) / 1e3], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(ts_, op=dist.ReduceOp.MAX)
+            strong = {"value": gn * K / float(ts_[0]), "unit": UNIT, "global_envs": gn, "envs_per_gpu": ns, "ms_per_step": 1e3 * float(ts_[0]) / K,
+                      "scaling": "strong", "what": "step only, the same 8192 environments split over the ranks"}
+            del st2
+        from brax_tracking_b200 import ppo
+        tenv = presets.make_env(args.model, device=local)
+        per_epoch = []
+        tn = 8192
+        ppo.train(tenv, num_timesteps=3 * tn * world * 16 * 32, episode_length=tenv.episode_length, num_envs=tn * world, num_evals=4,
+                  learning_rate=3e-4, entropy_cost=1e-3, discounting=0.99, unroll_length=16, batch_size=tn * world, num_minibatches=32,
+                  num_updates_per_batch=16, normalize_observations=True, run_evals=False,
+                  progress_fn=lambda s_, mt: per_epoch.append(mt["training/device_sps"]))
+        if rank == 0:
+            train_blk = {"value": float(np.mean(per_epoch[1:])), "unit": UNIT, "envs_per_gpu": tn, "global_envs": tn * world, "scaling": "weak",
+                         "training_steps_timed": len(per_epoch) - 1, "env_steps_per_training_step": tn * world * 16 * 32,
+                         "what": "custom_ppo.train: rollout (policy inference + fused step, CUDA-graphed) + 16 x 32 minibatch updates "
+                                 "(TF32 cuBLAS MLPs, fused tanh-Normal loss terms, one NCCL all-reduce of the flat gradient per minibatch, "
+                                 "fused flat Adam); device time per epoch, max over ranks; train_fly.yaml hyper-parameters"}
     if rank == 0:
         total_env_steps = world * n * K
         value = total_env_steps / t_dev
@@ -264,6 +305,10 @@ def run_gpu(args):
                          "traffic": ncu_traffic(args.model), "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
                          "avg_launch_ms": 1e3 * avg_launch_s},
         }
+        if strong is not None:
+            line["strong"] = strong
+        if train_blk is not None:
+            line["train"] = train_blk
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             # bounded sample of the same workload: ~10-30 CPU-seconds (wall time x threads) on the box's host cores
@@ -290,6 +335,7 @@ def main():
     ap.add_argument("--model", default="rodent", choices=sorted(ALGO_BYTES))
     ap.add_argument("--ref-envs", type=int, default=None)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the strong-scaling and PPO-training blocks")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

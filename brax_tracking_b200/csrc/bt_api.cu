@@ -79,10 +79,17 @@ struct BtDeviceGuard {
   }
 
 static inline BtLaunchCfg cfg_for(const BtModel* m, int n_envs, void* stream) {
-  int ctas = (n_envs + m->warps - 1) / m->warps;
+  // Persistent CTAs of `warps` environments each.  A batch that does not fill every SM at the full width (a strong-scaling shard,
+  // an evaluation batch) is spread over ALL the SMs with narrower CTAs instead of leaving SMs idle: warps = ceil(n / SMs).
+  int warps = m->warps;
+  if ((int64_t)n_envs < (int64_t)m->max_ctas * m->warps) {
+    warps = (n_envs + m->max_ctas - 1) / m->max_ctas;
+    if (warps < 1) warps = 1;
+  }
+  int ctas = (n_envs + warps - 1) / warps;
   if (ctas > m->max_ctas) ctas = m->max_ctas;
   if (ctas < 1) ctas = 1;
-  BtLaunchCfg c = {ctas, m->warps * 32, m->smem_bytes, (cudaStream_t)stream};
+  BtLaunchCfg c = {ctas, warps * 32, (int)((size_t)m->dev.smem_floats * 4 * warps), (cudaStream_t)stream, warps};
   return c;
 }
 #define BT_LAUNCHED()                    \
@@ -198,7 +205,7 @@ int bt_reset(BtModel* m, int n_envs, const uint32_t* keys, int fixed_start_frame
   BT_ON_DEVICE(m);
   if (fixed_start_frame >= m->dev.clip_len) { snprintf(g_err, sizeof(g_err), "fixed_start_frame beyond the clip"); return BT_E_ARG; }
   BtResetArgs a = {keys, fixed_start_frame, state, obs, reward, done, metrics, info_f, info_i};
-  m->ops->reset(cfg_for(m, n_envs, stream), m->dev, n_envs, m->warps, a);
+  { BtLaunchCfg c = cfg_for(m, n_envs, stream); m->ops->reset(c, m->dev, n_envs, c.warps, a); }
   BT_LAUNCHED();
   return BT_OK;
 }
@@ -214,7 +221,7 @@ int bt_step(BtModel* m, int n_envs, const float* action, BtStatePtrs state, BtSt
   if (n_envs == 0) return BT_OK;
   BT_ON_DEVICE(m);
   BtStepArgs a = {action, state, first, first_obs, first_info_i, obs, reward, done, metrics, info_f, info_i};
-  m->ops->step(cfg_for(m, n_envs, stream), m->dev, n_envs, m->warps, a);
+  { BtLaunchCfg c = cfg_for(m, n_envs, stream); m->ops->step(c, m->dev, n_envs, c.warps, a); }
   BT_LAUNCHED();
   return BT_OK;
 }
@@ -224,7 +231,7 @@ int bt_physics_step(BtModel* m, int n_envs, const float* ctrl, BtStatePtrs state
   if (check_state(m, state, false)) return BT_E_ARG;
   if (n_envs == 0) return BT_OK;
   BT_ON_DEVICE(m);
-  m->ops->physics(cfg_for(m, n_envs, stream), m->dev, n_envs, m->warps, ctrl, state, n_substeps);
+  { BtLaunchCfg c = cfg_for(m, n_envs, stream); m->ops->physics(c, m->dev, n_envs, c.warps, ctrl, state, n_substeps); }
   BT_LAUNCHED();
   return BT_OK;
 }
@@ -234,7 +241,7 @@ int bt_pipeline_init(BtModel* m, int n_envs, BtStatePtrs state, void* stream) {
   if (check_state(m, state, false)) return BT_E_ARG;
   if (n_envs == 0) return BT_OK;
   BT_ON_DEVICE(m);
-  m->ops->physics(cfg_for(m, n_envs, stream), m->dev, n_envs, m->warps, nullptr, state, 0);
+  { BtLaunchCfg c = cfg_for(m, n_envs, stream); m->ops->physics(c, m->dev, n_envs, c.warps, nullptr, state, 0); }
   BT_LAUNCHED();
   return BT_OK;
 }
@@ -246,7 +253,7 @@ int bt_reward_obs(BtModel* m, int n_envs, const float* action, BtStatePtrs state
   if (n_envs == 0) return BT_OK;
   BT_ON_DEVICE(m);
   BtRewardArgs a = {action, state, info_i, obs, reward, done, metrics, info_f};
-  m->ops->reward(cfg_for(m, n_envs, stream), m->dev, n_envs, m->warps, a);
+  { BtLaunchCfg c = cfg_for(m, n_envs, stream); m->ops->reward(c, m->dev, n_envs, c.warps, a); }
   BT_LAUNCHED();
   return BT_OK;
 }
@@ -257,7 +264,7 @@ int bt_forward_debug(BtModel* m, int n_envs, const float* ctrl, BtStatePtrs stat
   if (check_state(m, state, false)) return BT_E_ARG;
   if (n_envs == 0) return BT_OK;
   BT_ON_DEVICE(m);
-  m->ops->debug(cfg_for(m, n_envs, stream), m->dev, n_envs, m->warps, ctrl, state, stop, scratch, cdist, niter);
+  { BtLaunchCfg c = cfg_for(m, n_envs, stream); m->ops->debug(c, m->dev, n_envs, c.warps, ctrl, state, stop, scratch, cdist, niter); }
   BT_LAUNCHED();
   return BT_OK;
 }

@@ -67,9 +67,36 @@ __global__ void __launch_bounds__(256) k_tanh_normal_bwd(int B, int T, int A, co
     go[A + a] = dscale * (s > 20.f ? 1.f : sigmoid(s));
   }
 }
+// optax.adam over ONE flat parameter buffer, fused with the 1 / world scale that completes lax.pmean of the all-reduced (summed)
+// gradient (custom_brax/custom_ppo.py:246-257): p, m, v, g are [n]; `step` is a device-resident float holding the number of
+// updates already applied (read by every thread, advanced by the caller on the stream after the launch), so that the launch
+// is capturable in a CUDA graph.  optax semantics: m_hat = m / (1 - b1^t), v_hat = v / (1 - b2^t), p -= lr m_hat / (sqrt(v_hat) + eps).
+__global__ void __launch_bounds__(256) k_flat_adam(int64_t n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, const float* __restrict__ step, float lr, float b1, float b2,
+                                                   float eps, float gscale) {
+  const float t = *step + 1.f;
+  const float c1 = 1.f / (1.f - powf(b1, t)), c2 = 1.f / (1.f - powf(b2, t));
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gscale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= lr * (mi * c1) / (sqrtf(vi * c2) + eps);
+  }
+}
 }  // namespace
 
 extern "C" {
+int bt_ppo_flat_adam(int64_t n, float* p, const float* g, float* m, float* v, const float* step, float lr, float b1, float b2,
+                     float eps, float gscale, void* stream) {
+  if (n < 0 || !p || !g || !m || !v || !step) return BT_E_ARG;
+  if (n == 0) return BT_OK;
+  const int64_t blocks = (n + 255) / 256;
+  k_flat_adam<<<(unsigned)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, (cudaStream_t)stream>>>(n, p, g, m, v, step, lr, b1, b2, eps, gscale);
+  return cudaGetLastError() == cudaSuccess ? BT_OK : BT_E_CUDA;
+}
+
 int bt_ppo_tanh_normal_fwd(int B, int T, int A, const float* logits, const float* raw, int64_t raw_sb, int64_t raw_st,
                            const float* noise, int64_t noise_sb, int64_t noise_st, float* lp, float* ent, int64_t out_sb,
                            int64_t out_st, void* stream) {

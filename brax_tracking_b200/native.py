@@ -26,7 +26,7 @@ STATE_FIELDS = ("qpos", "qvel", "act", "qacc_warmstart", "time", "xpos")
 # exported symbols, exactly as declared in include/bt_api.h
 SYMBOLS = ["bt_model_create", "bt_model_destroy", "bt_model_dims", "bt_model_launch", "bt_reset", "bt_step",
            "bt_physics_step", "bt_pipeline_init", "bt_reward_obs", "bt_forward_debug", "bt_last_error", "bt_launch_count",
-           "bt_ppo_tanh_normal_fwd", "bt_ppo_tanh_normal_bwd"]
+           "bt_ppo_tanh_normal_fwd", "bt_ppo_tanh_normal_bwd", "bt_ppo_flat_adam"]
 
 
 class StatePtrs(C.Structure):
@@ -91,6 +91,19 @@ def ppo_tanh_normal(logits, raw, noise, grads=None):
     _check(lib().bt_ppo_tanh_normal_bwd(B, T, A, p(logits), p(raw), *_bt_strides(raw), p(noise), *_bt_strides(noise), p(glp), p(gent),
                                         osb, ost, p(out), stream))
     return out
+
+
+def ppo_flat_adam(p, g, m, v, step, lr: float, b1: float, b2: float, eps: float, gscale: float):
+    """bt_ppo_flat_adam: one fused optax.adam update of the flat parameter buffer ``p`` from the flat (summed) gradient ``g`` scaled by
+    ``gscale`` (= 1 / world); ``step`` is a 0-dim CUDA float tensor (updates applied so far; advanced by the caller)."""
+    import torch
+    for t in (p, g, m, v):
+        if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32 and t.numel() == p.numel()):
+            raise ValueError("ppo_flat_adam: p, g, m, v must be contiguous float32 CUDA tensors of one size")
+    stream = C.c_void_p(torch.cuda.current_stream(p.device).cuda_stream)
+    _check(lib().bt_ppo_flat_adam(C.c_int64(p.numel()), C.c_void_p(p.data_ptr()), C.c_void_p(g.data_ptr()), C.c_void_p(m.data_ptr()),
+                                  C.c_void_p(v.data_ptr()), C.c_void_p(step.data_ptr()), C.c_float(lr), C.c_float(b1), C.c_float(b2),
+                                  C.c_float(eps), C.c_float(gscale), stream))
 
 
 class NativeModel:

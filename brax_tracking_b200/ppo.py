@@ -95,23 +95,25 @@ class RunningStatistics:
         self.std = torch.ones(size, dtype=torch.float32, device=device)
 
     def update(self, batch: torch.Tensor, world: int = 1):
-        """Parallel (Chan) update with the batch of every rank (pmap_axis_name='i' in the reference)."""
+        """Parallel (Chan) update with the batch of every rank (pmap_axis_name='i' in the reference, custom_ppo.py:323-327).
+        The three psums of the reference (count, sum of deviations, sum of squared deviations about the NEW mean) are taken
+        about the OLD mean instead, which every rank already has, so that they travel as ONE packed all-reduce of 2 D + 1 floats:
+        sum (b - mean')(b - mean) = S2 - (S1 / N') S1 with S1 = sum (b - mean), S2 = sum (b - mean)^2."""
         b = batch.reshape(-1, batch.shape[-1]).to(torch.float32)
-        n = torch.tensor(float(b.shape[0]), dtype=torch.float64, device=b.device)
-        if world > 1:
-            dist.all_reduce(n)
-        new_count = self.count + n
+        D = b.shape[1]
         diff = b - self.mean
-        upd = diff.sum(0)
+        packed = torch.empty(2 * D + 1, dtype=torch.float64, device=b.device)
+        packed[:D] = diff.sum(0, dtype=torch.float64)
+        packed[D:2 * D] = (diff * diff).sum(0, dtype=torch.float64)
+        packed[2 * D] = float(b.shape[0])
         if world > 1:
-            dist.all_reduce(upd)
-        mean = self.mean + (upd / new_count).to(torch.float32)
-        var_upd = (diff * (b - mean)).sum(0)
-        if world > 1:
-            dist.all_reduce(var_upd)
+            dist.all_reduce(packed)
+        s1, s2, n = packed[:D], packed[D:2 * D], packed[2 * D]
+        new_count = self.count + n
+        delta = s1 / new_count
         # in place: captured CUDA graphs (rollout policy) keep reading these tensors
-        self.summed_variance.add_(var_upd)
-        self.mean.copy_(mean)
+        self.summed_variance.add_((s2 - delta * s1).to(torch.float32))
+        self.mean.add_(delta.to(torch.float32))
         self.count.copy_(new_count)
         self.std.copy_(torch.sqrt(torch.clamp(self.summed_variance / new_count.to(torch.float32), min=0.0)).clamp(1e-6, 1e6))
 
@@ -233,30 +235,103 @@ class TrainingState:
     env_steps: int = 0
 
 
-def _bind_flat_grads(params) -> torch.Tensor:
-    """Every parameter's ``.grad`` becomes a view into ONE flat buffer (autograd accumulates into an existing ``.grad`` in
-    place), so that lax.pmean(grads, 'i') is a single NCCL all-reduce with no gather / scatter copies around it."""
-    flat = torch.zeros(sum(p.numel() for p in params), dtype=params[0].dtype, device=params[0].device)
+def _bind_flat(params) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Every parameter and every ``.grad`` becomes a view into ONE flat buffer each (autograd accumulates into an existing
+    ``.grad`` in place), so that lax.pmean(grads, 'i') is a single NCCL all-reduce with no gather / scatter copies around it and
+    optax.adam is a single fused pass over the buffers."""
+    n = sum(p.numel() for p in params)
+    flat_p = torch.empty(n, dtype=params[0].dtype, device=params[0].device)
+    flat_g = torch.zeros(n, dtype=params[0].dtype, device=params[0].device)
     off = 0
     for p in params:
-        n = p.numel()
-        p.grad = flat[off:off + n].view_as(p)
-        off += n
-    return flat
+        k = p.numel()
+        flat_p[off:off + k].copy_(p.data.reshape(-1))
+        p.data = flat_p[off:off + k].view_as(p)
+        p.grad = flat_g[off:off + k].view_as(p)
+        off += k
+    return flat_p, flat_g
 
 
-def train(environment, num_timesteps: int, episode_length: int, action_repeat: int = 1, num_envs: int = 1,
+class FlatAdam:
+    """optax.adam(learning_rate) (custom_ppo.py:233) over the flat parameter buffer: one fused kernel per update
+    (csrc/bt_ppo.cu::k_flat_adam) that also applies the 1 / world of the gradient mean; the update count lives on the device so the
+    update is capturable in a CUDA graph.  CPU tensors (unit tests) take the same formulas through torch ops."""
+
+    def __init__(self, flat_p, flat_g, lr, b1=0.9, b2=0.999, eps=1e-8):
+        self.p, self.g, self.lr, self.b1, self.b2, self.eps = flat_p, flat_g, float(lr), b1, b2, eps
+        self.m, self.v = torch.zeros_like(flat_p), torch.zeros_like(flat_p)
+        self.step_count = torch.zeros((), dtype=torch.float32, device=flat_p.device)
+
+    def step(self, gscale: float = 1.0):
+        if self.p.is_cuda:
+            native.ppo_flat_adam(self.p, self.g, self.m, self.v, self.step_count, self.lr, self.b1, self.b2, self.eps, gscale)
+        else:
+            t = self.step_count + 1.0
+            g = self.g * gscale
+            self.m.mul_(self.b1).add_(g, alpha=1 - self.b1)
+            self.v.mul_(self.b2).addcmul_(g, g, value=1 - self.b2)
+            self.p.sub_(self.lr * (self.m / (1 - self.b1 ** t)) / (torch.sqrt(self.v / (1 - self.b2 ** t)) + self.eps))
+        self.step_count.add_(1.0)
+
+    def state_dict(self):
+        return dict(m=self.m, v=self.v, step=self.step_count)
+
+    def load_state_dict(self, d):
+        self.m.copy_(d["m"]); self.v.copy_(d["v"]); self.step_count.copy_(d["step"])
+
+
+class Evaluator:
+    """brax.training.acting.Evaluator over brax's EvalWrapper (custom_ppo.py:442-449,484-489): ``num_eval_envs`` environments run
+    ONE episode each (``episode_length // action_repeat`` steps of the wrapped env); per environment the reward and every metric
+    are summed while its first episode is active.  Returns ``eval/episode_<name>`` (mean over environments; ``reward`` included),
+    ``eval/avg_episode_length``, ``eval/epoch_eval_time``, ``eval/sps``, ``eval/walltime`` merged with the training metrics."""
+
+    def __init__(self, eval_env, make_policy, num_eval_envs: int, episode_length: int, action_repeat: int, key, deterministic: bool = False):
+        self._env, self._make_policy, self._n = eval_env, make_policy, int(num_eval_envs)
+        self._steps = episode_length // action_repeat
+        self._key, self._det, self._walltime = np.asarray(key, dtype=np.uint32), deterministic, 0.0
+
+    def run_evaluation(self, training_metrics: Dict[str, float]) -> Dict[str, float]:
+        self._key, unroll_key = prng.split(self._key, 2)
+        env, t0 = self._env, time.time()
+        state = env.reset(prng.split(unroll_key, self._n))
+        act = self._make_policy(deterministic=self._det)
+        sums = {k: torch.zeros_like(state.reward) for k in ("reward", *state.metrics)}
+        active = torch.ones_like(state.reward)
+        ep_steps = torch.zeros_like(state.reward)
+        for _ in range(self._steps):
+            state = env.step(state, act(state.obs)[0].contiguous())
+            ep_steps = torch.where(active > 0, state.info["steps"], ep_steps)
+            sums["reward"] += state.reward * active
+            for k, v in state.metrics.items():
+                sums[k] += v * active
+            active = active * (1.0 - state.done)
+        out = {f"eval/episode_{k}": float(v.mean()) for k, v in sums.items()}
+        out.update({f"eval/episode_{k}_std": float(v.std(unbiased=False)) for k, v in sums.items()})
+        dt = time.time() - t0
+        self._walltime += dt
+        out.update({"eval/avg_episode_length": float(ep_steps.mean()), "eval/epoch_eval_time": dt,
+                    "eval/sps": self._steps * self._n / dt, "eval/walltime": self._walltime, **training_metrics})
+        return out
+
+
+def train(environment, num_timesteps: int, episode_length: int, action_repeat: int = 1, num_envs: int = 1, num_eval_envs: int = 128,
           learning_rate: float = 1e-4, entropy_cost: float = 1e-4, discounting: float = 0.9, seed: int = 0, unroll_length: int = 10,
           batch_size: int = 32, num_minibatches: int = 16, num_updates_per_batch: int = 2, num_evals: int = 1,
-          normalize_observations: bool = False, reward_scaling: float = 1.0, clipping_epsilon: float = 0.3, gae_lambda: float = 0.95,
+          num_resets_per_eval: int = 0, normalize_observations: bool = False, reward_scaling: float = 1.0,
+          clipping_epsilon: float = 0.3, gae_lambda: float = 0.95, deterministic_eval: bool = False,
           policy_hidden_layer_sizes: Sequence[int] = (256, 256), value_hidden_layer_sizes: Sequence[int] = (256, 256),
-          progress_fn: Callable[[int, Dict], None] = lambda *a: None, normalize_advantage: bool = True,
+          progress_fn: Callable[[int, Dict], None] = lambda *a: None, normalize_advantage: bool = True, eval_env=None,
           policy_params_fn: Callable[..., None] = lambda *a: None, restore_checkpoint_path: Optional[str] = None,
-          matmul_precision: str = "tf32", use_cuda_graph: bool = True):
-    """PPO training on the fused B200 step.  Returns (make_policy, params, metrics) like the reference.
+          checkpoint_dir: Optional[str] = None, run_evals: bool = True, matmul_precision: str = "tf32", use_cuda_graph: bool = True):
+    """PPO training on the fused B200 step.  Returns (make_policy, params, metrics) like the reference (custom_ppo.py:65-506).
 
-    ``matmul_precision``: "tf32" (default; what XLA's DEFAULT precision gives the reference's f32 MLPs on Ampere and later
-    GPUs) or "highest" (plain fp32 matmuls)."""
+    Beyond the reference's arguments: ``checkpoint_dir`` -- rank 0 writes ``<dir>/<env_steps>.pt`` (``save_checkpoint``: normaliser,
+    policy, value, optimiser, step count, sampling-generator state, environment state) after every evaluation and at the end
+    (the reference saves (normaliser, policy) from ``policy_params_fn``, main.py:136-139,332-333); ``restore_checkpoint_path``
+    resumes from such a file, continuing at its ``env_steps``; ``run_evals=False`` skips the Evaluator (benchmarks);
+    ``matmul_precision``: "tf32" (default; what XLA's DEFAULT precision gives the reference's f32 MLPs on Ampere and later GPUs)
+    or "highest" (plain fp32 matmuls)."""
     torch.backends.cuda.matmul.allow_tf32 = matmul_precision == "tf32"
     torch.backends.cudnn.allow_tf32 = matmul_precision == "tf32"
     world = dist.get_world_size() if dist.is_initialized() else 1
@@ -265,7 +340,9 @@ def train(environment, num_timesteps: int, episode_length: int, action_repeat: i
     assert num_envs % world == 0                                             # custom_ppo.py:199
     env_step_per_training_step = batch_size * unroll_length * num_minibatches * action_repeat
     num_evals_after_init = max(num_evals - 1, 1)
-    num_training_steps_per_epoch = int(np.ceil(num_timesteps / (num_evals_after_init * env_step_per_training_step)))
+    # custom_ppo.py:176-183: training steps per epoch, with the extra resets dividing the epoch
+    num_training_steps_per_epoch = int(np.ceil(num_timesteps / (num_evals_after_init * env_step_per_training_step
+                                                                * max(num_resets_per_eval, 1))))
 
     env = envs_mod.wrap(environment, episode_length=episode_length, action_repeat=action_repeat)
     device = environment._native._dev()
@@ -273,8 +350,10 @@ def train(environment, num_timesteps: int, episode_length: int, action_repeat: i
     # keys: PRNGKey(seed) -> (global, local); local -> (local, key_env, eval_key)   (custom_ppo.py:189-196)
     key = prng.PRNGKey(seed)
     global_key, local_key = prng.split(key, 2)
-    _, key_env, _ = prng.split(local_key, 3)
-    state = env.reset(parallel.shard_keys(key_env, num_envs, rank, world))
+    local_key, key_env, eval_key = prng.split(local_key, 3)
+    key_envs = prng.split(key_env, num_envs)                                 # custom_ppo.py:221
+    lo, hi = parallel.shard_bounds(num_envs, rank, world)
+    state = env.reset(key_envs[lo:hi])
     gen = torch.Generator(device=device)
     gen.manual_seed(int(global_key[1]) + 7919 * rank)
 
@@ -284,12 +363,16 @@ def train(environment, num_timesteps: int, episode_length: int, action_repeat: i
     value = MLP([obs_size, *value_hidden_layer_sizes, 1], in_align=32).to(device)
     obs_pad = policy.in_padded
     params = list(policy.parameters()) + list(value.parameters())
-    flat_grad = _bind_flat_grads(params)
+    flat_param, flat_grad = _bind_flat(params)
     grad_ptrs = [p.grad.data_ptr() for p in params]
-    opt = torch.optim.Adam(params, lr=learning_rate, eps=1e-8, capturable=device.type == "cuda")
+    opt = FlatAdam(flat_param, flat_grad, learning_rate, eps=1e-8)
     ts = TrainingState(policy, value, opt, RunningStatistics(obs_size, device))
     if restore_checkpoint_path is not None:
-        load_checkpoint(ts, restore_checkpoint_path)
+        blob = load_checkpoint(ts, restore_checkpoint_path)
+        if "rng_state" in blob and world == 1:
+            gen.set_state(blob["rng_state"].cpu())
+        if "env_state" in blob and blob["env_state"]["qpos"].shape == state.pipeline_state["qpos"].shape:
+            restore_env_state(state, blob)
     norm = ts.normalizer.normalize if normalize_observations else (lambda x: x)
 
     def make_policy(deterministic: bool = False):
@@ -333,9 +416,8 @@ def train(environment, num_timesteps: int, episode_length: int, action_repeat: i
         flat_grad.zero_()
         loss.backward()
         if world > 1:
-            dist.all_reduce(flat_grad)                                       # lax.pmean(grads, 'i'): one all-reduce, in place
-            flat_grad.div_(world)
-        opt.step()
+            dist.all_reduce(flat_grad)       # lax.pmean(grads, 'i'): ONE all-reduce (sum), in place; the 1 / world rides in the Adam pass
+        opt.step(1.0 / world)
         return lm
 
     def run_minibatch():
@@ -343,13 +425,19 @@ def train(environment, num_timesteps: int, episode_length: int, action_repeat: i
             return minibatch_update()
         if graph["g"] is None and not graph["tried"]:
             graph["tried"] = True
-            try:  # three eager (real) updates on a side stream, then capture the fourth
+            ok = True
+            try:
+                # warm-up on a side stream (cuBLAS handles, autograd buffers) with the parameters and the optimiser state put back
+                # afterwards: only the replay applies this minibatch's update, as in the eager schedule
+                snap = [t.clone() for t in (flat_param, opt.m, opt.v, opt.step_count)]
                 side = torch.cuda.Stream(device)
                 side.wait_stream(torch.cuda.current_stream(device))
                 with torch.cuda.stream(side):
                     for _ in range(3):
                         minibatch_update()
                 torch.cuda.current_stream(device).wait_stream(side)
+                for t, c in zip((flat_param, opt.m, opt.v, opt.step_count), snap):
+                    t.copy_(c)
                 assert [p.grad.data_ptr() for p in params] == grad_ptrs, "autograd replaced a flat gradient view"
                 g = torch.cuda.CUDAGraph()
                 # the NCCL all-reduce is captured with the update (world > 1); thread-local capture mode because the process
@@ -357,12 +445,15 @@ def train(environment, num_timesteps: int, episode_length: int, action_repeat: i
                 with torch.cuda.graph(g, capture_error_mode="thread_local" if world > 1 else "global"):
                     graph["lm"] = minibatch_update()
                 graph["g"] = g
-                g.replay()  # capture only records: this minibatch's update runs now
-                return graph["lm"]
             except Exception as e:  # pragma: no cover - capture is an optimisation, never a requirement
                 print(f"[ppo] CUDA graph capture of the minibatch update failed ({e!r}); running eagerly", flush=True)
+                ok = False
+            if world > 1:   # every rank replays or every rank runs eagerly: the all-reduce counts must match
+                flag = torch.tensor([1.0 if ok else 0.0], device=device)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                ok = bool(flag.item() > 0)
+            if not ok:
                 graph["g"] = None
-                return minibatch_update()
         if graph["g"] is None:
             return minibatch_update()
         graph["g"].replay()
@@ -416,63 +507,125 @@ def train(environment, num_timesteps: int, episode_length: int, action_repeat: i
             v.copy_(ubuf[k])
         return state
 
+    def training_step(state):
+        # ---- rollout: acting.generate_unroll x n_unrolls (custom_ppo.py:296-314)
+        for u in range(n_unrolls):
+            state = run_unroll(state, u)
+        # [n_unrolls, T, n, ...] -> [n_unrolls * n, T, ...]  (custom_ppo.py:316-320)
+        for k, v in buf.items():
+            dst = data[k].view(n_unrolls, n_local, *data[k].shape[1:])
+            (dst[..., :obs_size] if "observation" in k else dst).copy_(v.transpose(1, 2))
+        if normalize_observations:
+            ts.normalizer.update(buf["observation"], world)                  # custom_ppo.py:323-327
+            for k in ("observation", "next_observation"):
+                data[k][..., :obs_size].sub_(ts.normalizer.mean).div_(ts.normalizer.std)
+        # ---- SGD: num_updates_per_batch x num_minibatches (custom_ppo.py:250-284,329-334)
+        lm = None
+        for _ in range(num_updates_per_batch):
+            perm = torch.randperm(B, device=device, generator=gen)
+            for mb in perm.reshape(num_minibatches, -1):
+                mb_idx.copy_(mb)
+                mb_noise.normal_(generator=gen)
+                lm = run_minibatch()
+        ts.env_steps += env_step_per_training_step
+        return state, lm
+
+    def checkpoint(state):
+        if checkpoint_dir is not None and rank == 0:
+            import os
+            os.makedirs(checkpoint_dir, exist_ok=True)
+            save_checkpoint(ts, os.path.join(checkpoint_dir, f"{ts.env_steps}.pt"), env_state=state, rng_state=gen.get_state())
+
+    evaluator = None
+    if run_evals and rank == 0:
+        # custom_ppo.py:430-449: the eval env is the same env under the same wrappers (brax adds its EvalWrapper inside Evaluator)
+        ev_base = eval_env if eval_env is not None else environment
+        ev_wrapped = ev_base if isinstance(ev_base, envs_mod.AutoResetWrapperTracking) else envs_mod.wrap(ev_base, episode_length=episode_length, action_repeat=action_repeat)
+        evaluator = Evaluator(ev_wrapped, make_policy, num_eval_envs, episode_length, action_repeat, eval_key, deterministic_eval)
+
     metrics: Dict[str, float] = {}
+    if evaluator is not None and num_evals > 1 and ts.env_steps == 0:       # initial eval (custom_ppo.py:452-459)
+        metrics = evaluator.run_evaluation({})
+        progress_fn(0, metrics)
     t_start = time.time()
-    for it in range(num_evals_after_init):
+    ev0, ev1 = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) if device.type == "cuda" else (None, None)
+    while ts.env_steps < num_timesteps:                                      # (a restored run continues at its env_steps)
         t0 = time.time()
-        ep_reward = 0.0
-        for _ in range(num_training_steps_per_epoch):
-            # ---- rollout: acting.generate_unroll x n_unrolls (custom_ppo.py:296-314)
-            for u in range(n_unrolls):
-                state = run_unroll(state, u)
-            ep_reward = float(buf["reward"].mean())
-            # [n_unrolls, T, n, ...] -> [n_unrolls * n, T, ...]  (custom_ppo.py:316-320)
-            for k, v in buf.items():
-                dst = data[k].view(n_unrolls, n_local, *data[k].shape[1:])
-                (dst[..., :obs_size] if "observation" in k else dst).copy_(v.transpose(1, 2))
-            if normalize_observations:
-                ts.normalizer.update(buf["observation"], world)              # custom_ppo.py:323-327
-                for k in ("observation", "next_observation"):
-                    data[k][..., :obs_size].sub_(ts.normalizer.mean).div_(ts.normalizer.std)
-            # ---- SGD: num_updates_per_batch x num_minibatches (custom_ppo.py:250-284,329-334)
-            for _ in range(num_updates_per_batch):
-                perm = torch.randperm(B, device=device, generator=gen)
-                for mb in perm.reshape(num_minibatches, -1):
-                    mb_idx.copy_(mb)
-                    mb_noise.normal_(generator=gen)
-                    lm = run_minibatch()
-            ts.env_steps += env_step_per_training_step
-        torch.cuda.synchronize(device)
+        lm, n_steps = None, 0
+        if ev0 is not None:
+            ev0.record()
+        for _ in range(max(num_resets_per_eval, 1)):
+            for _ in range(num_training_steps_per_epoch):
+                state, lm = training_step(state)
+                n_steps += 1
+            if num_resets_per_eval > 0:                                       # custom_ppo.py:476-480: fresh keys, host-side reset
+                key_envs = np.stack([prng.split(k, 2)[0] for k in key_envs])
+                state = env.reset(key_envs[lo:hi])
+        if ev1 is not None:
+            ev1.record()
+            torch.cuda.synchronize(device)
+            dev_s = ev0.elapsed_time(ev1) / 1e3                               # device time of the epoch ...
+            if world > 1:
+                tt = torch.tensor([dev_s], dtype=torch.float64, device=device)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)                     # ... max over ranks
+                dev_s = float(tt[0])
+        else:
+            dev_s = time.time() - t0
         dt = time.time() - t0
-        sps = num_training_steps_per_epoch * env_step_per_training_step / dt  # custom_ppo.py:373-377
-        metrics = {"training/sps": sps, "training/walltime": time.time() - t_start, "training/mean_step_reward": ep_reward,
-                   **{f"training/{k}": float(v) for k, v in lm.items()}}
+        sps = n_steps * env_step_per_training_step / dt                       # custom_ppo.py:373-377
+        training_metrics = {"training/sps": sps, "training/walltime": time.time() - t_start, "training/device_sps": n_steps * env_step_per_training_step / dev_s,
+                            "training/mean_step_reward": float(buf["reward"].mean()), **{f"training/{k}": float(v) for k, v in lm.items()}}
+        metrics = evaluator.run_evaluation(training_metrics) if evaluator is not None else training_metrics
+        if world > 1:
+            dist.barrier()                                                    # the other ranks wait for rank 0's evaluation
+        checkpoint(state)
         if rank == 0:
             progress_fn(ts.env_steps, metrics)
             policy_params_fn(ts.env_steps, make_policy, (ts.normalizer.state_dict(), policy.state_dict()))
+    train.last_state = (ts, state)   # for tests / tools: the final training state and env state
     return make_policy, (ts.normalizer.state_dict(), policy.state_dict()), metrics
 
 
 # ---------------------------------------------------------------------------------------------- checkpoints
-def save_checkpoint(ts: TrainingState, path: str, env_state=None) -> None:
-    """Symmetric save/restore of (normalizer, policy, value, optimizer, env_steps[, env state]) -- the reference saves only
-    (normalizer, policy) and restores through a different format."""
+_ENV_RAW_KEYS = ("obs", "reward", "done", "metrics", "info_f", "info_i", "first_obs", "first_info_i")
+
+
+def save_checkpoint(ts: TrainingState, path: str, env_state=None, rng_state=None) -> None:
+    """Symmetric save / restore of (normalizer, policy, value, optimizer, env_steps[, sampling-generator state, env state]) -- the
+    reference saves only (normalizer, policy) through ``policy_params_fn`` (main.py:136-139,332-333) and restores through a
+    different format (custom_ppo.py:411-423).  Plain tensors / numbers only: loads with ``weights_only=True``."""
     blob = dict(normalizer=ts.normalizer.state_dict(), policy=ts.policy.state_dict(), value=ts.value.state_dict(),
-                optimizer=ts.optimizer.state_dict(), env_steps=ts.env_steps)
+                optimizer=ts.optimizer.state_dict(), env_steps=int(ts.env_steps))
+    if rng_state is not None:
+        blob["rng_state"] = rng_state.clone()
     if env_state is not None:
         blob["env_state"] = {k: v.clone() for k, v in env_state.pipeline_state.items()}
-        blob["env_raw"] = {k: (v.clone() if torch.is_tensor(v) else {kk: vv.clone() for kk, vv in v.items()}) for k, v in env_state._raw.items()}
-    torch.save(blob, path)
+        blob["env_first"] = {k: v.clone() for k, v in env_state._raw["first"].items()} if "first" in env_state._raw else {}
+        blob["env_raw"] = {k: env_state._raw[k].clone() for k in _ENV_RAW_KEYS if k in env_state._raw}
+    tmp = path + ".tmp"
+    torch.save(blob, tmp)
+    import os
+    os.replace(tmp, path)                                                     # a killed run never leaves a truncated checkpoint
 
 
 def load_checkpoint(ts: TrainingState, path: str) -> dict:
-    blob = torch.load(path, map_location=ts.normalizer.mean.device, weights_only=False)
+    blob = torch.load(path, map_location=ts.normalizer.mean.device, weights_only=True)
     ts.normalizer.load_state_dict(blob["normalizer"])
-    ts.policy.load_state_dict(blob["policy"])
+    ts.policy.load_state_dict(blob["policy"])                                 # (in place: the parameters stay views of the flat buffer)
     ts.value.load_state_dict(blob["value"])
     ts.optimizer.load_state_dict(blob["optimizer"])
     ts.env_steps = int(blob["env_steps"])
     return blob
+
+
+def restore_env_state(state, blob) -> None:
+    """Puts a checkpointed environment state back into a freshly reset ``State`` of the same batch size, in place."""
+    for k, v in blob["env_state"].items():
+        state.pipeline_state[k].copy_(v)
+    for k, v in blob.get("env_first", {}).items():
+        state._raw["first"][k].copy_(v)
+    for k, v in blob["env_raw"].items():
+        state._raw[k].copy_(v)
 
 
 # ---------------------------------------------------------------------------------------------- evaluation rollout

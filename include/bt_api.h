@@ -19,6 +19,7 @@
  *   bt_pipeline_init  <- PipelineEnv.pipeline_init = mjx.forward (envs/fruitfly.py:477)
  *   bt_reward_obs     <- the part of env.step after pipeline_step (envs/fruitfly.py:502-596, _get_obs :598-646)
  *   bt_ppo_tanh_normal_fwd / _bwd <- the policy terms of brax compute_ppo_loss (custom_brax/custom_ppo.py:250-284)
+ *   bt_ppo_flat_adam  <- optax.adam + the mean of lax.pmean(grads) (custom_brax/custom_ppo.py:233,246-257)
  *   bt_forward_debug  <- no reference counterpart: dumps on-chip intermediates for the parity tests
  */
 #ifndef BT_API_H_
@@ -94,6 +95,11 @@ int bt_ppo_tanh_normal_fwd(int B, int T, int A, const float* logits, const float
 int bt_ppo_tanh_normal_bwd(int B, int T, int A, const float* logits, const float* raw, int64_t raw_sb, int64_t raw_st,
                            const float* noise, int64_t noise_sb, int64_t noise_st, const float* glp, const float* gent,
                            int64_t out_sb, int64_t out_st, float* glogits, void* stream);
+
+/* optax.adam on a flat parameter buffer fused with the 1/world scale of lax.pmean (custom_brax/custom_ppo.py:233,246-257): p, g,
+   m, v are [n] device floats, `step` a device float with the number of updates already applied (the caller advances it). */
+int bt_ppo_flat_adam(int64_t n, float* p, const float* g, float* m, float* v, const float* step, float lr, float b1, float b2,
+                     float eps, float gscale, void* stream);
 
 const char* bt_last_error(void);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */

@@ -268,36 +268,46 @@ def test_poisoned_scratch_and_scheduling_invariance():
                 assert np.array_equal(ref_out[k], out[k], equal_nan=True), (name, label, k)
 
 
+PPO_KW = dict(learning_rate=3e-4, entropy_cost=1e-3, discounting=0.99, unroll_length=4, batch_size=256, num_minibatches=4,
+              num_updates_per_batch=2, normalize_observations=True, num_eval_envs=16)
+
+
 def test_ppo_loop_runs_on_the_fused_step(tmp_path):
-    """configs[4] in miniature: two PPO training steps on 256 rodent envs; params move, metrics finite, checkpoint round-trips."""
+    """configs[4] in miniature: PPO training steps on 256 rodent envs; params move, training + Evaluator metrics finite
+    (custom_ppo.py:442-449,484-489), the initial eval is reported at step 0, eval rollouts are deterministic when asked."""
     import torch
     from brax_tracking_b200 import envs, ppo
     m, cfg, clip, _ = common.setup("rodent")
     env = envs.RodentSingleClip(clip, mj_model=m)
     seen = []
-    mk, params, metrics = ppo.train(env, num_timesteps=2 * 256 * 4 * 4, episode_length=cfg["episode_length"], num_envs=256, num_evals=2,
-                                    learning_rate=3e-4, entropy_cost=1e-3, discounting=0.99, unroll_length=4, batch_size=256,
-                                    num_minibatches=4, num_updates_per_batch=2, normalize_observations=True,
-                                    progress_fn=lambda s, mt: seen.append((s, mt)))
-    assert seen and seen[-1][0] >= 2 * 256 * 4 * 4
+    S = 256 * 4 * 4
+    mk, params, metrics = ppo.train(env, num_timesteps=2 * S, episode_length=cfg["episode_length"], num_envs=256, num_evals=3,
+                                    deterministic_eval=True, progress_fn=lambda s, mt: seen.append((s, mt)), **PPO_KW)
+    assert [s for s, _ in seen] == [0, S, 2 * S]                              # initial eval + one per epoch
+    assert "eval/episode_reward" in seen[0][1] and "training/sps" not in seen[0][1]
+    for k in ("eval/episode_reward", "eval/episode_pos_reward", "eval/avg_episode_length", "eval/sps", "training/sps", "training/v_loss"):
+        assert np.isfinite(metrics[k]), k
+    assert 1 <= metrics["eval/avg_episode_length"] <= cfg["episode_length"]
     assert all(np.isfinite(v) for v in metrics.values()), metrics
     act = mk(deterministic=True)
     a, raw, logits = act(torch.zeros(3, env.observation_size, device="cuda"))
     assert a.shape == (3, env.action_size) and torch.isfinite(a).all() and float(a.abs().max()) <= 1.0
-    assert float(params[0]["count"]) == 2 * 256 * 4 * 4
+    assert float(params[0]["count"]) == 2 * S
     # the CUDA-graph replays (unroll, minibatch update) compute what the eager loop computes: same seed, same draws, ONE
     # training step (the rollout runs on the initial policy in both; later steps amplify rounding through the contacts)
     one = {}
     for use_graph in (True, False):
         e = envs.RodentSingleClip(clip, mj_model=m)
-        one[use_graph] = ppo.train(e, num_timesteps=256 * 4 * 4, episode_length=cfg["episode_length"], num_envs=256, num_evals=2,
-                                   learning_rate=3e-4, entropy_cost=1e-3, discounting=0.99, unroll_length=4, batch_size=256,
-                                   num_minibatches=4, num_updates_per_batch=2, normalize_observations=True, use_cuda_graph=use_graph)[2]
+        one[use_graph] = ppo.train(e, num_timesteps=S, episode_length=cfg["episode_length"], num_envs=256, num_evals=2, run_evals=False,
+                                   use_cuda_graph=use_graph, **PPO_KW)[2]
+        one[(use_graph, "p")] = ppo.train.last_state[0].optimizer.p.clone()
     g_, e_ = one[True], one[False]
     assert abs(g_["training/mean_step_reward"] - e_["training/mean_step_reward"]) < 1e-4 * abs(e_["training/mean_step_reward"]), (g_, e_)
-    # (parameters are not compared: the first Adam steps move every weight by ~lr whatever its gradient's size, so weights
-    # with near-zero gradients amplify rounding differences to the size of the update itself)
     assert abs(g_["training/v_loss"] - e_["training/v_loss"]) < 0.05 * abs(e_["training/v_loss"]), (g_, e_)
+    # graph warm-up no longer applies extra Adam steps to the first minibatch (ADVICE r1): the first Adam steps move every weight by
+    # ~lr, so three extra updates would show as ~1e-3 differences; rounding differences between replay and eager stay far below
+    dp = (one[(True, "p")] - one[(False, "p")]).abs()
+    assert float(dp.median()) < 1e-5 and float(ppo.train.last_state[0].optimizer.step_count) == 8, (float(dp.median()), float(dp.max()))
     # evaluation rollout from frame 0 (main.py:136-258) + device FK for clip preprocessing (preprocess.py:144-204)
     tr = ppo.evaluate_rollout(env, act, common.jax_keys(4, seed=2), num_steps=10)
     assert tr["reward"].shape == (10, 4) and np.isfinite(tr["reward"]).all()
@@ -307,6 +317,34 @@ def test_ppo_loop_runs_on_the_fused_step(tmp_path):
     c_dev = preprocess.process_clip(q, m, kinematics=preprocess.device_kinematics(env._native))
     c_host = preprocess.process_clip(q, m)
     np.testing.assert_allclose(c_dev.body_positions, c_host.body_positions, atol=2e-6)
+
+
+def test_checkpoint_save_restore_continue(tmp_path):
+    """main.py:136-139,332-333 / custom_ppo.py:411-423 made symmetric: a run that saves after its first epoch, restored into a
+    fresh process state and continued, ends where the uninterrupted run ends (parameters, optimiser moments, normaliser, env
+    state, step count)."""
+    import torch
+    from brax_tracking_b200 import envs, ppo
+    m, cfg, clip, _ = common.setup("rodent")
+    S = 256 * 4 * 4
+    kw = dict(episode_length=cfg["episode_length"], num_envs=256, num_evals=3, run_evals=False, **PPO_KW)
+    d_a, d_b = str(tmp_path / "a"), str(tmp_path / "b")
+    ppo.train(envs.RodentSingleClip(clip, mj_model=m), num_timesteps=2 * S, checkpoint_dir=d_a, **kw)
+    import os
+    assert sorted(os.listdir(d_a)) == [f"{S}.pt", f"{2 * S}.pt"]
+    ppo.train(envs.RodentSingleClip(clip, mj_model=m), num_timesteps=2 * S, checkpoint_dir=d_b, restore_checkpoint_path=os.path.join(d_a, f"{S}.pt"), **kw)
+    assert os.listdir(d_b) == [f"{2 * S}.pt"]                                 # continued at S, not restarted at 0
+    A = torch.load(os.path.join(d_a, f"{2 * S}.pt"), weights_only=True)
+    Bc = torch.load(os.path.join(d_b, f"{2 * S}.pt"), weights_only=True)
+    assert A["env_steps"] == Bc["env_steps"] == 2 * S and float(A["optimizer"]["step"]) == float(Bc["optimizer"]["step"]) == 16
+    assert torch.equal(A["normalizer"]["count"], Bc["normalizer"]["count"])
+    for grp in ("policy", "value"):
+        for k in A[grp]:
+            torch.testing.assert_close(A[grp][k], Bc[grp][k], rtol=0, atol=2e-6, msg=f"{grp}.{k}")
+    torch.testing.assert_close(A["optimizer"]["m"], Bc["optimizer"]["m"], rtol=0, atol=1e-6)
+    torch.testing.assert_close(A["normalizer"]["mean"], Bc["normalizer"]["mean"], rtol=0, atol=1e-6)
+    assert torch.equal(A["env_raw"]["info_i"], Bc["env_raw"]["info_i"])      # same frames / counters in every environment
+    torch.testing.assert_close(A["env_state"]["qpos"], Bc["env_state"]["qpos"], rtol=0, atol=1e-4)
 
 
 def test_fused_tanh_normal_terms_match_the_torch_formulas():

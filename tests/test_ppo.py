@@ -95,3 +95,44 @@ def _check_linear_grads(net, x, tgt, tol):
     ((h - tgt) ** 2).sum().backward()
     for g, p in zip(got, net.parameters()):
         np.testing.assert_allclose(g.numpy(), p.grad.numpy(), rtol=tol, atol=tol * float(p.grad.abs().max()))
+
+
+def test_flat_adam_matches_torch_adam_and_keeps_parameters_as_views():
+    """FlatAdam (optax.adam semantics, custom_ppo.py:233) on the CPU path against torch.optim.Adam; parameters and gradients are
+    views of the two flat buffers, so a module's load_state_dict / backward keep writing into them."""
+    torch.manual_seed(0)
+    net_a, net_b = ppo.MLP([5, 8, 3]), ppo.MLP([5, 8, 3])
+    net_b.load_state_dict(net_a.state_dict())
+    params = list(net_a.parameters())
+    flat_p, flat_g = ppo._bind_flat(params)
+    opt_a = ppo.FlatAdam(flat_p, flat_g, 3e-3)
+    opt_b = torch.optim.Adam(net_b.parameters(), lr=3e-3, eps=1e-8)
+    x, y = torch.randn(16, 5), torch.randn(16, 3)
+    for _ in range(5):
+        flat_g.zero_()
+        (2.0 * ((net_a(x) - y) ** 2).mean()).backward()      # "summed over 2 ranks" gradient ...
+        opt_a.step(0.5)                                       # ... averaged inside the update
+        opt_b.zero_grad()
+        ((net_b(x) - y) ** 2).mean().backward()
+        opt_b.step()
+    for pa, pb in zip(net_a.parameters(), net_b.parameters()):
+        np.testing.assert_allclose(pa.detach().numpy(), pb.detach().numpy(), atol=2e-6)
+        assert pa.data.data_ptr() >= flat_p.data_ptr() and pa.data.data_ptr() < flat_p.data_ptr() + 4 * flat_p.numel()
+    assert float(opt_a.step_count) == 5
+
+
+def test_packed_running_statistics_update_equals_the_three_psum_form():
+    """One packed all-reduce (sums about the old mean) == brax's count / mean-update / variance-update psums."""
+    rng = np.random.default_rng(3)
+    rs = ppo.RunningStatistics(4, torch.device("cpu"))
+    mean = np.zeros(4); sv = np.zeros(4); count = 0.0
+    for _ in range(4):
+        b = (rng.standard_normal((50, 4)) * [1, 5, 0.1, 2] + [0, 10, -3, 100]).astype(np.float32)
+        rs.update(torch.from_numpy(b))
+        n = count + b.shape[0]                                # brax running_statistics.update
+        d_old = b - mean
+        mean = mean + d_old.sum(0) / n
+        sv = sv + (d_old * (b - mean)).sum(0)
+        count = n
+    np.testing.assert_allclose(rs.mean.numpy(), mean, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(rs.summed_variance.numpy(), sv, rtol=1e-4)

@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -40 > gpurun_out/pytest_${TAG}.log; tail -25 gpurun_out/pytest_${TAG}.log
 for model in ${@:-rodent}; do
   envs=8192; [ "$model" = "rodent_pair" ] && envs=4096
-  python bench.py --steps 30 --warmup 5 --model $model --envs $envs $( [ "$model" != "rodent" ] && echo --no-cpu ) > gpurun_out/bench_${TAG}_${model}.json 2> gpurun_out/bench_${TAG}_${model}.err
+  python bench.py --steps 30 --warmup 5 --model $model --envs $envs $( [ "$model" != "rodent" ] && echo "--no-cpu --no-extra" ) > gpurun_out/bench_${TAG}_${model}.json 2> gpurun_out/bench_${TAG}_${model}.err
   python - <<PY
 import json
 l=json.load(open("gpurun_out/bench_${TAG}_${model}.json"))

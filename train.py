@@ -23,7 +23,7 @@ from brax_tracking_b200 import ppo, presets  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--model", default="rodent", choices=["rodent", "fly_free", "fly_tethered"])
+    ap.add_argument("--model", default="rodent", choices=["rodent", "fly_free", "fly_tethered", "rodent_pair"])
     ap.add_argument("--num-envs", type=int, default=8192)
     ap.add_argument("--num-timesteps", type=int, default=10_000_000)
     ap.add_argument("--num-evals", type=int, default=5)
@@ -32,7 +32,11 @@ def main():
     ap.add_argument("--num-updates-per-batch", type=int, default=16)
     ap.add_argument("--unroll-length", type=int, default=16)
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--checkpoint", default=None)
+    ap.add_argument("--checkpoint", default=None, help="resume from this file (written by --checkpoint-dir)")
+    ap.add_argument("--checkpoint-dir", default=None, help="rank 0 saves <dir>/<env_steps>.pt after every evaluation and at the end")
+    ap.add_argument("--num-eval-envs", type=int, default=128)
+    ap.add_argument("--deterministic-eval", action="store_true")
+    ap.add_argument("--no-eval", action="store_true")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -47,7 +51,9 @@ def main():
     ppo.train(env, num_timesteps=a.num_timesteps, episode_length=env.episode_length, num_envs=a.num_envs, num_evals=a.num_evals,
               learning_rate=3e-4, entropy_cost=1e-3, discounting=0.99, seed=a.seed, unroll_length=a.unroll_length,
               batch_size=a.batch_size or a.num_envs, num_minibatches=a.num_minibatches, num_updates_per_batch=a.num_updates_per_batch,
-              normalize_observations=True, reward_scaling=1.0, progress_fn=progress, restore_checkpoint_path=a.checkpoint)
+              normalize_observations=True, reward_scaling=1.0, progress_fn=progress, restore_checkpoint_path=a.checkpoint,
+              checkpoint_dir=a.checkpoint_dir, num_eval_envs=a.num_eval_envs, deterministic_eval=a.deterministic_eval,
+              run_evals=not a.no_eval)
     if world > 1:
         dist.destroy_process_group()
 
