@@ -12,7 +12,7 @@ rows = list(csv.reader(src.splitlines()))
 hdr = rows[1]; ci = {h: i for i, h in enumerate(hdr)}; ins = rows[2:]
 dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout
 # function ranges in bt_impl.h
-impl = open("/root/repo/brax_tracking_b200/csrc/bt_impl.h").read().splitlines()
+impl = open(sys.argv[3] if len(sys.argv) > 3 else "/root/repo/brax_tracking_b200/csrc/bt_impl.h").read().splitlines()
 funcs = []
 for n, l in enumerate(impl, 1):
     mm = re.match(r"\s+(?:static )?(?:template <[^>]*>\s*)?BT_DEV\s+[\w:<>\*&\s]+?\s+(\w+)\(", l)

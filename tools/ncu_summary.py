@@ -14,13 +14,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1]
 model = sys.argv[2] if len(sys.argv) > 2 else "rodent"
 variant = sys.argv[3] if len(sys.argv) > 3 else "3_1"
-rep = os.path.join(ROOT, "gpurun_out", f"prof_{tag}.ncu-rep")
+rep = os.path.join(ROOT, "gpurun_out", f"prof_{tag}_{model}.ncu-rep")
+if not os.path.exists(rep):
+    rep = os.path.join(ROOT, "gpurun_out", f"prof_{tag}.ncu-rep")
 obj = os.path.join(ROOT, "brax_tracking_b200", "build", f"tu_step_{variant}.o")
 tmp = "/tmp/bt_cubin"
 os.makedirs(tmp, exist_ok=True)
 subprocess.run(["cuobjdump", "-xelf", "all", obj], cwd=tmp, check=True, capture_output=True)
 cubin = os.path.join(tmp, f"tu_step_{variant}.sm_100a.cubin")
-out = lambda name: os.path.join(ROOT, "profiles", f"{tag}_step_kernel_{name}.txt")
+out = lambda name: os.path.join(ROOT, "profiles", f"{tag}_{model}_step_kernel_{name}.txt")
 
 
 def run(cmd, path):
@@ -64,7 +66,7 @@ tr = to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum")
 tp = os.path.join(ROOT, "profiles", "traffic.json")
 t = json.load(open(tp)) if os.path.exists(tp) else {}
 t[model] = tr
-t["source"] = (f"profiles/{tag}: ncu --set full --clock-control none, bt_k_step_{variant}, dram__bytes_read.sum + "
-               "dram__bytes_write.sum of one launch, 8192 envs")
+t.setdefault("sources", {})[model] = (f"profiles/{tag}_{model}_*: ncu --set full --clock-control none, bt_k_step_{variant}, "
+                                       "dram__bytes_read.sum + dram__bytes_write.sum of one launch")
 json.dump(t, open(tp, "w"))
 print("traffic", tr, "->", tp)
