@@ -179,7 +179,7 @@ void bt_model_destroy(BtModel* m) {
 int bt_model_dims(const BtModel* m, int* dims) {
   if (!m || !dims) { snprintf(g_err, sizeof(g_err), "null argument"); return BT_E_ARG; }
   dims[0] = m->dev.nq; dims[1] = m->dev.nv; dims[2] = m->dev.nu; dims[3] = m->dev.na; dims[4] = m->dev.nbody;
-  dims[5] = m->dev.obs_size; dims[6] = m->dev.smem_floats; dims[7] = m->dev.ncon;
+  dims[5] = m->dev.obs_size; dims[6] = m->dev.smem_floats; dims[7] = m->dev.ncon; dims[8] = m->dev.n_clips;
   return BT_OK;
 }
 
@@ -198,13 +198,13 @@ static int check_state(const BtModel* m, const BtStatePtrs& s, bool need_xpos) {
 }
 
 int bt_reset(BtModel* m, int n_envs, const uint32_t* keys, int fixed_start_frame, BtStatePtrs state, float* obs, float* reward, float* done,
-             float* metrics, float* info_f, int32_t* info_i, void* stream) {
+             float* metrics, float* info_f, int32_t* info_i, int32_t* clip_idx, void* stream) {
   if (!m || n_envs < 0 || !keys || !obs || !reward || !done || !metrics || !info_f || !info_i) { snprintf(g_err, sizeof(g_err), "bad argument"); return BT_E_ARG; }
   if (check_state(m, state, true)) return BT_E_ARG;
   if (n_envs == 0) return BT_OK;
   BT_ON_DEVICE(m);
   if (fixed_start_frame >= m->dev.clip_len) { snprintf(g_err, sizeof(g_err), "fixed_start_frame beyond the clip"); return BT_E_ARG; }
-  BtResetArgs a = {keys, fixed_start_frame, state, obs, reward, done, metrics, info_f, info_i};
+  BtResetArgs a = {keys, fixed_start_frame, state, obs, reward, done, metrics, info_f, info_i, clip_idx};
   { BtLaunchCfg c = cfg_for(m, n_envs, stream); m->ops->reset(c, m->dev, n_envs, c.warps, a); }
   BT_LAUNCHED();
   return BT_OK;
@@ -212,7 +212,7 @@ int bt_reset(BtModel* m, int n_envs, const uint32_t* keys, int fixed_start_frame
 
 int bt_step(BtModel* m, int n_envs, const float* action, BtStatePtrs state, BtStatePtrs first, const float* first_obs,
             const int32_t* first_info_i, float* obs, float* reward, float* done, float* metrics, float* info_f, int32_t* info_i,
-            void* stream) {
+            const int32_t* clip_idx, void* stream) {
   if (!m || n_envs < 0 || !action || !first_obs || !first_info_i || !obs || !reward || !done || !metrics || !info_f || !info_i) {
     snprintf(g_err, sizeof(g_err), "bad argument");
     return BT_E_ARG;
@@ -220,7 +220,7 @@ int bt_step(BtModel* m, int n_envs, const float* action, BtStatePtrs state, BtSt
   if (check_state(m, state, true) || check_state(m, first, true)) return BT_E_ARG;
   if (n_envs == 0) return BT_OK;
   BT_ON_DEVICE(m);
-  BtStepArgs a = {action, state, first, first_obs, first_info_i, obs, reward, done, metrics, info_f, info_i};
+  BtStepArgs a = {action, state, first, first_obs, first_info_i, obs, reward, done, metrics, info_f, info_i, clip_idx};
   { BtLaunchCfg c = cfg_for(m, n_envs, stream); m->ops->step(c, m->dev, n_envs, c.warps, a); }
   BT_LAUNCHED();
   return BT_OK;
@@ -247,12 +247,12 @@ int bt_pipeline_init(BtModel* m, int n_envs, BtStatePtrs state, void* stream) {
 }
 
 int bt_reward_obs(BtModel* m, int n_envs, const float* action, BtStatePtrs state, int32_t* info_i, float* obs, float* reward,
-                  float* done, float* metrics, float* info_f, void* stream) {
+                  float* done, float* metrics, float* info_f, const int32_t* clip_idx, void* stream) {
   if (!m || n_envs < 0 || !action || !info_i || !obs || !reward || !done || !metrics || !info_f) { snprintf(g_err, sizeof(g_err), "bad argument"); return BT_E_ARG; }
   if (check_state(m, state, true)) return BT_E_ARG;
   if (n_envs == 0) return BT_OK;
   BT_ON_DEVICE(m);
-  BtRewardArgs a = {action, state, info_i, obs, reward, done, metrics, info_f};
+  BtRewardArgs a = {action, state, info_i, obs, reward, done, metrics, info_f, clip_idx};
   { BtLaunchCfg c = cfg_for(m, n_envs, stream); m->ops->reward(c, m->dev, n_envs, c.warps, a); }
   BT_LAUNCHED();
   return BT_OK;

@@ -41,9 +41,10 @@ static inline int bt_bind(BtDev* d, int n, const char* const* names, const void*
       {"hpass_desc", 256LL * d->nhpass}, {"apass_desc", 32LL * d->napass}, {"cmp_adr", d->nbanc + 1LL},
       {"dof_range", 2LL * d->nv}, {"dof_solimp", 5LL * d->nv}, {"cbcon_adr", d->ncb + 1LL}, {"wgrp_adr", d->nwgrp + 1LL},
       {"act_rec", 16LL * (d->nu > 0 ? d->nu : 1)},
-      {"clip_position", 3LL * d->clip_len * d->n_animals}, {"clip_quaternion", 4LL * d->clip_len * d->n_animals},
-      {"clip_joints", (int64_t)d->clip_len * d->clip_nj}, {"clip_body_positions", 3LL * d->clip_len * d->nbody},
-      {"clip_angular_velocity", 3LL * d->clip_len * d->n_animals}, {"joint_idxs", d->n_joint_idxs}, {"body_idxs", d->n_body_idxs},
+      // clip tables: n_clips clips of clip_len frames stacked on the leading axis (preprocess.py:254-258)
+      {"clip_position", 3LL * d->n_clips * d->clip_len * d->n_animals}, {"clip_quaternion", 4LL * d->n_clips * d->clip_len * d->n_animals},
+      {"clip_joints", (int64_t)d->n_clips * d->clip_len * d->clip_nj}, {"clip_body_positions", 3LL * d->n_clips * d->clip_len * d->nbody},
+      {"clip_angular_velocity", 3LL * d->n_clips * d->clip_len * d->n_animals}, {"joint_idxs", d->n_joint_idxs}, {"body_idxs", d->n_body_idxs},
       {"animal_rec", 8LL * d->n_animals}, {"jidx_adr", d->n_animals + 1LL}, {"bidx_adr", d->n_animals + 1LL}, {"eidx_adr", d->n_animals + 1LL},
   };
   for (size_t k = 0; k < sizeof(chk) / sizeof(chk[0]); k++) {
@@ -60,7 +61,7 @@ static inline int bt_bind(BtDev* d, int n, const char* const* names, const void*
     idx = bt_find_table(n, names, "con_xref");
     if (counts[idx] != d->ncon) { snprintf(err, errlen, "con_xref must have ncon rows"); return -1; }
   }
-  if (d->clip_len < d->ref_len || d->nv <= 0 || d->nbody <= 1 || d->n_animals < 1) { snprintf(err, errlen, "degenerate model"); return -1; }
+  if (d->clip_len < d->ref_len || d->nv <= 0 || d->nbody <= 1 || d->n_animals < 1 || d->n_clips < 1) { snprintf(err, errlen, "degenerate model"); return -1; }
   if (d->obs_size > d->smem_floats - d->o_crb) { snprintf(err, errlen, "observation row does not fit the staging region"); return -1; }
   return 0;
 }

@@ -144,7 +144,9 @@ struct BtEnv {
   int niter;       // solver iterations of the last substep (diagnostic)
   float cdist[CS]; // contact distances of the last collision pass (diagnostic / tests)
 
-  BT_DEV BtEnv(const BtDev& m_, float* s_, int lane_, bool live_ = true) : m(m_), s(s_), lane(lane_), live(live_), niter(0) {}
+  int clip;        // this environment's reference clip (RodentMultiClip: rows clip * clip_len .. of the stacked clip tables)
+
+  BT_DEV BtEnv(const BtDev& m_, float* s_, int lane_, bool live_ = true) : m(m_), s(s_), lane(lane_), live(live_), niter(0), clip(0) {}
 
   // ------------------------------------------------------------------ scratch regions
   BT_DEV float* qpos() const { return s + m.o_qpos; }
@@ -1718,6 +1720,7 @@ struct BtEnv {
     const int L = m.ref_len, nq = m.nq, nv = m.nv, NA = m.n_animals;
     int start = cur_frame + 1;
     start = start < 0 ? 0 : (start > m.clip_len - L ? m.clip_len - L : start);  // dynamic_slice clamps the start
+    start += clip * m.clip_len;                                                 // row of the stacked multi-clip tables
     for (int i = lane; i < nq; i += G) o[i] = bt_nan_to_num(qpos()[i]);
     for (int i = lane; i < nv; i += G) o[nq + i] = bt_nan_to_num(qvel()[i]);
     int base = nq + nv;
@@ -1776,7 +1779,7 @@ struct BtEnv {
     const int cur = cur_frame_in + hit;
     stc = stc * (hit ? 0 : 1);
     r.cur_frame = cur; r.steps_taken = stc;
-    const int fi = cur < 0 ? 0 : (cur > m.clip_len - 1 ? m.clip_len - 1 : cur);  // JAX gather clamps
+    const int fi = (cur < 0 ? 0 : (cur > m.clip_len - 1 ? m.clip_len - 1 : cur)) + clip * m.clip_len;  // JAX gather clamps; row of the stacked tables
     // Per-animal terms (fruitfly.py:514-552), combined over the animals of the model: reward terms ADD, termination flags and
     // the three tracking distances take the MAX (any animal off its clip ends the episode).  With one animal (every
     // reference env) this is the reference expression, operation for operation.

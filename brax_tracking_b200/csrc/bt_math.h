@@ -229,6 +229,8 @@ static inline float bt_impedance_pow(float x, float mid, float power) {
   return x < mid ? ia : ib;
 }
 
+BT_DEV int bt_clampi(int x, int lo, int hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
 // ---- JAX threefry2x32 ----
 BT_DEV unsigned bt_rotl(unsigned x, int d) { return (x << d) | (x >> (32 - d)); }
 BT_DEV void bt_threefry2x32(unsigned k0, unsigned k1, unsigned& x0, unsigned& x1) {

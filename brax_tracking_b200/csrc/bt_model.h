@@ -12,7 +12,7 @@
   X(nq) X(nv) X(nu) X(na) X(nbody) X(njnt) X(nhpass) X(napass) X(nbanc) X(ncon) X(ncb) X(nwgrp) X(nmerge)       \
   X(cone) X(iterations) X(ls_iterations) X(n_frames) X(sync_mode) X(ncross) X(poison)                                          \
   /* env layer */                                                                                               \
-  X(free_jnt) X(seed_root_from_clip) X(ref_len) X(clip_len) X(clip_nj) X(n_joint_idxs) X(n_body_idxs) X(n_animals) \
+  X(free_jnt) X(seed_root_from_clip) X(ref_len) X(clip_len) X(clip_nj) X(n_joint_idxs) X(n_body_idxs) X(n_animals) X(n_clips) \
   X(n_endeff_idxs) X(torso_idx) X(terminate_when_unhealthy) X(steps_for_cur_frame) X(episode_length)            \
   X(start_frame_range) X(obs_size)                                                                              \
   /* per-environment scratch layout (offsets in floats) */                                                      \

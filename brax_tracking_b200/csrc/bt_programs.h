@@ -11,6 +11,7 @@ struct BtStepArgs {
   const int32_t* first_info_i;
   float *obs, *reward, *done, *metrics, *info_f;
   int32_t* info_i;
+  const int32_t* clip_idx;  // [n] reference clip of every environment, or NULL (single clip)
 };
 
 template <int G, int DS, int CS>
@@ -34,6 +35,7 @@ BT_DEV void bt_prog_step(const BtDev& m, float* s, int lane, int env, bool live,
     cur_in = a.info_i[(size_t)env * BT_NINFOI + BT_II_CUR_FRAME];
     stc_in = a.info_i[(size_t)env * BT_NINFOI + BT_II_STEPS_TAKEN];
     time = a.state.time[env];
+    if (a.clip_idx) E.clip = bt_clampi(a.clip_idx[env], 0, m.n_clips - 1);
     W::sync();  // all lanes have read done / info before lane 0 overwrites them below
     E.poison_scratch();
     E.load_state(a.state, env);
@@ -95,6 +97,7 @@ struct BtResetArgs {
   BtState state;
   float *obs, *reward, *done, *metrics, *info_f;
   int32_t* info_i;
+  int32_t* clip_idx;  // [n] OUT: the clip drawn for every environment (randint(rng_pos, (), 0, n_clips)), or NULL (single clip)
 };
 
 // wrap(env).reset  (fruitfly.py:449-495, rodent.py:154-159; JAX threefry per SURVEY Appendix D)
@@ -122,6 +125,24 @@ BT_DEV void bt_prog_reset(const BtDev& m, float* s, int lane, int env, bool live
   mult = (mult * mult) % span;
   const unsigned off = (hi_bits % span) * mult + (lo_bits % span);
   const int start = a.fixed_start_frame < 0 ? (int)(off % span) : a.fixed_start_frame;
+  // RodentMultiClip (envs/rodent.py:377, an empty class in the reference): the clip of an environment
+  // is drawn from the fourth key of the reset's split(rng, 4) -- `rng_pos`, which the reference draws and never uses
+  // (envs/fruitfly.py:451) -- as randint(rng_pos, (), 0, n_clips); it stays with the environment through auto-resets, which
+  // restore the cached first state (custom_wrappers.py:62-80)
+  if (a.clip_idx && m.n_clips > 1 && a.fixed_start_frame < 0) {
+    unsigned cs4[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) cs4[i] = bt_random_bits(sk[6], sk[7], i, 4);
+    const unsigned chi = bt_random_bits(cs4[0], cs4[1], 0, 1), clo = bt_random_bits(cs4[2], cs4[3], 0, 1);
+    const unsigned cspan = (unsigned)m.n_clips;
+    unsigned cmult = 65536u % cspan;
+    cmult = (cmult * cmult) % cspan;
+    E.clip = (int)(((chi % cspan) * cmult + (clo % cspan)) % cspan);
+  } else if (a.clip_idx && m.n_clips > 1) {
+    // render / evaluation rollout (no rng_pos in its split(rng, 3)): the caller chooses the clip
+    E.clip = bt_clampi(a.clip_idx[env], 0, m.n_clips - 1);
+  }
+  const int crow = E.clip * m.clip_len;
   const float lo = -m.reset_noise_scale, hi = m.reset_noise_scale;
   for (int i = lane; i < m.nq; i += G) {
     float q0 = BT_LDG(m.qpos0 + i);
@@ -129,8 +150,8 @@ BT_DEV void bt_prog_reset(const BtDev& m, float* s, int lane, int env, bool live
       const int fs = start > m.clip_len - 1 ? m.clip_len - 1 : start;  // JAX gather clamps (a clip shorter than the start-frame range)
       for (int an = 0; an < m.n_animals; an++) {   // every animal's root x, y and orientation from its own copy of the clip
         const int rel = i - BT_LDG(m.animal_rec + 8 * an);
-        if (rel >= 0 && rel < 2) q0 = BT_LDG(m.clip_position + 3 * (fs * m.n_animals + an) + rel);
-        else if (rel >= 3 && rel < 7) q0 = BT_LDG(m.clip_quaternion + 4 * (fs * m.n_animals + an) + rel - 3);
+        if (rel >= 0 && rel < 2) q0 = BT_LDG(m.clip_position + 3 * ((crow + fs) * m.n_animals + an) + rel);
+        else if (rel >= 3 && rel < 7) q0 = BT_LDG(m.clip_quaternion + 4 * ((crow + fs) * m.n_animals + an) + rel - 3);
       }
     }
     E.qpos()[i] = q0 + bt_bits_to_uniform(bt_random_bits(sk[2], sk[3], i, m.nq), lo, hi);
@@ -153,6 +174,7 @@ BT_DEV void bt_prog_reset(const BtDev& m, float* s, int lane, int env, bool live
     for (int k = 0; k < BT_NINFOF; k++) a.info_f[(size_t)env * BT_NINFOF + k] = 0.f;
     a.info_i[(size_t)env * BT_NINFOI + BT_II_CUR_FRAME] = start;
     a.info_i[(size_t)env * BT_NINFOI + BT_II_STEPS_TAKEN] = 0;
+    if (a.clip_idx) a.clip_idx[env] = E.clip;
   }
   W::sync();
 }
@@ -186,6 +208,7 @@ struct BtRewardArgs {
   BtState state;
   int32_t* info_i;
   float *obs, *reward, *done, *metrics, *info_f;
+  const int32_t* clip_idx;
 };
 
 // env.step after pipeline_step (fruitfly.py:502-596), no wrappers
@@ -196,6 +219,7 @@ BT_DEV void bt_prog_reward(const BtDev& m, float* s, int lane, int env, bool liv
   BtEnv<G, DS, CS> E(m, s, lane);
   const int cur_in = a.info_i[(size_t)env * BT_NINFOI + BT_II_CUR_FRAME];
   const int stc_in = a.info_i[(size_t)env * BT_NINFOI + BT_II_STEPS_TAKEN];
+  if (a.clip_idx) E.clip = bt_clampi(a.clip_idx[env], 0, m.n_clips - 1);
   W::sync();
   E.poison_scratch();
   E.load_state(a.state, env);

@@ -44,6 +44,8 @@ static ffi::Error BtStepImpl(cudaStream_t stream, int64_t model_handle, F32Buf a
                              // operands 9..17: the state the step advances (aliased to results 0..8)
                              F32Buf qpos_in, F32Buf qvel_in, F32Buf act_in, F32Buf warm_in, F32Buf time_in, F32Buf xpos_in,
                              F32Buf done_in, F32Buf info_f_in, S32Buf info_i_in,
+                             // operand 18: the clip of every environment (RodentMultiClip; zeros for a single-clip model), read only
+                             S32Buf clip_idx,
                              // results 0..8 (aliased) and 9..11 (pure outputs)
                              F32Res qpos, F32Res qvel, F32Res act, F32Res warm, F32Res time, F32Res xpos, F32Res done, F32Res info_f,
                              S32Res info_i, F32Res obs, F32Res reward, F32Res metrics) {
@@ -58,7 +60,7 @@ static ffi::Error BtStepImpl(cudaStream_t stream, int64_t model_handle, F32Buf a
                        first_time.typed_data(), first_xpos.typed_data()};
   const int rc = bt_step(m, n, action.typed_data(), st, first, first_obs.typed_data(), first_info_i.typed_data(), obs->typed_data(),
                          reward->typed_data(), done->typed_data(), metrics->typed_data(), info_f->typed_data(), info_i->typed_data(),
-                         stream);
+                         clip_idx.typed_data(), stream);
   if (rc != BT_OK) return ffi::Error(ffi::ErrorCode::kInternal, bt_last_error());
   return ffi::Error::Success();
 }
@@ -72,6 +74,7 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(BtStepFfi, BtStepImpl,
                                   .Arg<F32Buf>().Arg<S32Buf>()                                                // 7 first_obs, 8 first_info_i
                                   .Arg<F32Buf>().Arg<F32Buf>().Arg<F32Buf>().Arg<F32Buf>().Arg<F32Buf>().Arg<F32Buf>()  // 9..14 state (aliased)
                                   .Arg<F32Buf>().Arg<F32Buf>().Arg<S32Buf>()                                  // 15 done, 16 info_f, 17 info_i (aliased)
+                                  .Arg<S32Buf>()                                                              // 18 clip_idx
                                   .Ret<F32Buf>().Ret<F32Buf>().Ret<F32Buf>().Ret<F32Buf>().Ret<F32Buf>().Ret<F32Buf>()  // 0..5 state
                                   .Ret<F32Buf>().Ret<F32Buf>().Ret<S32Buf>()                                  // 6 done, 7 info_f, 8 info_i
                                   .Ret<F32Buf>().Ret<F32Buf>().Ret<F32Buf>());                                // 9 obs, 10 reward, 11 metrics
@@ -81,12 +84,13 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(BtStepFfi, BtStepImpl,
 // state / obs / info_i as the wrapper's first_* (a plain jnp copy on the JAX side).
 static ffi::Error BtResetImpl(cudaStream_t stream, int64_t model_handle, int64_t fixed_start_frame, ffi::Buffer<ffi::U32> keys,
                               F32Res qpos, F32Res qvel, F32Res act, F32Res warm, F32Res time, F32Res xpos, F32Res obs, F32Res reward,
-                              F32Res done, F32Res metrics, F32Res info_f, S32Res info_i) {
+                              F32Res done, F32Res metrics, F32Res info_f, S32Res info_i, S32Res clip_idx) {
   BtModel* m = reinterpret_cast<BtModel*>(model_handle);
   const int n = static_cast<int>(keys.dimensions()[0]);
   BtStatePtrs st = {qpos->typed_data(), qvel->typed_data(), act->typed_data(), warm->typed_data(), time->typed_data(), xpos->typed_data()};
   const int rc = bt_reset(m, n, keys.typed_data(), static_cast<int>(fixed_start_frame), st, obs->typed_data(), reward->typed_data(),
-                          done->typed_data(), metrics->typed_data(), info_f->typed_data(), info_i->typed_data(), stream);
+                          done->typed_data(), metrics->typed_data(), info_f->typed_data(), info_i->typed_data(), clip_idx->typed_data(),
+                          stream);
   if (rc != BT_OK) return ffi::Error(ffi::ErrorCode::kInternal, bt_last_error());
   return ffi::Error::Success();
 }
@@ -98,5 +102,6 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(BtResetFfi, BtResetImpl,
                                   .Attr<int64_t>("fixed_start_frame")
                                   .Arg<ffi::Buffer<ffi::U32>>()                                               // keys [n, 2]
                                   .Ret<F32Buf>().Ret<F32Buf>().Ret<F32Buf>().Ret<F32Buf>().Ret<F32Buf>().Ret<F32Buf>()  // state
-                                  .Ret<F32Buf>().Ret<F32Buf>().Ret<F32Buf>().Ret<F32Buf>().Ret<F32Buf>().Ret<S32Buf>()); // obs reward done metrics info_f info_i
+                                  .Ret<F32Buf>().Ret<F32Buf>().Ret<F32Buf>().Ret<F32Buf>().Ret<F32Buf>().Ret<S32Buf>()  // obs reward done metrics info_f info_i
+                                  .Ret<S32Buf>());                                                            // clip_idx (the clip drawn per environment)
 #endif

@@ -42,6 +42,8 @@ def _views(out) -> tuple:
     metrics = {k: out["metrics"][:, i] for i, k in enumerate(native.METRIC_NAMES)}
     info = {k: out["info_f"][:, i] for i, k in enumerate(native.INFO_F_NAMES)}
     info.update({k: out["info_i"][:, i] for i, k in enumerate(native.INFO_I_NAMES)})
+    if "clip_idx" in out:
+        info["clip_idx"] = out["clip_idx"]
     return metrics, info
 
 
@@ -49,7 +51,13 @@ class TrackingEnv:
     """Single-clip imitation env on the fused sm_100a step (batched; one process drives one GPU)."""
 
     def __init__(self, mj_model: mjcf.Model, reference_clip, env_args: dict, device: int = 0):
-        clip = reference_clip.as_dict() if isinstance(reference_clip, ReferenceClip) else dict(reference_clip)
+        """``reference_clip``: a ``ReferenceClip`` / dict of its arrays, or a list of them (multi-clip, ``RodentMultiClip``): stacked
+        on a leading clip axis as ``preprocess.save_reference_clip`` stores them (preprocessing/preprocess.py:254-258)."""
+        if isinstance(reference_clip, (list, tuple)):
+            cs = [c.as_dict() if isinstance(c, ReferenceClip) else dict(c) for c in reference_clip]
+            clip = {k: np.stack([np.asarray(c[k]) for c in cs]) for k in cs[0]}
+        else:
+            clip = reference_clip.as_dict() if isinstance(reference_clip, ReferenceClip) else dict(reference_clip)
         self.sys = mj_model
         self._cfg = configs.resolve(mj_model, env_args)
         self._tables = model_mod.pack(mj_model, self._cfg, clip)
@@ -90,12 +98,23 @@ class TrackingEnv:
             rng = rng.view(torch.int32)
         return rng.to(device=self._native._dev(), dtype=torch.int32).contiguous()
 
+    def _new_clip_idx(self, out, n, clip_idx=None):
+        """multi-clip models carry ``info['clip_idx']`` ([n] int32; drawn by the reset kernel, or given for render rollouts)"""
+        if self._native.n_clips <= 1:
+            return None
+        import torch
+        c = torch.zeros(n, dtype=torch.int32, device=self._native._dev())
+        if clip_idx is not None:
+            c.copy_(torch.as_tensor(clip_idx, dtype=torch.int32))
+        out["clip_idx"] = c
+        return c
+
     def reset(self, rng) -> State:
         """Fruitfly_Tethered_Free.reset (fruitfly.py:449-495) for a batch of JAX keys ``[n, 2]``."""
         keys = self._keys(rng)
         n = keys.shape[0]
         st, out = self._native.new_state(n), self._native.new_outputs(n)
-        self._native.reset(keys, st, out)
+        self._native.reset(keys, st, out, clip_idx=self._new_clip_idx(out, n))
         metrics, info = _views(out)
         info.pop("steps"); info.pop("truncation")  # those belong to the EpisodeWrapper
         return State(st, out["obs"], out["reward"], out["done"], metrics, info, _raw=out)
@@ -103,7 +122,7 @@ class TrackingEnv:
     def step(self, state: State, action) -> State:
         """Fruitfly_Tethered_Free.step (fruitfly.py:497-596), unwrapped: pipeline_step + reward/obs, in place."""
         self._native.physics_step(action, state.pipeline_state, self._n_frames)
-        self._native.reward_obs(action, state.pipeline_state, state._raw)
+        self._native.reward_obs(action, state.pipeline_state, state._raw, clip_idx=state._raw.get("clip_idx"))
         return state
 
     def pipeline_init(self, qpos, qvel) -> Dict[str, Any]:
@@ -127,6 +146,14 @@ def _load(name, mj_model):
 def RodentSingleClip(reference_clip, mj_model: Optional[mjcf.Model] = None, device: int = 0, **overrides) -> TrackingEnv:
     """envs/rodent.py:19-136 with the canonical fixes of SURVEY.md Appendix B.3."""
     return TrackingEnv(_load("rodent", mj_model), reference_clip, dict(configs.RODENT_ENV_ARGS, **overrides), device)
+
+
+def RodentMultiClip(reference_clips, mj_model: Optional[mjcf.Model] = None, device: int = 0, **overrides) -> TrackingEnv:
+    """envs/rodent.py:377 -- an EMPTY class body in the reference (a SyntaxError).  Defined here as RodentSingleClip
+    over several clips stacked on a leading axis (preprocessing/preprocess.py:254-258): every environment draws its clip at reset
+    (``randint(rng_pos, (), 0, n_clips)``, the key the single-clip reset splits off and never uses, fruitfly.py:451), keeps it in
+    ``info['clip_idx']`` and through auto-resets, and every clip gather of the step is offset by it."""
+    return TrackingEnv(_load("rodent", mj_model), list(reference_clips), dict(configs.RODENT_ENV_ARGS, **overrides), device)
 
 
 def Fruitfly_Tethered_Free(reference_clip, mj_model: Optional[mjcf.Model] = None, device: int = 0, **overrides) -> TrackingEnv:
@@ -161,7 +188,7 @@ class AutoResetWrapperTracking:
         keys = env._keys(rng)
         n = keys.shape[0]
         st, out = env._native.new_state(n), env._native.new_outputs(n)
-        env._native.reset(keys, st, out)
+        env._native.reset(keys, st, out, clip_idx=env._new_clip_idx(out, n))
         metrics, info = _views(out)
         # custom_wrappers.py:46-52: cache the first state / obs / frame counters for the auto-reset selection
         first = {k: v.clone() for k, v in st.items()}
@@ -175,7 +202,7 @@ class AutoResetWrapperTracking:
 
     def step(self, state: State, action) -> State:
         r = state._raw
-        self.env._native.step(action, state.pipeline_state, r["first"], r["first_obs"], r["first_info_i"], r)
+        self.env._native.step(action, state.pipeline_state, r["first"], r["first_obs"], r["first_info_i"], r, clip_idx=r.get("clip_idx"))
         return state
 
     def bind_host_obs(self, state: State):
@@ -200,12 +227,13 @@ class RenderRolloutWrapperTracking:
     def __getattr__(self, name):
         return getattr(self.env, name)
 
-    def reset(self, rng) -> State:
+    def reset(self, rng, clip_idx=None) -> State:
+        """``clip_idx`` ([n] ints, multi-clip models only): the clip every environment replays (default: clip 0)."""
         env = self.env
         keys = env._keys(rng)
         n = keys.shape[0]
         st, out = env._native.new_state(n), env._native.new_outputs(n)
-        env._native.reset(keys, st, out, fixed_start_frame=0)
+        env._native.reset(keys, st, out, fixed_start_frame=0, clip_idx=env._new_clip_idx(out, n, clip_idx))
         metrics, info = _views(out)
         info.pop("steps"); info.pop("truncation")
         return State(st, out["obs"], out["reward"], out["done"], metrics, info, _raw=out)

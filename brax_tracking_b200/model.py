@@ -572,8 +572,13 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
     SF("tolerance", m.tolerance); SF("ls_tolerance", m.ls_tolerance); SF("meaninertia", m.meaninertia)
 
     # ------------------------------------------------------------------ env layer (fruitfly.py:405-447)
-    T = int(np.asarray(clip["joints"]).shape[0])
-    nj = int(np.asarray(clip["joints"]).shape[1])
+    # one clip `[T, ...]`, or several stacked on a leading clip axis `[C, T, ...]` (preprocess.py:254-258: RodentMultiClip)
+    multi = np.asarray(clip["joints"]).ndim == 3
+    NC = int(np.asarray(clip["joints"]).shape[0]) if multi else 1
+    clip = {k: (np.asarray(v) if multi else np.asarray(v)[None]) for k, v in clip.items() if k in CLIP_FIELDS}
+    T = int(clip["joints"].shape[1])
+    nj = int(clip["joints"].shape[2])
+    S("n_clips", NC)
     S("free_jnt", int(cfg["free_jnt"])); S("seed_root_from_clip", int(cfg["seed_root_from_clip"]))
     S("ref_len", cfg["ref_len"]); S("clip_len", T); S("clip_nj", nj)
     # per-animal index lists (configs.resolve: cfg["animals"]); joint ids index the ANIMAL's own joint columns
@@ -612,10 +617,10 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
     S("obs_size", obs_size)
     for k in CLIP_FIELDS:
         t["clip_" + k] = _f(clip[k])
-    assert np.asarray(clip["body_positions"]).shape[1:] == (nbody, 3)
+    assert clip["body_positions"].shape == (NC, T, nbody, 3), clip["body_positions"].shape
     assert nj == (nq - 7 * NA if cfg["free_jnt"] else nq), (nj, nq)
     for k, w in (("position", 3), ("quaternion", 4), ("angular_velocity", 3)):
-        assert np.asarray(clip[k]).reshape(T, -1).shape[1] == w * NA, (k, np.asarray(clip[k]).shape, NA)
+        assert clip[k].reshape(NC, T, -1).shape[2] == w * NA, (k, clip[k].shape, NA)
 
     # ------------------------------------------------------------------ per-environment scratch layout (floats)
     lay, off = {}, 0

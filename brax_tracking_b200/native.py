@@ -126,9 +126,9 @@ class NativeModel:
         self._h = h
         self.device = int(device)
         self.tables = tables
-        d = (C.c_int * 8)()
+        d = (C.c_int * 9)()
         _check(l.bt_model_dims(h, d))
-        self.nq, self.nv, self.nu, self.na, self.nbody, self.obs_size, self.smem_floats, self.ncon = [int(x) for x in d]
+        self.nq, self.nv, self.nu, self.na, self.nbody, self.obs_size, self.smem_floats, self.ncon, self.n_clips = [int(x) for x in d]
         g = (C.c_int * 3)()
         _check(l.bt_model_launch(h, g))
         self.warps_per_cta, self.max_ctas, self.smem_bytes = int(g[0]), int(g[1]), int(g[2])
@@ -189,23 +189,27 @@ class NativeModel:
         return C.c_void_p(self._torch().cuda.current_stream(self.device).cuda_stream)
 
     # ---- entry points ----------------------------------------------------------------------------
-    def reset(self, keys, state, out, fixed_start_frame: int = -1):
+    def _clip(self, clip_idx, n):
+        """[n] int32 clip indices (RodentMultiClip) or None: a NULL pointer, the single-clip behaviour"""
+        return None if clip_idx is None else self._p(clip_idx, (n,), self._torch().int32)
+
+    def reset(self, keys, state, out, fixed_start_frame: int = -1, clip_idx=None):
         torch = self._torch()
         n = keys.shape[0]
         _check(lib().bt_reset(self._h, n, self._p(keys, (n, 2), torch.uint32 if keys.dtype == torch.uint32 else torch.int32),
                               int(fixed_start_frame), self._sp(state, n), self._p(out["obs"], (n, self.obs_size)), self._p(out["reward"], (n,)),
                               self._p(out["done"], (n,)), self._p(out["metrics"], (n, NUM_METRICS)),
                               self._p(out["info_f"], (n, NUM_INFO_F)), self._p(out["info_i"], (n, NUM_INFO_I), torch.int32),
-                              self._stream()))
+                              self._clip(clip_idx, n), self._stream()))
 
-    def step(self, action, state, first, first_obs, first_info_i, out):
+    def step(self, action, state, first, first_obs, first_info_i, out, clip_idx=None):
         torch = self._torch()
         n = action.shape[0]
         _check(lib().bt_step(self._h, n, self._p(action, (n, self.nu)), self._sp(state, n), self._sp(first, n),
                              self._p(first_obs, (n, self.obs_size)), self._p(first_info_i, (n, NUM_INFO_I), torch.int32),
                              self._p(out["obs"], (n, self.obs_size)), self._p(out["reward"], (n,)), self._p(out["done"], (n,)),
                              self._p(out["metrics"], (n, NUM_METRICS)), self._p(out["info_f"], (n, NUM_INFO_F)),
-                             self._p(out["info_i"], (n, NUM_INFO_I), torch.int32), self._stream()))
+                             self._p(out["info_i"], (n, NUM_INFO_I), torch.int32), self._clip(clip_idx, n), self._stream()))
 
     def physics_step(self, ctrl, state, n_substeps: int):
         n = state["qpos"].shape[0]
@@ -215,13 +219,13 @@ class NativeModel:
         n = state["qpos"].shape[0]
         _check(lib().bt_pipeline_init(self._h, n, self._sp(state, n), self._stream()))
 
-    def reward_obs(self, action, state, out):
+    def reward_obs(self, action, state, out, clip_idx=None):
         torch = self._torch()
         n = action.shape[0]
         _check(lib().bt_reward_obs(self._h, n, self._p(action, (n, self.nu)), self._sp(state, n),
                                    self._p(out["info_i"], (n, NUM_INFO_I), torch.int32), self._p(out["obs"], (n, self.obs_size)),
                                    self._p(out["reward"], (n,)), self._p(out["done"], (n,)), self._p(out["metrics"], (n, NUM_METRICS)),
-                                   self._p(out["info_f"], (n, NUM_INFO_F)), self._stream()))
+                                   self._p(out["info_f"], (n, NUM_INFO_F)), self._clip(clip_idx, n), self._stream()))
 
     def kinematics(self, qpos):
         """Batched forward kinematics (mjx smooth.kinematics; preprocessing/preprocess.py:144-204): qpos [n, nq] ->

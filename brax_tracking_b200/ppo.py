@@ -587,7 +587,7 @@ def train(environment, num_timesteps: int, episode_length: int, action_repeat: i
 
 
 # ---------------------------------------------------------------------------------------------- checkpoints
-_ENV_RAW_KEYS = ("obs", "reward", "done", "metrics", "info_f", "info_i", "first_obs", "first_info_i")
+_ENV_RAW_KEYS = ("obs", "reward", "done", "metrics", "info_f", "info_i", "first_obs", "first_info_i", "clip_idx")
 
 
 def save_checkpoint(ts: TrainingState, path: str, env_state=None, rng_state=None) -> None:

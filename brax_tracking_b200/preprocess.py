@@ -5,8 +5,10 @@ Mirrors /root/reference/preprocessing/preprocess.py:99-230: per-frame forward ki
 ``lax.scan`` of ``mjx`` kinematics), last-frame padding (:126), six zero columns appended for tethered models (:128-129),
 finite-difference velocities with the quaternion-log angular velocity of
 ``compute_velocity_from_kinematics`` (:207-230; ``transformations.quat_diff`` / ``quat_to_axisangle``) and joint-velocity
-clipping (:131-134).  On-disk format: ``.npz`` with the ``ReferenceClip`` field names (the reference uses pickles / HDF5;
-h5py is not available in this image), a leading clip axis for multi-clip files (preprocess.py:254-258).
+clipping (:131-134).  On-disk formats: ``.npz`` with the ``ReferenceClip`` field names and a leading clip axis for multi-clip
+files (preprocess.py:254-258) -- written and read here; the reference's own ``.p`` pickles (main.py:57-74: a pickled
+``ReferenceClip`` flax dataclass of jax arrays, or a dict of them) -- read here WITHOUT jax / flax through a restricted unpickler
+(``load_reference_clip_pickle``).  The reference's HDF5 variant (:233-293) needs h5py, which this image does not have.
 """
 from __future__ import annotations
 
@@ -116,3 +118,61 @@ def load_reference_clip(path: str, clip_idx: Optional[int] = None) -> ReferenceC
             raise ValueError("multi-clip file: pass clip_idx")
         return ReferenceClip(**{k: z[k][clip_idx] for k in ReferenceClip.__dataclass_fields__})
     return ReferenceClip(**{k: z[k] for k in ReferenceClip.__dataclass_fields__})
+
+
+# ---------------------------------------------------------------------------------------------- the reference's .p pickles
+class _PickledStruct:
+    """Stand-in for any class the pickle names that is not importable here (``preprocessing.preprocess.ReferenceClip``, a
+    flax.struct dataclass): keeps the instance ``__dict__`` / state."""
+
+    def __init__(self, *a, **k):
+        self.__dict__.update(k)
+
+    def __setstate__(self, state):
+        self.__dict__.update(state if isinstance(state, dict) else {"state": state})
+
+
+def _reconstruct_jax_array(fun, args, arr_state, aval_state=None):
+    """``jax._src.array._reconstruct_array``: a pickled ``jax.Array`` is (numpy reconstructor, its args, the ndarray state, the aval
+    state) -- rebuild the numpy array and drop the device placement."""
+    arr = fun(*args)
+    arr.__setstate__(arr_state)
+    return np.asarray(arr)
+
+
+def load_reference_clip_pickle(path: str):
+    """Reads what /root/reference/main.py:57-74 reads with ``pickle.load``: a ``ReferenceClip`` instance (or a dict / list of them)
+    whose leaves are jax or numpy arrays.  Only numpy reconstruction and the array / dataclass stand-ins above are allowed to run
+    (a pickle is code: nothing else is ever imported or called).  Returns a ``ReferenceClip``, or {name: ReferenceClip} / a list."""
+    import pickle
+
+    allowed = {("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"), ("numpy", "ndarray"), ("numpy", "dtype"),
+               ("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar"), ("collections", "OrderedDict")}
+
+    class Unpickler(pickle.Unpickler):
+        def find_class(self, module, name):
+            if (module, name) in allowed:
+                return super().find_class(module, name)
+            if name == "_reconstruct_array" and module.startswith("jax"):
+                return _reconstruct_jax_array
+            if module.startswith(("jax", "jaxlib", "flax")) and name in ("ShapedArray", "UnspecifiedValue", "ArrayImpl"):
+                return _PickledStruct
+            if name == "ReferenceClip" or module.startswith("preprocessing"):
+                return _PickledStruct
+            raise pickle.UnpicklingError(f"refusing to load {module}.{name} from a clip pickle")
+
+    with open(path, "rb") as f:
+        obj = Unpickler(f).load()
+
+    def to_clip(o):
+        d = o if isinstance(o, dict) else o.__dict__
+        missing = [k for k in ReferenceClip.__dataclass_fields__ if k not in d]
+        if missing:
+            raise ValueError(f"not a ReferenceClip: missing {missing}")
+        return ReferenceClip(**{k: np.ascontiguousarray(np.asarray(d[k]), dtype=np.float32) for k in ReferenceClip.__dataclass_fields__})
+
+    if isinstance(obj, (list, tuple)):
+        return [to_clip(o) for o in obj]
+    if isinstance(obj, dict) and not set(ReferenceClip.__dataclass_fields__) <= set(obj):
+        return {k: to_clip(v) for k, v in obj.items()}
+    return to_clip(obj)

@@ -57,28 +57,32 @@ typedef struct BtStatePtrs {
 int bt_model_create(int n_tables, const char* const* names, const void* const* data, const int64_t* counts,
                     const int* is_float, int device, BtModel** out);
 void bt_model_destroy(BtModel* m);
-/* dims[0..7] = nq, nv, nu, na, nbody, obs_size, smem_floats, ncon */
+/* dims[0..8] = nq, nv, nu, na, nbody, obs_size, smem_floats, ncon, n_clips */
 int bt_model_dims(const BtModel* m, int* dims);
 /* launch geometry chosen for this model: out[0] = warps (= envs) per CTA, out[1] = max CTAs, out[2] = dynamic smem bytes */
 int bt_model_launch(const BtModel* m, int* out);
 
 /* fixed_start_frame < 0: training reset (random start frame in [0, 44), split(rng, 4));
    fixed_start_frame >= 0: RenderRolloutWrapperTracking.reset (custom_brax/custom_wrappers.py:85-125: that frame, split(rng, 3)) */
+/* clip_idx [n] (may be NULL: single clip): the reference clip of every environment when the model holds several stacked clips
+   (RodentMultiClip, envs/rodent.py:377; preprocessing/preprocess.py:254-258).  bt_reset WRITES it on a training reset
+   (randint(rng_pos, (), 0, n_clips), rng_pos = the fourth key of the reset's split(rng, 4)) and READS it on a render reset;
+   bt_step / bt_reward_obs read it.  It stays with the environment through auto-resets, like the cached first state. */
 int bt_reset(BtModel* m, int n_envs, const uint32_t* keys /*[n,2]*/, int fixed_start_frame, BtStatePtrs state,
              float* obs /*[n,O]*/, float* reward, float* done, float* metrics /*[n,12]*/, float* info_f /*[n,5]*/,
-             int32_t* info_i /*[n,2]*/, void* stream);
+             int32_t* info_i /*[n,2]*/, int32_t* clip_idx /*[n] or NULL*/, void* stream);
 
 int bt_step(BtModel* m, int n_envs, const float* action /*[n,nu]*/, BtStatePtrs state /*in-out*/,
             BtStatePtrs first /*auto-reset source*/, const float* first_obs, const int32_t* first_info_i,
             float* obs, float* reward, float* done /*in: previous, out: new*/, float* metrics, float* info_f,
-            int32_t* info_i, void* stream);
+            int32_t* info_i, const int32_t* clip_idx /*[n] or NULL*/, void* stream);
 
 int bt_physics_step(BtModel* m, int n_envs, const float* ctrl /*[n,nu]*/, BtStatePtrs state, int n_substeps,
                     void* stream);
 int bt_pipeline_init(BtModel* m, int n_envs, BtStatePtrs state, void* stream);
 int bt_reward_obs(BtModel* m, int n_envs, const float* action, BtStatePtrs state /*read only*/,
                   int32_t* info_i /*in-out*/, float* obs, float* reward, float* done, float* metrics,
-                  float* info_f, void* stream);
+                  float* info_f, const int32_t* clip_idx /*[n] or NULL*/, void* stream);
 /* runs mjx.forward up to `stop` (0 = all of it) and copies every env's scratch block: scratch [n, smem_floats],
    cdist [n, ncon], niter [n] */
 int bt_forward_debug(BtModel* m, int n_envs, const float* ctrl, BtStatePtrs state, int stop, float* scratch,

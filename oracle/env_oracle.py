@@ -132,9 +132,14 @@ class EnvOracle:
         self.o = physics
         self.m = physics.m
         self.dt = np.dtype(dtype)
-        self.clip = {k: np.asarray(v, dtype=self.dt) for k, v in clip.items()}
+        # several clips stacked on a leading axis (preprocess.py:254-258) are kept as ONE table of n_clips * T rows; an environment
+        # with clip index c reads row c * T + frame (the frame clamps stay per clip)
+        multi = np.asarray(clip["joints"]).ndim == 3
+        self.n_clips = int(np.asarray(clip["joints"]).shape[0]) if multi else 1
+        self.T = int(np.asarray(clip["joints"]).shape[1 if multi else 0])
+        self.clip = {k: np.asarray(v, dtype=self.dt).reshape((self.n_clips * self.T,) + np.asarray(v).shape[(2 if multi else 1):])
+                     for k, v in clip.items()}
         self.c = dict(cfg)
-        self.T = self.clip["joints"].shape[0]
 
     def animals(self):
         """Per-animal constants (brax_tracking_b200.configs.resolve): every reference env has one animal; the two-rodent
@@ -145,18 +150,20 @@ class EnvOracle:
                                          body_idxs=c["body_idxs"], endeff_idxs=c["endeff_idxs"])]
 
     # -- fruitfly.py:598-646 ---------------------------------------------------------------------
-    def get_obs(self, qpos, qvel, xpos, cur_frame):
+    def get_obs(self, qpos, qvel, xpos, cur_frame, clip_idx=None):
         c, dt = self.c, self.dt
         N = qpos.shape[0]
         L = c["ref_len"]
         start = np.clip(cur_frame + 1, 0, self.T - L)  # dynamic_slice clamps the start
+        if clip_idx is not None:
+            start = start + np.asarray(clip_idx) * self.T
         win = start[:, None] + np.arange(L)[None, :]   # [N, L]
         parts = [qpos, qvel]
         free = c["free_jnt"]
         ans = self.animals()
         NA = len(ans)
-        cpos = self.clip["position"].reshape(self.T, NA, 3)
-        cquat = self.clip["quaternion"].reshape(self.T, NA, 4)
+        cpos = self.clip["position"].reshape(-1, NA, 3)
+        cquat = self.clip["quaternion"].reshape(-1, NA, 4)
         for a, an in enumerate(ans):
             qa = an["qadr"]
             # tethered: fruitfly.py:271-319 -- no pos/quat terms, full qpos joints, offsets rotated by qpos[3:7] (joint angles!)
@@ -183,7 +190,7 @@ class EnvOracle:
         return 0.5 * np.arccos(dist)
 
     # -- reset: fruitfly.py:449-495 (+ rodent.py:154-159), EpisodeWrapper.reset, AutoReset.reset -----
-    def reset(self, keys, fixed_start_frame=-1, start_frames=None):
+    def reset(self, keys, fixed_start_frame=-1, start_frames=None, clip_idx=None):
         """keys: [N,2] uint32 (one JAX key per env, as jax.random.split(key_env, num_envs)).
         fixed_start_frame >= 0: RenderRolloutWrapperTracking.reset (custom_wrappers.py:85-125): split(rng, 3), that frame.
         start_frames (test-only): per-env start frames replacing the randint draw (late-clip cases)."""
@@ -192,6 +199,7 @@ class EnvOracle:
         qpos = np.zeros((N, m.nq), dtype=dt)
         qvel = np.zeros((N, m.nv), dtype=dt)
         start = np.zeros(N, dtype=np.int32)
+        clip_sel = np.zeros(N, dtype=np.int32) if clip_idx is None else np.asarray(clip_idx, np.int32).copy()
         lo, hi = -c["reset_noise_scale"], c["reset_noise_scale"]
         for e in range(N):
             k = split((keys[e, 0], keys[e, 1]), 4 if fixed_start_frame < 0 else 3)
@@ -199,25 +207,29 @@ class EnvOracle:
             start[e] = randint(rng, 0, 44) if fixed_start_frame < 0 else fixed_start_frame
             if start_frames is not None:
                 start[e] = start_frames[e]
+            if self.n_clips > 1 and fixed_start_frame < 0:
+                # RodentMultiClip (an empty class in the reference): clip = randint(rng_pos, (), 0, n_clips), rng_pos = the fourth key
+                clip_sel[e] = randint((k[3, 0], k[3, 1]), 0, self.n_clips)
+            crow = int(clip_sel[e]) * self.T
             q0 = m.qpos0.astype(dt).copy()
             if c["seed_root_from_clip"] and fixed_start_frame < 0:
                 fs = min(max(int(start[e]), 0), self.T - 1)   # JAX gather clamps
                 ans = self.animals()
                 for a, an in enumerate(ans):                  # every animal from its own copy of the clip
                     qa = an["qadr"]
-                    q0[qa:qa + 2] = self.clip["position"].reshape(self.T, len(ans), 3)[fs, a, :2]
-                    q0[qa + 3:qa + 7] = self.clip["quaternion"].reshape(self.T, len(ans), 4)[fs, a]
+                    q0[qa:qa + 2] = self.clip["position"].reshape(-1, len(ans), 3)[crow + fs, a, :2]
+                    q0[qa + 3:qa + 7] = self.clip["quaternion"].reshape(-1, len(ans), 4)[crow + fs, a]
             qpos[e] = q0 + uniform(rng1, m.nq, lo, hi).astype(dt)
             qvel[e] = uniform(rng2, m.nv, lo, hi).astype(dt)
         st = dict(qpos=qpos, qvel=qvel, act=np.zeros((N, m.na), dtype=dt), qacc_warmstart=np.zeros((N, m.nv), dtype=dt),
                   time=np.zeros(N, dtype=dt))
         ps = self.o.pipeline_batch(st, None, 0, forward_only=True)  # pipeline_init = mjx.forward
         ps = {k: np.asarray(v, dtype=dt) for k, v in ps.items()}
-        obs = self.get_obs(ps["qpos"], ps["qvel"], ps["xpos"], start)
+        obs = self.get_obs(ps["qpos"], ps["qvel"], ps["xpos"], start, clip_sel)
         state = dict(
             pipeline_state=ps, obs=obs, reward=np.zeros(N, dtype=dt), done=np.zeros(N, dtype=dt),
             metrics={k: np.zeros(N, dtype=dt) for k in METRIC_NAMES},
-            info=dict(cur_frame=start.copy(), steps_taken_cur_frame=np.zeros(N, dtype=np.int32),
+            info=dict(cur_frame=start.copy(), steps_taken_cur_frame=np.zeros(N, dtype=np.int32), clip_idx=clip_sel,
                       summed_pos_distance=np.zeros(N, dtype=dt), quat_distance=np.zeros(N, dtype=dt),
                       joint_distance=np.zeros(N, dtype=dt),
                       steps=np.zeros(N, dtype=dt), truncation=np.zeros(N, dtype=dt)),
@@ -249,13 +261,16 @@ class EnvOracle:
         stc = stc * np.where(hit, 0, 1).astype(np.int32)
         info["steps_taken_cur_frame"], info["cur_frame"] = stc, cur
         fi = np.clip(cur, 0, self.T - 1)  # JAX gather clamps
+        cidx = info.get("clip_idx")
+        if cidx is not None:
+            fi = fi + np.asarray(cidx) * self.T
         qpos, qvel, xpos = ps["qpos"], ps["qvel"], ps["xpos"]
         free = c["free_jnt"]
         ans = self.animals()
         NA = len(ans)
-        cpos = self.clip["position"].reshape(self.T, NA, 3)
-        cquat = self.clip["quaternion"].reshape(self.T, NA, 4)
-        cang = self.clip["angular_velocity"].reshape(self.T, NA, 3)
+        cpos = self.clip["position"].reshape(-1, NA, 3)
+        cquat = self.clip["quaternion"].reshape(-1, NA, 4)
+        cang = self.clip["angular_velocity"].reshape(-1, NA, 3)
         min_z, max_z = c["healthy_z_range"]
         z32 = lambda: np.zeros(N, dtype=dt)
         tot = {k: z32() for k in ("pos", "quat", "joint", "angvel", "bodypos", "endeff", "healthy")}
@@ -313,7 +328,7 @@ class EnvOracle:
         info["quat_distance"] = dist["quat_distance"]
         action = np.asarray(action, dtype=dt)
         ctrl_cost = f32(c["ctrl_cost_weight"]) * np.sum(np.square(action), -1)
-        obs = self.get_obs(qpos, qvel, xpos, cur)
+        obs = self.get_obs(qpos, qvel, xpos, cur, cidx)
         reward = (joint_reward + pos_reward + quat_reward + angvel_reward + bodypos_reward + endeff_reward
                   + healthy_reward - ctrl_cost)
         done = fall if c["terminate_when_unhealthy"] else np.zeros(N, dtype=dt)

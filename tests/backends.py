@@ -26,19 +26,19 @@ class EmuBackend:
     def new_outputs(self, N):
         return self.e.new_outputs(N)
 
-    def reset(self, keys, fixed_start_frame=-1):
-        return self.e.reset(keys, fixed_start_frame)
+    def reset(self, keys, fixed_start_frame=-1, clip_idx=None):
+        return self.e.reset(keys, fixed_start_frame, clip_idx)
 
-    def step(self, st, out, first, first_obs, first_ii, action):
-        self.e.step(st, out, first, first_obs, first_ii, action)
+    def step(self, st, out, first, first_obs, first_ii, action, clip_idx=None):
+        self.e.step(st, out, first, first_obs, first_ii, action, clip_idx)
         return st, out
 
     def physics_step(self, st, ctrl, n):
         self.e.physics_step(st, ctrl, n)
         return st
 
-    def reward_obs(self, st, out, action):
-        self.e.reward_obs(st, out, action)
+    def reward_obs(self, st, out, action, clip_idx=None):
+        self.e.reward_obs(st, out, action, clip_idx)
         return out
 
     def pipeline_init(self, st):
@@ -74,15 +74,19 @@ class CudaBackend:
     def new_outputs(self, N):
         return {k: v.cpu().numpy() for k, v in self.nm.new_outputs(N).items()}
 
-    def reset(self, keys, fixed_start_frame=-1):
+    def reset(self, keys, fixed_start_frame=-1, clip_idx=None):
         N = keys.shape[0]
         st, out = self.nm.new_state(N), self.nm.new_outputs(N)
-        self.nm.reset(self._d(np.ascontiguousarray(keys, dtype=np.uint32).view(np.int32)), st, out, fixed_start_frame)
+        dc = None if clip_idx is None else self._d(clip_idx)
+        self.nm.reset(self._d(np.ascontiguousarray(keys, dtype=np.uint32).view(np.int32)), st, out, fixed_start_frame, clip_idx=dc)
+        if dc is not None:
+            clip_idx[...] = dc.cpu().numpy()
         return {k: v.cpu().numpy() for k, v in st.items()}, {k: v.cpu().numpy() for k, v in out.items()}
 
-    def step(self, st, out, first, first_obs, first_ii, action):
+    def step(self, st, out, first, first_obs, first_ii, action, clip_idx=None):
         dst, dout = self._dst(st), {k: self._d(out[k]) for k in OUT}
-        self.nm.step(self._d(np.asarray(action, np.float32)), dst, self._dst(first), self._d(first_obs), self._d(first_ii), dout)
+        self.nm.step(self._d(np.asarray(action, np.float32)), dst, self._dst(first), self._d(first_obs), self._d(first_ii), dout,
+                     clip_idx=None if clip_idx is None else self._d(clip_idx))
         self._back(dst, st); self._back(dout, out)
         return st, out
 
@@ -92,9 +96,9 @@ class CudaBackend:
         self._back(dst, st)
         return st
 
-    def reward_obs(self, st, out, action):
+    def reward_obs(self, st, out, action, clip_idx=None):
         dst, dout = self._dst(st), {k: self._d(out[k]) for k in OUT}
-        self.nm.reward_obs(self._d(np.asarray(action, np.float32)), dst, dout)
+        self.nm.reward_obs(self._d(np.asarray(action, np.float32)), dst, dout, clip_idx=None if clip_idx is None else self._d(clip_idx))
         self._back(dout, out)
         return out
 

@@ -81,29 +81,29 @@ class Emu:
         return dict(obs=np.zeros((N, self.obs_size), np.float32), reward=np.zeros(N, np.float32), done=np.zeros(N, np.float32),
                     metrics=np.zeros((N, 12), np.float32), info_f=np.zeros((N, 5), np.float32), info_i=np.zeros((N, 2), np.int32))
 
-    def reset(self, keys, fixed_start_frame=-1):
+    def reset(self, keys, fixed_start_frame=-1, clip_idx=None):
         keys = np.ascontiguousarray(keys, dtype=np.uint32)
         N = keys.shape[0]
         st, out = self.new_state(N), self.new_outputs(N)
         self.lib.emu_reset(self.h, N, _ptr(keys), int(fixed_start_frame), self.sp(st), _ptr(out["obs"]), _ptr(out["reward"]), _ptr(out["done"]),
-                           _ptr(out["metrics"]), _ptr(out["info_f"]), _ptr(out["info_i"]))
+                           _ptr(out["metrics"]), _ptr(out["info_f"]), _ptr(out["info_i"]), _ptr(clip_idx))
         return st, out
 
-    def step(self, st, out, first_st, first_obs, first_info_i, action):
+    def step(self, st, out, first_st, first_obs, first_info_i, action, clip_idx=None):
         action = np.ascontiguousarray(action, dtype=np.float32)
         N = action.shape[0]
         self.lib.emu_step(self.h, N, _ptr(action), self.sp(st), self.sp(first_st), _ptr(first_obs), _ptr(first_info_i),
                           _ptr(out["obs"]), _ptr(out["reward"]), _ptr(out["done"]), _ptr(out["metrics"]), _ptr(out["info_f"]),
-                          _ptr(out["info_i"]))
+                          _ptr(out["info_i"]), _ptr(clip_idx))
 
     def physics_step(self, st, ctrl, n_substeps):
         ctrl = None if ctrl is None else np.ascontiguousarray(ctrl, dtype=np.float32)
         self.lib.emu_physics_step(self.h, st["qpos"].shape[0], _ptr(ctrl), self.sp(st), n_substeps)
 
-    def reward_obs(self, st, out, action):
+    def reward_obs(self, st, out, action, clip_idx=None):
         action = np.ascontiguousarray(action, dtype=np.float32)
         self.lib.emu_reward_obs(self.h, action.shape[0], _ptr(action), self.sp(st), _ptr(out["info_i"]), _ptr(out["obs"]),
-                                _ptr(out["reward"]), _ptr(out["done"]), _ptr(out["metrics"]), _ptr(out["info_f"]))
+                                _ptr(out["reward"]), _ptr(out["done"]), _ptr(out["metrics"]), _ptr(out["info_f"]), _ptr(clip_idx))
 
     def forward_debug(self, st, ctrl, stop=0):
         N = st["qpos"].shape[0]

@@ -42,16 +42,17 @@ int emu_model_create(int n, const char* const* names, const void* const* data, c
 void emu_model_destroy(EmuModel* m) { delete m; }
 
 int emu_reset(EmuModel* m, int n, const uint32_t* keys, int fixed_start_frame, BtStatePtrs st, float* obs, float* reward, float* done,
-              float* metrics, float* info_f, int32_t* info_i) {
+              float* metrics, float* info_f, int32_t* info_i, int32_t* clip_idx) {
   std::vector<float> s(m->dev.smem_floats);
-  BtResetArgs a = {keys, fixed_start_frame, st, obs, reward, done, metrics, info_f, info_i};
+  BtResetArgs a = {keys, fixed_start_frame, st, obs, reward, done, metrics, info_f, info_i, clip_idx};
   for (int e = 0; e < n; e++) bt_prog_reset<1, EMU_DS, EMU_CS>(m->dev, s.data(), 0, e, true, a);
   return 0;
 }
 int emu_step(EmuModel* m, int n, const float* action, BtStatePtrs st, BtStatePtrs first, const float* first_obs,
-             const int32_t* first_info_i, float* obs, float* reward, float* done, float* metrics, float* info_f, int32_t* info_i) {
+             const int32_t* first_info_i, float* obs, float* reward, float* done, float* metrics, float* info_f, int32_t* info_i,
+             const int32_t* clip_idx) {
   std::vector<float> s(m->dev.smem_floats);
-  BtStepArgs a = {action, st, first, first_obs, first_info_i, obs, reward, done, metrics, info_f, info_i};
+  BtStepArgs a = {action, st, first, first_obs, first_info_i, obs, reward, done, metrics, info_f, info_i, clip_idx};
   for (int e = 0; e < n; e++) bt_prog_step<1, EMU_DS, EMU_CS>(m->dev, s.data(), 0, e, true, a);
   return 0;
 }
@@ -61,9 +62,9 @@ int emu_physics_step(EmuModel* m, int n, const float* ctrl, BtStatePtrs st, int 
   return 0;
 }
 int emu_reward_obs(EmuModel* m, int n, const float* action, BtStatePtrs st, int32_t* info_i, float* obs, float* reward,
-                   float* done, float* metrics, float* info_f) {
+                   float* done, float* metrics, float* info_f, const int32_t* clip_idx) {
   std::vector<float> s(m->dev.smem_floats);
-  BtRewardArgs a = {action, st, info_i, obs, reward, done, metrics, info_f};
+  BtRewardArgs a = {action, st, info_i, obs, reward, done, metrics, info_f, clip_idx};
   for (int e = 0; e < n; e++) bt_prog_reward<1, EMU_DS, EMU_CS>(m->dev, s.data(), 0, e, true, a);
   return 0;
 }

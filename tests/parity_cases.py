@@ -453,3 +453,55 @@ def check_physics_1_10_100(backend, name, N=8, seed=11):
         if label == "zero" and free:
             np.testing.assert_allclose(st["qpos"][:, 2], p64["qpos"][:, 2], atol=5e-3)   # same resting height
     return res
+
+
+def check_multi_clip(make_backend, N=24, T=12, n_clips=3, seed=19):
+    """RodentMultiClip: n_clips clips stacked on a leading axis; the reset draws every environment's
+    clip (randint(rng_pos, (), 0, n_clips), bit exact), seeds the root from THAT clip, and every clip gather of the step (reward
+    targets, observation window) is offset by it; auto-resets keep the clip."""
+    from brax_tracking_b200 import clips, configs, model, presets
+    import env_oracle
+    m, args, _ = presets.load("rodent")
+    cfg = configs.resolve(m, args)
+    cfg["episode_length"] = 6
+    cs = [clips.synthetic_clip(m, True, seed=k, amplitude=0.2 + 0.1 * k).as_dict() for k in range(n_clips)]
+    stacked = {k: np.stack([c[k] for c in cs]) for k in cs[0]}
+    tables = model.pack(m, cfg, stacked)
+    assert int(tables["n_clips"][0]) == n_clips
+    b = make_backend(tables)
+    o64, _ = common.oracles("rodent")
+    eo = env_oracle.EnvOracle(o64, stacked, cfg, dtype=np.float32)
+    keys = common.jax_keys(N, seed=seed)
+    cidx = np.full(N, -1, np.int32)
+    st, out = b.reset(keys, clip_idx=cidx)
+    s = eo.reset(keys)
+    assert np.array_equal(cidx, s["info"]["clip_idx"]) and len(set(cidx.tolist())) == n_clips     # drawn clips: bit exact, all used
+    assert np.array_equal(out["info_i"][:, 0], s["info"]["cur_frame"])
+    np.testing.assert_allclose(st["qpos"], s["pipeline_state"]["qpos"], atol=1.2e-7)               # root seeded from the env's own clip
+    np.testing.assert_allclose(out["obs"], s["obs"], atol=2e-5)
+    # the same keys on clip 0 alone differ wherever another clip was drawn
+    s_one = env_oracle.EnvOracle(o64, cs[0], cfg, dtype=np.float32).reset(keys)
+    assert (np.abs(s_one["obs"] - s["obs"]).max(1) > 1e-3)[cidx != 0].all()
+    first = state_from_oracle(s["info"]["first_pipeline_state"], N)
+    first_obs = np.array(s["info"]["first_obs"], np.float32)
+    first_ii = np.stack([s["info"]["first_cur_frame"], s["info"]["first_steps_taken_cur_frame"]], 1).astype(np.int32)
+    acts = common.actions(T, N, m.nu, seed=seed + 1, scale=0.3)
+    n_done = 0
+    for t in range(T):
+        stt = state_from_oracle(s["pipeline_state"], N)
+        o2 = b.new_outputs(N)
+        o2["done"][:] = s["done"]; o2["info_f"][:, 3] = s["info"]["steps"]
+        o2["info_i"][:, 0] = s["info"]["cur_frame"]; o2["info_i"][:, 1] = s["info"]["steps_taken_cur_frame"]
+        b.step(stt, o2, first, first_obs, first_ii, acts[t], clip_idx=cidx)
+        over = {k: (stt[k].reshape(N, m.nbody, 3) if k == "xpos" else stt[k]) for k in stt}
+        chk = eo.step(s, acts[t], physics_override=over)
+        s = eo.step(s, acts[t])
+        assert np.array_equal(o2["done"], s["done"]) and np.array_equal(o2["info_i"][:, 0], s["info"]["cur_frame"])
+        live = s["done"] == 0
+        n_done += int((~live).sum())
+        np.testing.assert_allclose(o2["obs"][live], chk["obs"][live], atol=2e-5, rtol=1e-6)        # the env's own clip window
+        np.testing.assert_allclose(o2["reward"][live], chk["reward"][live], atol=1e-4)
+        assert np.array_equal(o2["obs"][~live], first_obs[~live])
+        assert np.array_equal(s["info"]["clip_idx"], cidx)                                          # the clip survives auto-resets
+    assert n_done > 0
+    return dict(clips=np.bincount(cidx, minlength=n_clips).tolist(), n_done=n_done)

@@ -57,8 +57,8 @@ def test_product_never_imports_the_oracle():
 
 def test_xla_ffi_shim_type_checks(tmp_path):
     """csrc/xla_ffi_shim.cc (BtStepFfi, BtResetFfi) against a stand-in of jaxlib's typed-FFI binder (tests/ffi_mock): every
-    handler is invocable with exactly the types its binding declares -- 18 operands (9 of them aliased in/out state) + 12 results
-    for the step, 1 operand + 12 results for the reset -- and both symbols are emitted."""
+    handler is invocable with exactly the types its binding declares -- 19 operands (9 of them aliased in/out state) + 12 results
+    for the step, 1 operand + 13 results for the reset -- and both symbols are emitted."""
     import subprocess
     so = str(tmp_path / "shim.so")
     subprocess.run(["g++", "-std=c++17", "-shared", "-fPIC", "-I" + os.path.join(ROOT, "tests", "ffi_mock"), "-I" + os.path.join(ROOT, "include"),
@@ -68,6 +68,6 @@ def test_xla_ffi_shim_type_checks(tmp_path):
     assert "BtStepFfi_arity" in out and "BtResetFfi_arity" in out
     src = open(os.path.join(ROOT, "brax_tracking_b200", "csrc", "xla_ffi_shim.cc")).read()
     step = src[src.index("XLA_FFI_DEFINE_HANDLER_SYMBOL(BtStepFfi"):src.index("// wrap(env).reset")]
-    assert step.count(".Arg<") == 18 and step.count(".Ret<") == 12
+    assert step.count(".Arg<") == 19 and step.count(".Ret<") == 12
     reset = src[src.index("XLA_FFI_DEFINE_HANDLER_SYMBOL(BtResetFfi"):]
-    assert reset.count(".Arg<") == 1 and reset.count(".Ret<") == 12
+    assert reset.count(".Arg<") == 1 and reset.count(".Ret<") == 13

@@ -75,3 +75,8 @@ def test_two_rodent_model_with_inter_animal_contacts():
     bt = EmuBackend(common.setup(name, FLY_EPISODE)[3])
     r = pc.check_teacher_forced(bt, name, N=4, T=20, episode_length=FLY_EPISODE)
     assert r["n_done"] > 0
+
+
+def test_multi_clip_gather():
+    """RodentMultiClip: per-environment clip index drawn at reset, every clip gather offset by it."""
+    print(pc.check_multi_clip(EmuBackend, N=12, T=8))

@@ -107,6 +107,27 @@ def test_env_classes_against_the_oracle():
     assert np.isfinite(tr["reward"]).all() and tr["pos_reward"].shape == (T, n)
 
 
+def test_multi_clip_gather():
+    """RodentMultiClip (envs/rodent.py:377; preprocess.py:254-258): clip_idx drawn in the reset kernel, gathered in the step kernel;
+    and the host-side env class carrying info['clip_idx']."""
+    import torch
+    from backends import CudaBackend
+    print(pc.check_multi_clip(CudaBackend, N=48, T=12))
+    from brax_tracking_b200 import clips, envs
+    m, cfg, clip, _ = common.setup("rodent")
+    cs = [clips.synthetic_clip(m, True, seed=k, amplitude=0.2 + 0.1 * k) for k in range(3)]
+    env = envs.wrap(envs.RodentMultiClip(cs, mj_model=m), episode_length=20)
+    keys = common.jax_keys(64, seed=19)
+    state = env.reset(keys)
+    c0 = state.info["clip_idx"].clone()
+    assert set(c0.cpu().tolist()) == {0, 1, 2}
+    for t in range(25):
+        state = env.step(state, torch.zeros(64, m.nu, device="cuda"))
+    assert torch.equal(state.info["clip_idx"], c0) and torch.isfinite(state.obs).all()
+    r = envs.RenderRolloutWrapperTracking(env.env).reset(keys[:4], clip_idx=[2, 1, 0, 2])
+    assert r.info["clip_idx"].cpu().tolist() == [2, 1, 0, 2] and not r.info["cur_frame"].any().item()
+
+
 def test_physics_1_10_100(rodent_cuda):
     print(pc.check_physics_1_10_100(rodent_cuda, "rodent", N=8))
 

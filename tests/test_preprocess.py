@@ -64,3 +64,58 @@ def test_render_rollout_reset_starts_at_frame_zero():
     st_t, _ = b.reset(keys)                                    # the training reset draws different noise (split(rng, 4))
     assert not np.array_equal(st_t["qvel"], st["qvel"])
     assert np.abs(st["qpos"][:, :2]).max() < 2e-3              # not seeded from the clip
+
+
+def test_reference_pickle_reader_without_jax(tmp_path):
+    """main.py:57-74 unpickles a `preprocessing.preprocess.ReferenceClip` (flax dataclass of jax arrays).  Neither module exists
+    here: the restricted unpickler maps the class to a stand-in, rebuilds `jax.Array` leaves from their numpy payload
+    (`jax._src.array._reconstruct_array`) and refuses everything else."""
+    import pickle
+    import sys
+    import types
+    m, cfg, clip, _ = common.setup("rodent")
+    fields = {k: np.asarray(v)[:7] for k, v in clip.items()}
+    # build the pickle the way the reference would: fake module path for the class, jax-style reduce for two of the arrays
+    pre = types.ModuleType("preprocessing"); pp = types.ModuleType("preprocessing.preprocess")
+    jx = types.ModuleType("jax"); jsrc = types.ModuleType("jax._src"); jarr = types.ModuleType("jax._src.array")
+
+    class ReferenceClip:                                    # pickled by reference: module path + __dict__
+        pass
+    ReferenceClip.__module__, ReferenceClip.__qualname__ = "preprocessing.preprocess", "ReferenceClip"
+    pp.ReferenceClip = ReferenceClip
+
+    def _reconstruct_array(fun, args, arr_state, aval_state):
+        raise AssertionError("only referenced by name")
+    _reconstruct_array.__module__, _reconstruct_array.__qualname__ = "jax._src.array", "_reconstruct_array"
+    jarr._reconstruct_array = _reconstruct_array
+
+    class FakeJaxArray:
+        def __init__(self, a):
+            self.a = np.ascontiguousarray(a)
+
+        def __reduce__(self):
+            fun, args, state = self.a.__reduce__()
+            return _reconstruct_array, (fun, args, state, ("aval",))
+    mods = {"preprocessing": pre, "preprocessing.preprocess": pp, "jax": jx, "jax._src": jsrc, "jax._src.array": jarr}
+    sys.modules.update(mods)
+    try:
+        obj = ReferenceClip()
+        for k, v in fields.items():
+            setattr(obj, k, FakeJaxArray(v) if k in ("position", "joints") else v)
+        p = str(tmp_path / "clip.p")
+        with open(p, "wb") as f:
+            pickle.dump(obj, f)
+        with open(str(tmp_path / "multi.p"), "wb") as f:
+            pickle.dump({"walk": obj, "rear": obj}, f)
+    finally:
+        for k in mods:
+            sys.modules.pop(k, None)
+    back = preprocess.load_reference_clip_pickle(p)
+    for k, v in fields.items():
+        assert np.array_equal(getattr(back, k), v.astype(np.float32)), k
+    multi = preprocess.load_reference_clip_pickle(str(tmp_path / "multi.p"))
+    assert sorted(multi) == ["rear", "walk"] and np.array_equal(multi["walk"].joints, back.joints)
+    with open(str(tmp_path / "evil.p"), "wb") as f:          # a pickle is code: anything outside the whitelist is refused
+        pickle.dump(preprocess.process_clip, f)
+    with pytest.raises(pickle.UnpicklingError):
+        preprocess.load_reference_clip_pickle(str(tmp_path / "evil.p"))

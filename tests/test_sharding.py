@@ -24,15 +24,15 @@ def test_shard_keys_partition_the_split():
 
 
 def _flat_grad_of_mean_loss(rank, world):
-    """Gradient of a mean loss over rank `rank`'s contiguous share of a fixed batch, through ppo._bind_flat_grads
-    (every .grad a view of one flat buffer that autograd accumulates into in place)."""
+    """Gradient of a mean loss over rank `rank`'s contiguous share of a fixed batch, through ppo._bind_flat
+    (every parameter / .grad a view of one flat buffer each; autograd accumulates into the gradient views in place)."""
     import torch
     from brax_tracking_b200 import ppo
     torch.manual_seed(5)
     net = ppo.MLP([9, 8, 3], in_align=4)
     x, y = torch.randn(12, 9), torch.randn(12, 3)
     params = list(net.parameters())
-    flat = ppo._bind_flat_grads(params)
+    _, flat = ppo._bind_flat(params)
     ptrs = [p.grad.data_ptr() for p in params]
     lo, hi = parallel.shard_bounds(12, rank, world)
     for _ in range(2):                                                       # a second pass reuses the same views
@@ -69,8 +69,16 @@ def _worker(rank, world, port, n_envs, q):
     grad = _flat_grad_of_mean_loss(rank, world)
     dist.all_reduce(grad)
     grad /= world
+    # ... and the running statistics of the observations (custom_ppo.py:323-327): ONE packed all-reduce per update
+    from brax_tracking_b200 import ppo
+    rs = ppo.RunningStatistics(5, torch.device("cpu"))
+    gen = torch.Generator().manual_seed(11)
+    allx = torch.randn(3, 12, 5, generator=gen) * torch.tensor([1.0, 4.0, 0.2, 2.0, 9.0]) + torch.tensor([0.0, 3.0, -1.0, 50.0, 0.5])
+    lo2, hi2 = parallel.shard_bounds(12, rank, world)
+    for chunk in allx:
+        rs.update(chunk[lo2:hi2], world)
     if rank == 0:
-        q.put((torch.cat(gathered).numpy(), grad.numpy()))
+        q.put((torch.cat(gathered).numpy(), grad.numpy(), rs.mean.numpy(), rs.std.numpy(), float(rs.count)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -85,7 +93,16 @@ def test_two_rank_gloo_matches_single_process():
     procs = [ctx.Process(target=_worker, args=(r, world, port, n_envs, q)) for r in range(world)]
     for p in procs:
         p.start()
-    got, grad = q.get(timeout=300)
+    import queue
+    res = None
+    for _ in range(300):                                                     # a worker that died must fail the test at once
+        try:
+            res = q.get(timeout=1)
+            break
+        except queue.Empty:
+            assert all(p.is_alive() or p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    assert res is not None, "the ranks never reported"
+    got, grad, rs_mean, rs_std, rs_count = res
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -100,3 +117,10 @@ def test_two_rank_gloo_matches_single_process():
     want = np.concatenate([st["qpos"], out["obs"], out["reward"][:, None], out["done"][:, None]], 1)
     assert np.array_equal(got, want)
     np.testing.assert_allclose(grad, _flat_grad_of_mean_loss(0, 1).numpy(), atol=1e-6)   # pmean of the shard gradients
+    import torch
+    gen = torch.Generator().manual_seed(11)
+    allx = (torch.randn(3, 12, 5, generator=gen) * torch.tensor([1.0, 4.0, 0.2, 2.0, 9.0]) + torch.tensor([0.0, 3.0, -1.0, 50.0, 0.5])).numpy()
+    flat = allx.reshape(-1, 5)
+    assert rs_count == flat.shape[0]
+    np.testing.assert_allclose(rs_mean, flat.mean(0), rtol=1e-5, atol=1e-5)          # statistics of the GLOBAL batch on every rank
+    np.testing.assert_allclose(rs_std, flat.std(0), rtol=1e-4)
