@@ -62,6 +62,6 @@ static inline int bt_bind(BtDev* d, int n, const char* const* names, const void*
     if (counts[idx] != d->ncon) { snprintf(err, errlen, "con_xref must have ncon rows"); return -1; }
   }
   if (d->clip_len < d->ref_len || d->nv <= 0 || d->nbody <= 1 || d->n_animals < 1 || d->n_clips < 1) { snprintf(err, errlen, "degenerate model"); return -1; }
-  if (d->obs_size > d->smem_floats - d->o_crb) { snprintf(err, errlen, "observation row does not fit the staging region"); return -1; }
+  if (d->obs_size + 3 > d->smem_floats - d->o_crb) { snprintf(err, errlen, "observation row does not fit the staging region"); return -1; }
   return 0;
 }

@@ -144,9 +144,10 @@ struct BtEnv {
   int niter;       // solver iterations of the last substep (diagnostic)
   float cdist[CS]; // contact distances of the last collision pass (diagnostic / tests)
 
+  int obs_pad;     // 0..3, see obsbuf()
   int clip;        // this environment's reference clip (RodentMultiClip: rows clip * clip_len .. of the stacked clip tables)
 
-  BT_DEV BtEnv(const BtDev& m_, float* s_, int lane_, bool live_ = true) : m(m_), s(s_), lane(lane_), live(live_), niter(0), clip(0) {}
+  BT_DEV BtEnv(const BtDev& m_, float* s_, int lane_, bool live_ = true) : m(m_), s(s_), lane(lane_), live(live_), niter(0), obs_pad(0), clip(0) {}
 
   // ------------------------------------------------------------------ scratch regions
   BT_DEV float* qpos() const { return s + m.o_qpos; }
@@ -1702,7 +1703,9 @@ struct BtEnv {
   }
 
   // ================================================================== env layer
-  BT_DEV float* obsbuf() const { return s + m.o_crb; }  // staged observation row (crb/LD/T are dead by then)
+  // staged observation row (crb/LD/T are dead by then), shifted by obs_pad floats so that it sits at the same offset modulo 16 bytes
+  // as its destination row (bt_write_obs: 128-bit copies)
+  BT_DEV float* obsbuf() const { return s + m.o_crb + obs_pad; }
 
   // per-animal constants of the env layer (model.py: animal_rec = qadr dadr nj jbase torso 0 0 0): one record per tracked
   // free root.  Every reference env has ONE animal; the two-rodent stress model (BASELINE.json configs[3]) has two, each

@@ -2,6 +2,8 @@
 // Shared verbatim by the sm_100a kernels (bt_kernels.cu, G = 32) and the host emulation used by the CPU
 // tests (tests/host_emu, G = 1).
 #pragma once
+#include <stdint.h>
+
 #include "bt_impl.h"
 
 struct BtStepArgs {
@@ -14,9 +16,28 @@ struct BtStepArgs {
   const int32_t* clip_idx;  // [n] reference clip of every environment, or NULL (single clip)
 };
 
+// Observation row -> the caller's [n, obs_size] buffer (the largest algorithmic HBM write of the step: 2.5 - 5.2 kB per environment).
+// Rows of the reference's row-major layout are 4-byte aligned only (617 floats = 2468 B per rodent row), which rules out bulk /
+// TMA copies (16-byte aligned addresses AND sizes); the row is instead staged in shared memory at the SAME offset modulo 16 bytes as
+// its destination (BtEnv::obs_pad), so that after 0-3 head floats the body moves with 128-bit loads and coalesced 128-bit stores
+// (a quarter of the store instructions; full 16-byte write transactions, which also matters when the buffer is mapped host memory).
 template <int G, int DS, int CS>
 BT_DEV void bt_write_obs(BtEnv<G, DS, CS>& E, float* obs_row, const float* src) {
-  for (int i = E.lane; i < E.m.obs_size; i += G) obs_row[i] = src[i];
+  const int n = E.m.obs_size;
+#ifdef __CUDACC__
+  if ((((uintptr_t)obs_row ^ (uintptr_t)src) & 15) == 0) {
+    int head = (int)((16 - ((uintptr_t)obs_row & 15)) & 15) >> 2;
+    head = head < n ? head : n;
+    const int nvec = (n - head) >> 2, tail = head + 4 * nvec;
+    if (E.lane < head) obs_row[E.lane] = src[E.lane];
+    const float4* s4 = reinterpret_cast<const float4*>(src + head);
+    float4* d4 = reinterpret_cast<float4*>(obs_row + head);
+    for (int i = E.lane; i < nvec; i += G) d4[i] = s4[i];
+    if (E.lane < n - tail) obs_row[tail + E.lane] = src[tail + E.lane];
+    return;
+  }
+#endif
+  for (int i = E.lane; i < n; i += G) obs_row[i] = src[i];
 }
 
 // wrap(env).step  (custom_wrappers.py:54-80 o EpisodeWrapper.step o fruitfly.py:497-596)
@@ -50,6 +71,8 @@ BT_DEV void bt_prog_step(const BtDev& m, float* s, int lane, int env, bool live,
   if (!live) return;
   typename BtEnv<G, DS, CS>::StepOut r;
   E.reward_terms(E.ctrl(), cur_in, stc_in, r);
+  float* obs_row = a.obs + (size_t)env * m.obs_size;
+  E.obs_pad = (int)(((uintptr_t)obs_row >> 2) & 3);
   E.build_obs(r.cur_frame);
   // EpisodeWrapper.step (action_repeat = 1)
   steps += 1.f;
@@ -57,7 +80,6 @@ BT_DEV void bt_prog_step(const BtDev& m, float* s, int lane, int env, bool live,
   const float done = over ? 1.f : r.done;
   const float trunc = over ? 1.f - r.done : 0.f;
   int cur = r.cur_frame, stc = r.steps_taken;
-  float* obs_row = a.obs + (size_t)env * m.obs_size;
   if (done > 0.f) {
     // reset selection (custom_wrappers.py:62-80): restore the cached first state / obs / frame counters
     const size_t e = (size_t)env;
@@ -164,6 +186,7 @@ BT_DEV void bt_prog_reset(const BtDev& m, float* s, int lane, int env, bool live
   for (int i = lane; i < m.nu; i += G) E.ctrl()[i] = 0.f;
   W::sync();
   E.forward();  // pipeline_init = mjx.forward (leaves qacc_warmstart = qacc)
+  E.obs_pad = (int)(((uintptr_t)(a.obs + (size_t)env * m.obs_size) >> 2) & 3);
   E.build_obs(start);
   E.store_state(a.state, env, 0.f);
   bt_write_obs(E, a.obs + (size_t)env * m.obs_size, E.obsbuf());
@@ -228,6 +251,7 @@ BT_DEV void bt_prog_reward(const BtDev& m, float* s, int lane, int env, bool liv
   W::sync();
   typename BtEnv<G, DS, CS>::StepOut r;
   E.reward_terms(E.ctrl(), cur_in, stc_in, r);
+  E.obs_pad = (int)(((uintptr_t)(a.obs + (size_t)env * m.obs_size) >> 2) & 3);
   E.build_obs(r.cur_frame);
   bt_write_obs(E, a.obs + (size_t)env * m.obs_size, E.obsbuf());
   if (lane == 0) {

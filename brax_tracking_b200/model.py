@@ -670,7 +670,9 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
     lay["tmpv"] = lay["qacc_smooth"]    # solve() temp (g_k): qacc_smooth is consumed (into registers) before the first CG solve
     for k, v in lay.items():
         S("o_" + k, v)
-    off = max(off, lay["crb"] + obs_size)  # the observation row is staged over crb/LD/T at the end of the step
+    # the observation row is staged over crb/LD/T at the end of the step, shifted by up to 3 floats to the 16-byte phase of its
+    # destination row (csrc/bt_programs.h::bt_write_obs)
+    off = max(off, lay["crb"] + obs_size + 3)
     S("smem_floats", off + (-off) % 4)
     return t
 
