@@ -15,8 +15,8 @@ for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 import common  # noqa: E402
 
-N, T, EPISODE = 8, 8, 6
-for name in ("rodent", "fly_free", "fly_tethered"):
+EPISODE = 6
+for name, N, T in (("rodent", 8, 8), ("fly_free", 8, 8), ("fly_tethered", 8, 8), ("rodent_pair", 4, 6)):
     m, cfg, clip, _ = common.setup(name, EPISODE)
     _, eo = common.oracles(name, np.float64, EPISODE)
     keys = common.jax_keys(N, seed=21)

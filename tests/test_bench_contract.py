@@ -30,3 +30,24 @@ def test_other_ranks_of_the_reference_arm_exit_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                         "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_own_arm_line_has_the_contract_keys_in_the_committed_profile():
+    """The GPU arm cannot run here; the line it printed on the B200 is committed under profiles/ and must carry every key of the
+    contract, the two extra blocks (`strong`, `train`) and a roofline recomputable from its own numbers."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r2*_bench.json")))
+    assert files, "no round-2 bench line under profiles/"
+    d = json.load(open(files[-1]))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["vs_baseline"] is None and d["dtype"] == "f32" and d["gpu_launches"] == d["steps"] and d["config"]["envs_per_gpu"] == 8192
+    rf = d["roofline"]
+    assert rf["bound"] == "hbm" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12
+    assert abs(rf["achieved"] - 4776 * 8192 / (rf["avg_launch_ms"] * 1e-3) / 1e9) < 1e-6 * rf["achieved"]     # 4776 B x 8192 envs per launch
+    assert d["e2e"]["h2d_bytes_per_step"] == 8192 * 38 * 4 and d["e2e"]["d2h_bytes_per_step"] == 8192 * (617 + 2) * 4
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    if "strong" in d:
+        assert d["strong"]["scaling"] == "strong" and d["strong"]["global_envs"] == 8192
+        assert d["train"]["scaling"] == "weak" and d["train"]["value"] > 0

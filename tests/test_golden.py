@@ -37,6 +37,6 @@ def run_against_golden(make_backend, name):
             np.testing.assert_allclose(out["reward"], g["reward"][t], atol=2e-2)
 
 
-@pytest.mark.parametrize("name", ["rodent", "fly_free", "fly_tethered"])
+@pytest.mark.parametrize("name", ["rodent", "fly_free", "fly_tethered", "rodent_pair"])
 def test_emulated_programs_match_golden(name):
     run_against_golden(EmuBackend, name)

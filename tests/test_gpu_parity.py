@@ -148,7 +148,7 @@ def test_fly_elliptic_cone(name):
         print(pc.check_late_clip(bt, name, N=16, T=24, episode_length=12))
 
 
-@pytest.mark.parametrize("name", ["rodent", "fly_free", "fly_tethered"])
+@pytest.mark.parametrize("name", ["rodent", "fly_free", "fly_tethered", "rodent_pair"])
 def test_cuda_matches_golden(name):
     from backends import CudaBackend
     from test_golden import run_against_golden
