@@ -42,7 +42,15 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        # stdout carries the progress lines only: NCCL prints its version banner to fd 1 when the communicator is created
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os.dup2(saved, 1)
     env = presets.make_env(a.model, device=local)
 
     def progress(step, metrics):
