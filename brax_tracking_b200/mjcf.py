@@ -967,46 +967,45 @@ def compile_mjcf(
                         act_elems.append((e, ""))
         else:
             act_elems = [(e, "") for e in plain]
-    if True:
-        for e, sfx in act_elems:
-            at = defaults.resolve(e.tag, e, None)
-            u = {"name": at.get("name", "") + sfx}
-            if "joint" in at:
-                jname = at["joint"] + sfx
-                jid = m.name2id("joint", jname)
-                if jid < 0:
-                    raise ValueError(f"actuator joint {jname} not found")
-                u["trntype"], u["trnid"] = TRN_JOINT, jid
-            elif "tendon" in at:
-                tid = m.name2id("tendon", at["tendon"])
-                if tid < 0:
-                    raise ValueError(f"actuator tendon {at['tendon']} not found")
-                u["trntype"], u["trnid"] = TRN_TENDON, tid
-            else:
-                raise NotImplementedError("only joint/tendon transmissions are used")
-            u["gear"] = _vec(at.get("gear"), 6, [1, 0, 0, 0, 0, 0])[0]
-            gainprm = _vec(at.get("gainprm"), 3, [1, 0, 0])
-            biasprm = _vec(at.get("biasprm"), 3, [0, 0, 0])
-            dynprm = _vec(at.get("dynprm"), 3, [1, 0, 0])
-            dyntype = {"none": DYN_NONE, "integrator": DYN_INTEGRATOR, "filter": DYN_FILTER}[at.get("dyntype", "none")]
-            gaintype = {"fixed": GAIN_FIXED, "affine": GAIN_AFFINE}[at.get("gaintype", "fixed")]
-            biastype = {"none": BIAS_NONE, "affine": BIAS_AFFINE}[at.get("biastype", "none")]
-            if e.tag == "motor":
-                dyntype, gaintype, biastype = DYN_NONE, GAIN_FIXED, BIAS_NONE
-                gainprm = np.array([1.0, 0, 0])
-                biasprm = np.zeros(3)
-            elif e.tag != "general":
-                raise NotImplementedError(f"actuator shortcut <{e.tag}> is unused by the selected assets")
-            if dyntype == DYN_INTEGRATOR:
-                raise NotImplementedError("integrator dyntype unused")
-            cl = at.get("ctrllimited", "auto")
-            ctrllimited = (autolimits and "ctrlrange" in at) if cl == "auto" else (cl == "true")
-            fl = at.get("forcelimited", "auto")
-            forcelimited = (autolimits and "forcerange" in at) if fl == "auto" else (fl == "true")
-            u.update(dyntype=dyntype, gaintype=gaintype, biastype=biastype, gainprm=gainprm, biasprm=biasprm,
-                     dynprm=dynprm, ctrllimited=ctrllimited, forcelimited=forcelimited,
-                     ctrlrange=_vec(at.get("ctrlrange"), 2, [0, 0]), forcerange=_vec(at.get("forcerange"), 2, [0, 0]))
-            acts.append(u)
+    for e, sfx in act_elems:
+        at = defaults.resolve(e.tag, e, None)
+        u = {"name": at.get("name", "") + sfx}
+        if "joint" in at:
+            jname = at["joint"] + sfx
+            jid = m.name2id("joint", jname)
+            if jid < 0:
+                raise ValueError(f"actuator joint {jname} not found")
+            u["trntype"], u["trnid"] = TRN_JOINT, jid
+        elif "tendon" in at:
+            tid = m.name2id("tendon", at["tendon"])
+            if tid < 0:
+                raise ValueError(f"actuator tendon {at['tendon']} not found")
+            u["trntype"], u["trnid"] = TRN_TENDON, tid
+        else:
+            raise NotImplementedError("only joint/tendon transmissions are used")
+        u["gear"] = _vec(at.get("gear"), 6, [1, 0, 0, 0, 0, 0])[0]
+        gainprm = _vec(at.get("gainprm"), 3, [1, 0, 0])
+        biasprm = _vec(at.get("biasprm"), 3, [0, 0, 0])
+        dynprm = _vec(at.get("dynprm"), 3, [1, 0, 0])
+        dyntype = {"none": DYN_NONE, "integrator": DYN_INTEGRATOR, "filter": DYN_FILTER}[at.get("dyntype", "none")]
+        gaintype = {"fixed": GAIN_FIXED, "affine": GAIN_AFFINE}[at.get("gaintype", "fixed")]
+        biastype = {"none": BIAS_NONE, "affine": BIAS_AFFINE}[at.get("biastype", "none")]
+        if e.tag == "motor":
+            dyntype, gaintype, biastype = DYN_NONE, GAIN_FIXED, BIAS_NONE
+            gainprm = np.array([1.0, 0, 0])
+            biasprm = np.zeros(3)
+        elif e.tag != "general":
+            raise NotImplementedError(f"actuator shortcut <{e.tag}> is unused by the selected assets")
+        if dyntype == DYN_INTEGRATOR:
+            raise NotImplementedError("integrator dyntype unused")
+        cl = at.get("ctrllimited", "auto")
+        ctrllimited = (autolimits and "ctrlrange" in at) if cl == "auto" else (cl == "true")
+        fl = at.get("forcelimited", "auto")
+        forcelimited = (autolimits and "forcerange" in at) if fl == "auto" else (fl == "true")
+        u.update(dyntype=dyntype, gaintype=gaintype, biastype=biastype, gainprm=gainprm, biasprm=biasprm,
+                 dynprm=dynprm, ctrllimited=ctrllimited, forcelimited=forcelimited,
+                 ctrlrange=_vec(at.get("ctrlrange"), 2, [0, 0]), forcerange=_vec(at.get("forcerange"), 2, [0, 0]))
+        acts.append(u)
     m.nu = len(acts)
     m.na = sum(1 for u in acts if u["dyntype"] != DYN_NONE)
     a["actuator_trntype"] = np.array([u["trntype"] for u in acts], dtype=np.int32)

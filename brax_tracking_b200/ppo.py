@@ -323,13 +323,15 @@ def train(environment, num_timesteps: int, episode_length: int, action_repeat: i
           policy_hidden_layer_sizes: Sequence[int] = (256, 256), value_hidden_layer_sizes: Sequence[int] = (256, 256),
           progress_fn: Callable[[int, Dict], None] = lambda *a: None, normalize_advantage: bool = True, eval_env=None,
           policy_params_fn: Callable[..., None] = lambda *a: None, restore_checkpoint_path: Optional[str] = None,
-          checkpoint_dir: Optional[str] = None, run_evals: bool = True, matmul_precision: str = "tf32", use_cuda_graph: bool = True):
+          checkpoint_dir: Optional[str] = None, run_evals: bool = True, matmul_precision: str = "tf32", use_cuda_graph: bool = True,
+          state_out: Optional[dict] = None):
     """PPO training on the fused B200 step.  Returns (make_policy, params, metrics) like the reference (custom_ppo.py:65-506).
 
     Beyond the reference's arguments: ``checkpoint_dir`` -- rank 0 writes ``<dir>/<env_steps>.pt`` (``save_checkpoint``: normaliser,
     policy, value, optimiser, step count, sampling-generator state, environment state) after every evaluation and at the end
     (the reference saves (normaliser, policy) from ``policy_params_fn``, main.py:136-139,332-333); ``restore_checkpoint_path``
-    resumes from such a file, continuing at its ``env_steps``; ``run_evals=False`` skips the Evaluator (benchmarks);
+    resumes from such a file, continuing at its ``env_steps``; ``run_evals=False`` skips the Evaluator (benchmarks); ``state_out``: a
+    dict that receives the final ``TrainingState`` and env ``State`` (tools, tests);
     ``matmul_precision``: "tf32" (default; what XLA's DEFAULT precision gives the reference's f32 MLPs on Ampere and later GPUs)
     or "highest" (plain fp32 matmuls)."""
     torch.backends.cuda.matmul.allow_tf32 = matmul_precision == "tf32"
@@ -582,7 +584,8 @@ def train(environment, num_timesteps: int, episode_length: int, action_repeat: i
         if rank == 0:
             progress_fn(ts.env_steps, metrics)
             policy_params_fn(ts.env_steps, make_policy, (ts.normalizer.state_dict(), policy.state_dict()))
-    train.last_state = (ts, state)   # for tests / tools: the final training state and env state
+    if state_out is not None:
+        state_out.update(training_state=ts, env_state=state)
     return make_policy, (ts.normalizer.state_dict(), policy.state_dict()), metrics
 
 

@@ -319,16 +319,18 @@ def test_ppo_loop_runs_on_the_fused_step(tmp_path):
     one = {}
     for use_graph in (True, False):
         e = envs.RodentSingleClip(clip, mj_model=m)
+        so = {}
         one[use_graph] = ppo.train(e, num_timesteps=S, episode_length=cfg["episode_length"], num_envs=256, num_evals=2, run_evals=False,
-                                   use_cuda_graph=use_graph, **PPO_KW)[2]
-        one[(use_graph, "p")] = ppo.train.last_state[0].optimizer.p.clone()
+                                   use_cuda_graph=use_graph, state_out=so, **PPO_KW)[2]
+        one[(use_graph, "p")] = so["training_state"].optimizer.p.clone()
+        one[(use_graph, "n")] = float(so["training_state"].optimizer.step_count)
     g_, e_ = one[True], one[False]
     assert abs(g_["training/mean_step_reward"] - e_["training/mean_step_reward"]) < 1e-4 * abs(e_["training/mean_step_reward"]), (g_, e_)
     assert abs(g_["training/v_loss"] - e_["training/v_loss"]) < 0.05 * abs(e_["training/v_loss"]), (g_, e_)
     # graph warm-up no longer applies extra Adam steps to the first minibatch: the first Adam steps move every weight by
     # ~lr, so three extra updates would show as ~1e-3 differences; rounding differences between replay and eager stay far below
     dp = (one[(True, "p")] - one[(False, "p")]).abs()
-    assert float(dp.median()) < 1e-5 and float(ppo.train.last_state[0].optimizer.step_count) == 8, (float(dp.median()), float(dp.max()))
+    assert float(dp.median()) < 1e-5 and one[(True, "n")] == one[(False, "n")] == 8, (float(dp.median()), float(dp.max()))
     # evaluation rollout from frame 0 (main.py:136-258) + device FK for clip preprocessing (preprocess.py:144-204)
     tr = ppo.evaluate_rollout(env, act, common.jax_keys(4, seed=2), num_steps=10)
     assert tr["reward"].shape == (10, 4) and np.isfinite(tr["reward"]).all()
