@@ -852,6 +852,62 @@ struct BtEnv {
       W::sync();
     }
   }
+  // The two root->leaves sweeps that follow the qM factorisation -- w = mulM_down(v) (first half of qM v) and x = solve_down(g)
+  // (second half of qM^-1 qfrc_smooth) -- need nothing but the factor, so they walk the chains TOGETHER: one pass over the dof
+  // records, two independent recurrences per lane (a1 for M v, a2 for the solve: twice the instruction-level parallelism of a
+  // lone sweep), both sets of contact-body chain sums dropped at the segment ends.  Hand-over slots: ctop(c) and ctop(nchain + c).
+  BT_DEV void sweep_down_mul_and_solve(const float* v, const float* dscale, float* w, float* cb1, float* x, float* cb2) {
+    for (int ps = 0; ps < m.nhpass; ps++) {
+      for (int vl = lane; vl < 32; vl += G) {
+        const ChainD cd = pass_d(ps, vl);
+        if (cd.kb < cd.k0) continue;
+        const int c = cd.c, k0 = cd.k0;
+        float a1[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, a2[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (cd.pc >= 0) { bt_ld6(ctop(cd.pc), a1); bt_ld6(ctop(m.nchain + cd.pc), a2); }
+        const float* rp = cdof() + 12 * k0;
+        const float* vq = v + k0;
+        const float* dq = dscale + k0;
+        float* wq = w + k0;
+        float* xq = x + k0;
+        auto load = [&](int o, float (&R)[12], float& vk, float& dk, float& gk) {  // dof k + o
+          bt_ld12(rp + 12 * o, R);
+          vk = vq[o]; dk = dq[o]; gk = xq[o];
+        };
+        auto step = [&](const float (&R)[12], float vk, float dk, float gk, int o) {
+          wq[o] = dk * (vk + bt_dot6(R + 6, a1));
+          const float xk = gk - bt_dot6(R + 6, a2);
+          xq[o] = xk;
+          bt_axpy6(a1, R, vk);
+          bt_axpy6(a2, R, xk);
+        };
+        float A[12], B[12], va, da, ga, vb, db, gb;
+        int k = k0;
+        for (int sgi = cd.sadr; sgi < cd.sadr + cd.nseg; sgi++) {
+          const int ke = BT_LDG(m.seg_end + sgi);
+          load(0, A, va, da, ga);
+          for (; k < ke; k += 2) {
+            load(1, B, vb, db, gb);
+            step(A, va, da, ga, 0);
+            if (k + 2 <= ke) load(2, A, va, da, ga);
+            step(B, vb, db, gb, 1);
+            rp += 24; vq += 2; dq += 2; wq += 2; xq += 2;
+          }
+          if (k == ke) {
+            step(A, va, da, ga, 0);
+            k++; rp += 12; vq++; dq++; wq++; xq++;
+          }
+          const int cbi = BT_LDG(m.seg_cb + sgi);
+          if (cbi >= 0) {
+#pragma unroll
+            for (int j = 0; j < 6; j++) { cb1[6 * cbi + j] = a1[j]; cb2[6 * cbi + j] = a2[j]; }
+          }
+        }
+        bt_st6(ctop(c), a1);
+        bt_st6(ctop(m.nchain + c), a2);
+      }
+      W::sync();
+    }
+  }
   BT_DEV void solve_down(float* x, float* cbout) { sweep_down<false>(x, nullptr, x, cbout); }  // in place: g -> M^-1 x
   // y = M v through the factor: mulM_down then mulM_up
   BT_DEV void mulM_down(const float* v, float* w, float* cbout) { sweep_down<true>(v, Dd(), w, cbout); }
@@ -1624,10 +1680,12 @@ struct BtEnv {
       if (live) {
         if (phase == 0) {
           // qM * qacc_warmstart (consumed by the solver's warm-start test) through the factor
-          mulM_down(warm(), qacc(), cbJ(1));
+          // ... together with the root->leaves half of the smooth solve (both need only the factor)
+          sweep_down_mul_and_solve(warm(), Dd(), qacc(), cbJ(1), xv(), cbJ(2));
           mulM_up(qacc(), qfrc_c());
+        } else {
+          solve_down(xv(), nullptr);
         }
-        solve_down(xv(), phase == 0 ? cbJ(2) : nullptr);
       }
       if (phase == 0) {
         if (live) {

@@ -9,7 +9,7 @@
 
 // ---- scalar ints (1-element int tables, by name) ----
 #define BT_INT_SCALARS(X) \
-  X(nq) X(nv) X(nu) X(na) X(nbody) X(njnt) X(nhpass) X(napass) X(nbanc) X(ncon) X(ncb) X(nwgrp) X(nmerge)       \
+  X(nq) X(nv) X(nu) X(na) X(nbody) X(njnt) X(nhpass) X(napass) X(nbanc) X(ncon) X(ncb) X(nwgrp) X(nmerge) X(nchain) \
   X(cone) X(iterations) X(ls_iterations) X(n_frames) X(sync_mode) X(ncross) X(poison)                                          \
   /* env layer */                                                                                               \
   X(free_jnt) X(seed_root_from_clip) X(ref_len) X(clip_len) X(clip_nj) X(n_joint_idxs) X(n_body_idxs) X(n_animals) X(n_clips) \
