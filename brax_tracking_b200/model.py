@@ -563,7 +563,11 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
     # phase alignment of the step kernel's warps, one barrier per substep (bits, csrc/bt_impl.h::substep): 1 = all warps of
     # the CTA, 32 / 64 / 128 = only within a contiguous half / equal parity / equal (index mod 4); 2..16 = extra barrier
     # points; 0 = none.  Measured (rodent, 8192 envs): 0: 1.39 M (r1q), 1: 2.756 M, 32: 2.777 M, 64: 2.781 M, 128: 2.61 M.
-    S("sync_mode", int(os.environ.get("BT_SYNC", "64")))
+    sync_mode = int(os.environ.get("BT_SYNC", "64"))
+    if bin(sync_mode & (32 | 64 | 128)).count("1") > 1:
+        # two different groupings would meet on the same named barriers with different arrival counts: a deadlock
+        raise ValueError("BT_SYNC: at most one of the group-alignment bits 32 / 64 / 128 may be set")
+    S("sync_mode", sync_mode)
     # initcheck substitute: fill the scratch slice with NaN before every program (csrc/bt_impl.h::poison_scratch)
     S("poison", int(os.environ.get("BT_POISON", "0")))
     SF("timestep", m.timestep)
