@@ -1260,6 +1260,40 @@ struct BtEnv {
 
   // qfrc_constraint = J^T f  (per-dof gather over the contacts whose chain contains the dof) -> scratch + regs
   BT_DEV void jt_force(const Efc& e, const float fbase[CS][3], const float lforce[DS]) {
+#ifdef __CUDACC__
+    if (G == 32 && CS == 1 && m.jt_seg_steps > 0) {
+      // Every contact has ONE moving body and the contacts of a contact body sit in consecutive lanes (model.py: jt_seg; the
+      // rodent: 30 floor contacts on 8 bodies, segments of 1-6): the wrench stays in registers and the per-body sums are a
+      // segmented shuffle reduction (3 steps) instead of a shared-memory round trip with dependent index loads.
+      float w6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      int mask = 0, head = -1;
+      if (lane < m.ncon) {
+        float cg[12];
+        bt_ld12(congeo() + 12 * lane, cg);
+        float F[3], tq[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) F[k] = cg[3 + k] * fbase[0][0] + cg[6 + k] * fbase[0][1] + cg[9 + k] * fbase[0][2];
+        bt_cross(cg, F, tq);
+        w6[0] = tq[0]; w6[1] = tq[1]; w6[2] = tq[2]; w6[3] = F[0]; w6[4] = F[1]; w6[5] = F[2];
+        const int sm_ = BT_LDG(m.con_seg + lane);   // bits 0..4: lane + 2^s is in the same segment; bits 8..: contact body + 1 when this lane heads it
+        mask = sm_ & 0xff;
+        head = (sm_ >> 8) - 1;
+      }
+      for (int st = 0; st < m.jt_seg_steps; st++) {
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+          const float o = __shfl_down_sync(0xffffffffu, w6[j], 1 << st);
+          if ((mask >> st) & 1) w6[j] += o;
+        }
+      }
+      if (head >= 0) {
+#pragma unroll
+        for (int j = 0; j < 6; j++) cbA()[6 * head + j] = w6[j];
+      }
+      W::sync();
+    } else
+#endif
+    {
 #pragma unroll
     for (int sl = 0; sl < CS; sl++) {
       const int c = lane + sl * G;
@@ -1301,6 +1335,7 @@ struct BtEnv {
       cbA()[it] = acc;
     }
     W::sync();
+    }
     // one summed wrench per GROUP of dofs with the same contact bodies below them (in the per-contact wrench slots, which
     // are dead by now), then one dot product per dof
     float* wg = wrench();

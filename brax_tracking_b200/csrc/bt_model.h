@@ -10,7 +10,7 @@
 // ---- scalar ints (1-element int tables, by name) ----
 #define BT_INT_SCALARS(X) \
   X(nq) X(nv) X(nu) X(na) X(nbody) X(njnt) X(nhpass) X(napass) X(nbanc) X(ncon) X(ncb) X(nwgrp) X(nmerge) X(nchain) \
-  X(cone) X(iterations) X(ls_iterations) X(n_frames) X(sync_mode) X(ncross) X(poison)                                          \
+  X(cone) X(iterations) X(ls_iterations) X(n_frames) X(sync_mode) X(ncross) X(poison) X(jt_seg_steps)                                          \
   /* env layer */                                                                                               \
   X(free_jnt) X(seed_root_from_clip) X(ref_len) X(clip_len) X(clip_nj) X(n_joint_idxs) X(n_body_idxs) X(n_animals) X(n_clips) \
   X(n_endeff_idxs) X(torso_idx) X(terminate_when_unhealthy) X(steps_for_cur_frame) X(episode_length)            \
@@ -36,7 +36,7 @@
   X(jnt_type) X(jnt_qposadr) X(jnt_dofadr) X(jnt_bodyid)                                                        \
   X(dof_qposadr) X(dof_limited) X(dof_vflag) X(dof_irec) X(merge_adr) X(merge_dst) X(merge_src)                 \
   X(cchild_id) X(hpass_desc) X(apass_desc) X(seg_end) X(seg_cb)                                   \
-  X(cgeom_bodyid) X(con_g1) X(con_g2) X(con_cb1) X(con_cb2) X(con_ref) X(con_fn) X(con_sub) X(con_dim) X(con_xref) X(con_xslot) \
+  X(cgeom_bodyid) X(con_g1) X(con_g2) X(con_cb1) X(con_cb2) X(con_ref) X(con_fn) X(con_sub) X(con_dim) X(con_xref) X(con_xslot) X(con_seg) \
   X(cbcon_adr) X(cbcon_cs) X(dof_wgrp) X(wgrp_adr) X(wgrp_cb) X(cb_lastdof)                                     \
   X(joint_idxs) X(body_idxs) X(endeff_idxs) X(animal_rec) X(jidx_adr) X(bidx_adr) X(eidx_adr)
 

@@ -464,6 +464,27 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
         for ci, sg in cbcon[k]:
             cbcon_c.append(ci); cbcon_s.append(sg)
         cbcon_adr.append(len(cbcon_c))
+    # contact -> contact-body sums by a segmented warp-shuffle reduction (csrc/bt_impl.h::jt_force) when every contact has exactly
+    # one moving body (geom2's), the contacts of a contact body are consecutive, and all contacts fit one lane each
+    con_cb = [cb_slot.get(c["b2"], -1) for c in con]
+    jt_seg = (0 < ncon <= lanes and ncross == 0 and all(c["b1"] not in cb_slot for c in con) and all(x >= 0 for x in con_cb)
+              and all(con_cb[i] <= con_cb[i + 1] for i in range(ncon - 1)))
+    seg = np.zeros(max(ncon, 1), dtype=np.int32)
+    steps = 0
+    if jt_seg:
+        maxlen = max(con_cb.count(k) for k in set(con_cb))
+        steps = int(np.ceil(np.log2(maxlen))) if maxlen > 1 else 0
+        for i in range(ncon):
+            bits = 0
+            for st in range(steps):
+                j = i + (1 << st)
+                if j < ncon and con_cb[j] == con_cb[i]:
+                    bits |= 1 << st
+            head = con_cb[i] + 1 if (i == 0 or con_cb[i - 1] != con_cb[i]) else 0
+            seg[i] = bits | (head << 8)
+        steps = max(steps, 1)      # 0 would disable the path: a model whose segments all have one contact still takes it
+    S("jt_seg_steps", steps if jt_seg else 0)
+    t["con_seg"] = seg
     dofcb = [[] for _ in range(nv)]
     for k, b in enumerate(cbs):
         for d in chain(b):
