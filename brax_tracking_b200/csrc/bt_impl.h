@@ -104,6 +104,14 @@ struct BtLanes<32> {
     else if (id == 3) asm volatile("bar.sync 3, %0;" ::"r"(cnt << 5) : "memory");
     else asm volatile("bar.sync 4, %0;" ::"r"(cnt << 5) : "memory");
   }
+  // "any" over the warps of equal parity (group_sync mode 1) on the same named barriers
+  static BT_DEV int group_any(int p) {
+    const int nw = blockDim.x >> 5, w = threadIdx.x >> 5, r = w & 1, cnt = ((nw - r + 1) >> 1) << 5;
+    int out;
+    if (r == 0) asm volatile("{\n.reg .pred q, o;\nsetp.ne.s32 q, %1, 0;\nbarrier.red.or.pred o, 1, %2, q;\nselp.s32 %0, 1, 0, o;\n}" : "=r"(out) : "r"(p), "r"(cnt) : "memory");
+    else asm volatile("{\n.reg .pred q, o;\nsetp.ne.s32 q, %1, 0;\nbarrier.red.or.pred o, 2, %2, q;\nselp.s32 %0, 1, 0, o;\n}" : "=r"(out) : "r"(p), "r"(cnt) : "memory");
+    return out;
+  }
   // 8-lane groups: lane r (< 7) of a group holds u[0]; every lane of the group receives all seven values
   // (called by all 32 lanes: the chain loops of aba_factor are warp-uniform)
   template <int NR>
@@ -124,6 +132,7 @@ struct BtLanes<1> {
   static BT_DEV void cta_sync() {}
   static BT_DEV void group_sync(int) {}
   static BT_DEV int cta_any(int p) { return p; }
+  static BT_DEV int group_any(int p) { return p; }
   template <int NR>
   static BT_DEV void gather7(const float* u, float* U, int) {
     for (int c = 0; c < 7; c++) U[c] = u[c];
@@ -1673,7 +1682,7 @@ struct BtEnv {
       }
       // the warps share this loop's code whatever their iteration; with sync bit 16 they also walk it in step (a warp that
       // has converged idles through the remaining passes: it would wait at the next substep barrier anyway)
-      if (m.sync_mode & 16) { if (!W::cta_any(active)) break; }
+      if (m.sync_mode & 16) { if (!((m.sync_mode & 1024) ? W::group_any(active) : W::cta_any(active))) break; }
       else if (!active) break;
     }
     niter = it;
@@ -1688,6 +1697,7 @@ struct BtEnv {
   BT_DEV bool substep(bool do_euler, int stop = BT_STOP_NONE, int frame = 0) {
     // `live` is warp-uniform and `stop` / `do_euler` are CTA-uniform, so every warp of the CTA reaches every barrier
     // sync_mode bits: 1 substep start, 2 after the tree pass, 4 before each factorisation, 8 before collision, 16 every CG pass
+    //                 (1024: the extra points 2..16 align the warps of equal parity only, as bit 64 does at the substep start)
     const int sm = m.sync_mode;
     if (sm & 1) W::cta_sync();
     if (sm & 32) W::group_sync(0);
@@ -1695,12 +1705,12 @@ struct BtEnv {
     if (sm & 128) W::group_sync(2);
     if (live) tree_forward();
     if (stop == BT_STOP_TREE) return false;
-    if (sm & 2) W::cta_sync();
+    if (sm & 2) { if (sm & 1024) W::group_sync(1); else W::cta_sync(); }
     if (live) smooth_forces();
     if (stop == BT_STOP_SMOOTH) return false;
     const float h = m.timestep;
     for (int phase = 0; phase < (do_euler ? 2 : 1); phase++) {
-      if (sm & 4) W::cta_sync();
+      if ((sm & 4) && !(sm & (phase == 0 ? 4096 : 2048))) { if (sm & 1024) W::group_sync(1); else W::cta_sync(); }  // 2048 / 4096: first / second only
       if (live) {
         if (phase == 0) {
           // factor qM; the spare rows of the sweep finish qfrc_smooth (RNE bias) and run the first half of the smooth solve
@@ -1728,7 +1738,7 @@ struct BtEnv {
           W::sync();
         }
         if (stop == BT_STOP_QACC_SMOOTH) return false;
-        if (sm & 8) W::cta_sync();
+        if (sm & 8) { if (sm & 1024) W::group_sync(1); else W::cta_sync(); }
         if (live) collide();
         if (stop == BT_STOP_COLLISION) return false;
         solve_constraints();

@@ -280,6 +280,10 @@ def test_poisoned_scratch_and_scheduling_invariance():
         variants = {"poison": (dict(tables, poison=np.array([1], np.int32)), None),
                     "sync=1": (dict(tables, sync_mode=np.array([1], np.int32)), None),
                     "sync=0": (dict(tables, sync_mode=np.array([0], np.int32)), None),
+                    "sync=64": (dict(tables, sync_mode=np.array([64], np.int32)), None),
+                    # every extra alignment point, among the warps of equal parity (incl. the barrier-reduction of the CG loop)
+                    "sync=64+1024+2+4+8+16": (dict(tables, sync_mode=np.array([64 + 1024 + 30], np.int32)), None),
+                    "sync=1+2+4+8+16": (dict(tables, sync_mode=np.array([31], np.int32)), None),
                     "warps=3": (tables, {"BT_WARPS": "3"}), "warps=1": (tables, {"BT_WARPS": "1"})}
         for label, (tb, env) in variants.items():
             st, out = rollout(tb, env)

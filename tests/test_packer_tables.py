@@ -126,3 +126,22 @@ def test_regions_with_128_bit_accesses_are_aligned(name):
     views = ("o_cbA", "o_wrench")                               # sub-views of T / of Dd | cbJ, not regions of their own
     nxt = min(int(v[0]) for k, v in t.items() if k.startswith("o_") and k not in views and int(v[0]) > int(t["o_T"][0]))
     assert int(t["o_T"][0]) + need <= nxt
+
+
+def test_default_alignment_mode_follows_the_environments_per_sm(monkeypatch):
+    """model.default_sync_mode: one extra parity-group barrier before the Euler factorisation when a barrier group has 7-8 warps
+    (rodent 14, flies 16 environments per SM), the substep barrier alone for the two-rodent model (6 per SM); BT_SYNC overrides and
+    rejects groupings that would meet on the same named barriers with different arrival counts."""
+    from brax_tracking_b200 import model
+    monkeypatch.delenv("BT_SYNC", raising=False)
+    for name, want in (("rodent", 64 | 1024 | 4 | 4096), ("fly_free", 64 | 1024 | 4 | 4096), ("fly_tethered", 64 | 1024 | 4 | 4096),
+                       ("rodent_pair", 64)):
+        t = common.setup(name)[3]
+        assert int(t["sync_mode"][0]) == want, name
+        assert model.default_sync_mode(int(t["smem_floats"][0])) == want
+    monkeypatch.setenv("BT_SYNC", "1")
+    assert model.default_sync_mode(4000) == 1
+    for bad in ("96", "192", str(32 | 1024 | 4), str(128 | 1024 | 16)):
+        monkeypatch.setenv("BT_SYNC", bad)
+        with pytest.raises(ValueError):
+            model.default_sync_mode(4000)
