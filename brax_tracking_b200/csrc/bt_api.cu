@@ -89,7 +89,7 @@ static inline BtLaunchCfg cfg_for(const BtModel* m, int n_envs, void* stream) {
   int ctas = (n_envs + warps - 1) / warps;
   if (ctas > m->max_ctas) ctas = m->max_ctas;
   if (ctas < 1) ctas = 1;
-  BtLaunchCfg c = {ctas, warps * 32, (int)((size_t)m->dev.smem_floats * 4 * warps), (cudaStream_t)stream, warps};
+  BtLaunchCfg c = {ctas, warps * 32, (int)((size_t)m->dev.sh_stage_floats * 4 + (size_t)m->dev.smem_floats * 4 * warps), (cudaStream_t)stream, warps};
   return c;
 }
 #define BT_LAUNCHED()                    \
@@ -143,7 +143,12 @@ int bt_model_create(int n, const char* const* names, const void* const* data, co
   e = cudaGetDeviceProperties(&prop, device);
   if (e != cudaSuccess) { snprintf(g_err, sizeof(g_err), "cudaGetDeviceProperties failed: %s", cudaGetErrorString(e)); return fail(BT_E_CUDA); }
   const size_t per_env = (size_t)m->dev.smem_floats * 4;
-  int warps = (int)(prop.sharedMemPerBlockOptin / per_env);
+  const size_t staged = (size_t)m->dev.sh_stage_floats * 4;   // CTA-shared constant records in front of the environments' slices
+  if (staged > prop.sharedMemPerBlockOptin || m->dev.sh_stage_floats < 0 || (m->dev.sh_stage_floats & 3)) {
+    snprintf(g_err, sizeof(g_err), "sh_stage_floats = %d is not a multiple of 4 within shared memory", m->dev.sh_stage_floats);
+    return fail(BT_E_ARG);
+  }
+  int warps = (int)((prop.sharedMemPerBlockOptin - staged) / per_env);
   if (warps > m->ops->max_warps) warps = m->ops->max_warps;
   if (warps < 1) {
     snprintf(g_err, sizeof(g_err), "per-environment scratch (%zu B) exceeds shared memory", per_env);
@@ -152,7 +157,7 @@ int bt_model_create(int n, const char* const* names, const void* const* data, co
   if (const char* w = getenv("BT_WARPS")) { int v = atoi(w); if (v >= 1 && v <= warps) warps = v; }
   m->warps = warps;
   m->max_ctas = prop.multiProcessorCount;
-  m->smem_bytes = (int)(per_env * warps);
+  m->smem_bytes = (int)(staged + per_env * warps);
   {
     const BtVariantOps* o = m->ops;
     cudaError_t pe = o->prepare_step(m->smem_bytes);

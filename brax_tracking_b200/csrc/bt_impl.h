@@ -158,6 +158,28 @@ struct BtEnv {
 
   BT_DEV BtEnv(const BtDev& m_, float* s_, int lane_, bool live_ = true) : m(m_), s(s_), lane(lane_), live(live_), niter(0), obs_pad(0), clip(0) {}
 
+  // ------------------------------------------------------------------ constant records shared by the warps of the CTA
+  // N4 consecutive 128-bit words of the record table at offset `off` of sh_tab, starting at float `idx`: from shared memory when
+  // the kernel staged the table (model.py: sh_stage_floats; tables are staged whole and in order, so "starts below the limit"
+  // means staged), else through the read-only path.  Two explicit paths: a generic load could be neither hoisted above the
+  // scratch stores nor served by the read-only path (measured: -2.5 % on the fly).
+  // kSmallModel: the 2-slot variant serves the fly models (nv <= 64), whose tables fit the L1 (16 x 12 KB of scratch) and which
+  // lost 1.5 - 2.4 % to the mere presence of the second path (same-box A/B, profiles/r2l_staged_records.txt): compiled out there,
+  // and model.py stages nothing for them.
+  static constexpr bool kSmallModel = DS <= 2;
+  template <int N4>
+  BT_DEV void crec(const float* tab, int off, int idx, float* o) const {   // tab = the table on its own (== sh_tab + off)
+#ifdef __CUDACC__
+    extern __shared__ __align__(16) float bt_cta_smem[];
+    if (!kSmallModel && off < m.sh_stage_floats) {
+#pragma unroll
+      for (int q = 0; q < N4; q++) bt_ld4(bt_cta_smem + off + idx + 4 * q, o + 4 * q);
+      return;
+    }
+#endif
+#pragma unroll
+    for (int q = 0; q < N4; q++) bt_ldg4(tab + idx + 4 * q, o + 4 * q);
+  }
   // ------------------------------------------------------------------ scratch regions
   BT_DEV float* qpos() const { return s + m.o_qpos; }
   BT_DEV float* qvel() const { return s + m.o_qvel; }
@@ -218,15 +240,13 @@ struct BtEnv {
     // packed constants (model.py: body_rec = pos quat jntadr jntnum parent ref; jnt_rec = type qposadr dofadr at_origin pos
     // axis qpos0): three 128-bit loads each
     float br[12];
-#pragma unroll
-    for (int q4 = 0; q4 < 3; q4++) bt_ldg4(m.body_rec + 12 * b + 4 * q4, br + 4 * q4);
+    crec<3>(m.body_rec, m.sho_body_rec, 12 * b, br);
     float p[3] = {br[0], br[1], br[2]};
     float q[4] = {br[3], br[4], br[5], br[6]};
     const int jadr = (int)br[7], jnum = (int)br[8];
     for (int jj = 0; jj < jnum; jj++) {
       float jr[12];
-#pragma unroll
-      for (int q4 = 0; q4 < 3; q4++) bt_ldg4(m.jnt_rec + 12 * (jadr + jj) + 4 * q4, jr + 4 * q4);
+      crec<3>(m.jnt_rec, m.sho_jnt_rec, 12 * (jadr + jj), jr);
       const int qa = (int)jr[1], da = (int)jr[2];
       if ((int)jr[0] == BT_JNT_FREE) {
         // a free joint hangs off the world: the "local" frame is the absolute pose
@@ -324,8 +344,7 @@ struct BtEnv {
     const float* cv = pvec();
     float pos[3], quat[4], cvel[6], cacc[6], rp[3];
     float br[16];  // packed constants (model.py: bl_rec = ipos iquat inertia mass | fluidbox lastdof ref)
-#pragma unroll
-    for (int q4 = 0; q4 < 4; q4++) bt_ldg4(m.bl_rec + 16 * b + 4 * q4, br + 4 * q4);
+    crec<4>(m.bl_rec, m.sho_bl_rec, 16 * b, br);
     const int rs = (int)br[15];
 #pragma unroll
     for (int k = 0; k < 3; k++) { pos[k] = xpos()[3 * b + k]; rp[k] = ref()[3 * rs + k]; }
@@ -1351,7 +1370,14 @@ struct BtEnv {
     for (int it = lane; it < m.nwgrp * 6; it += G) {
       const int g = it / 6, j = it - g * 6;
       float acc = 0.f;
-      for (int k = BT_LDG(m.wgrp_adr + g), k1 = BT_LDG(m.wgrp_adr + g + 1); k < k1; k++) acc += cbA()[6 * BT_LDG(m.wgrp_cb + k) + j];
+      if (!kSmallModel && m.wgrp_contig) {
+        // the contact bodies below a dof are a contiguous range (DFS numbering): one packed load, then independent shared loads
+        const int rg = BT_LDG(m.wgrp_rng + g);
+        const float* p = cbA() + 6 * (rg & 0xffff) + j;
+        for (int k = rg >> 16; k > 0; k--, p += 6) acc += *p;
+      } else {
+        for (int k = BT_LDG(m.wgrp_adr + g), k1 = BT_LDG(m.wgrp_adr + g + 1); k < k1; k++) acc += cbA()[6 * BT_LDG(m.wgrp_cb + k) + j];
+      }
       wg[it] = acc;
     }
     W::sync();

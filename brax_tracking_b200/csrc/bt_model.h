@@ -10,7 +10,7 @@
 // ---- scalar ints (1-element int tables, by name) ----
 #define BT_INT_SCALARS(X) \
   X(nq) X(nv) X(nu) X(na) X(nbody) X(njnt) X(nhpass) X(napass) X(nbanc) X(ncon) X(ncb) X(nwgrp) X(nmerge) X(nchain) \
-  X(cone) X(iterations) X(ls_iterations) X(n_frames) X(sync_mode) X(ncross) X(poison) X(jt_seg_steps)                                          \
+  X(cone) X(iterations) X(ls_iterations) X(n_frames) X(sync_mode) X(ncross) X(poison) X(jt_seg_steps) X(wgrp_contig)                                          \
   /* env layer */                                                                                               \
   X(free_jnt) X(seed_root_from_clip) X(ref_len) X(clip_len) X(clip_nj) X(n_joint_idxs) X(n_body_idxs) X(n_animals) X(n_clips) \
   X(n_endeff_idxs) X(torso_idx) X(terminate_when_unhealthy) X(steps_for_cur_frame) X(episode_length)            \
@@ -18,7 +18,9 @@
   /* per-environment scratch layout (offsets in floats) */                                                      \
   X(o_qpos) X(o_qvel) X(o_act) X(o_ctrl) X(o_warm) X(o_xpos) X(o_xquat) X(o_cdof) X(o_crb) X(o_Dinv) X(o_Dd)    \
   X(o_cbJ) X(o_pvec) X(o_T) X(o_ref) X(o_aforce) X(o_actdot) X(o_qfrc_smooth) X(o_qacc_smooth) X(o_qacc) X(o_x) \
-  X(o_search) X(o_qfrc_c) X(o_tmpv) X(o_wrench) X(o_cbA) X(smem_floats)
+  X(o_search) X(o_qfrc_c) X(o_tmpv) X(o_wrench) X(o_cbA) X(smem_floats)                                            \
+  /* CTA-shared constant records (offsets into sh_tab; the first sh_stage_floats floats are staged in shared memory) */ \
+  X(sh_stage_floats) X(sho_body_rec) X(sho_bl_rec) X(sho_jnt_rec)
 
 // ---- scalar floats ----
 #define BT_FLT_SCALARS(X) \
@@ -37,7 +39,7 @@
   X(dof_qposadr) X(dof_limited) X(dof_vflag) X(dof_irec) X(merge_adr) X(merge_dst) X(merge_src)                 \
   X(cchild_id) X(hpass_desc) X(apass_desc) X(seg_end) X(seg_cb)                                   \
   X(cgeom_bodyid) X(con_g1) X(con_g2) X(con_cb1) X(con_cb2) X(con_ref) X(con_fn) X(con_sub) X(con_dim) X(con_xref) X(con_xslot) X(con_seg) \
-  X(cbcon_adr) X(cbcon_cs) X(dof_wgrp) X(wgrp_adr) X(wgrp_cb) X(cb_lastdof)                                     \
+  X(cbcon_adr) X(cbcon_cs) X(dof_wgrp) X(wgrp_adr) X(wgrp_cb) X(wgrp_rng) X(cb_lastdof)                                     \
   X(joint_idxs) X(body_idxs) X(endeff_idxs) X(animal_rec) X(jidx_adr) X(bidx_adr) X(eidx_adr)
 
 // ---- float tables ----
@@ -45,7 +47,7 @@
   X(qpos0) X(dof_armature) X(dof_damping) X(dof_range) X(dof_solref) X(dof_solimp) X(dof_margin) X(dof_invweight0) \
   X(cgeom_pos) X(cgeom_quat) X(cgeom_size)                                                                      \
   X(con_mu) X(con_solref) X(con_solimp) X(con_includemargin) X(con_invweight)                                   \
-  X(act_rec) X(wrap_rec) X(dof_rec) X(dofact_rec) X(body_rec) X(jnt_rec) X(bl_rec)                              \
+  X(act_rec) X(wrap_rec) X(dof_rec) X(dofact_rec) X(body_rec) X(jnt_rec) X(bl_rec) X(sh_tab)                                                    \
   X(clip_position) X(clip_quaternion) X(clip_joints) X(clip_body_positions) X(clip_angular_velocity)
 
 struct BtDev {

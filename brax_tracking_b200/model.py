@@ -507,6 +507,11 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
     for key in grp_list:
         wgrp_cb.extend(key); wgrp_adr.append(len(wgrp_cb))
     S("nwgrp", len(grp_list))
+    # contact bodies are numbered in DFS order, so the ones below a dof are a contiguous range: first | count << 16 (one load, no
+    # dependent index loads in the summation loop); 0 in wgrp_contig keeps the index list
+    contig = all(list(key) == list(range(key[0], key[0] + len(key))) for key in grp_list) and os.environ.get("BT_WGRP_CONTIG", "1") != "0"
+    S("wgrp_contig", int(contig))
+    t["wgrp_rng"] = _i([key[0] | (len(key) << 16) for key in grp_list]) if grp_list and contig else Z(max(len(grp_list), 1), np.int32)
     assert 6 * len(grp_list) <= 6 * max(ncon, 1), "the group wrench sums reuse the per-contact wrench slots"
     t["dof_wgrp"] = dof_wgrp; t["wgrp_adr"] = _i(wgrp_adr); t["wgrp_cb"] = _i(wgrp_cb) if wgrp_cb else Z(1, np.int32)
     t["cbcon_adr"] = _i(cbcon_adr); t["cbcon_c"] = _i(cbcon_c) if cbcon_c else Z(1, np.int32)
@@ -694,6 +699,36 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
     off = max(off, lay["crb"] + obs_size + 3)
     S("smem_floats", off + (-off) % 4)
     S("sync_mode", default_sync_mode(int(t["smem_floats"][0])))
+    # ------------------------------------------------------------------ constant records shared by the warps of a CTA
+    # The per-body / per-joint constant records that the body-parallel passes of EVERY substep read (body_frame, body_local: 10.7 KB
+    # for the rodent) are one contiguous table, `sh_tab`; the kernels copy its first `sh_stage_floats` floats (whole record tables,
+    # in this order) into the shared memory that the per-environment slices leave free and read them from there (BtEnv::crec).
+    # Why: with 14 x 16 KB of scratch the L1 is 22 KB against ~31 KB of tables touched per substep -- a cyclic pattern that an LRU
+    # cache misses every time (ncu, rodent: 4.2 M L1 miss sectors per launch at 14 warps per CTA against 1.8 M at 12, where the
+    # carve-out leaves 55 KB of L1).  Tables that do not fit are read from global memory as before.  Measured
+    # (profiles/r2l_staged_records.txt): rodent +1.2 %, two rodents +3.1 %, flies +0.5 %; the actuator / dof records gain nothing.
+    order = ("body_rec", "bl_rec", "jnt_rec")
+    parts, so = [], 0
+    for k in order:
+        v = np.asarray(t[k], dtype=np.float32)
+        S("sho_" + k, so)
+        pad = (-v.size) % 4
+        parts.append(np.concatenate([v, np.zeros(pad, np.float32)]))
+        so += v.size + pad
+    t["sh_tab"] = np.concatenate(parts)
+    env_bytes = 4 * int(t["smem_floats"][0])
+    need_ds, need_cs = (nv + 31) // 32, max((ncon + 31) // 32, 1)
+    max_warps = MAX_WARPS_PER_CTA if (need_ds <= 3 and need_cs <= 1) else 8      # csrc/bt_ops.h: BT_VARIANT_MAX_WARPS
+    budget = SMEM_BYTES_PER_SM - min(max_warps, SMEM_BYTES_PER_SM // env_bytes) * env_bytes   # what the environments leave free
+    stage = 0
+    # (the 2-slot kernel variant -- nv <= 64: the fly models -- reads these records from global memory: csrc/bt_impl.h, kSmallModel)
+    nstage = 0 if need_ds <= 2 else int(os.environ.get("BT_STAGE", len(order)))   # BT_STAGE = n: at most the first n tables
+    for k in order[:nstage]:
+        end = int(t["sho_" + k][0]) + t[k].size + (-t[k].size) % 4
+        if 4 * end > budget:
+            break
+        stage = end
+    S("sh_stage_floats", stage)
     return t
 
 

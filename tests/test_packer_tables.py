@@ -71,6 +71,10 @@ def test_wrench_groups_and_merge_lists(name):
         g = t["dof_wgrp"][d]
         got = set(t["wgrp_cb"][t["wgrp_adr"][g]:t["wgrp_adr"][g + 1]]) if g >= 0 else set()
         assert got == below[d]
+        if g >= 0 and int(t["wgrp_contig"][0]):   # the packed (first | count << 16) form the kernel reads
+            rg = int(t["wgrp_rng"][g])
+            assert set(range(rg & 0xffff, (rg & 0xffff) + (rg >> 16))) == below[d]
+    assert int(t["wgrp_contig"][0]) == 1           # DFS numbering of the contact bodies: true for every shipped model
     # link records: every moving body is either the record of its dof or merged into it exactly once
     lastdof = np.asarray(m.a["body_lastdof"])
     owner = {}
