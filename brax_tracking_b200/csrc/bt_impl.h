@@ -662,6 +662,9 @@ struct BtEnv {
         if (row == 7) { ix[i][j] = 0; sg[i][j] = 0.f; }
         ix[i][j] += 4 * (row == 6 ? m.o_T : m.o_crb);  // byte offset from the scratch base; + rb * pmul selects the record
 #ifdef __CUDACC__
+        // ... made an ABSOLUTE 32-bit shared-memory address: the per-step address is then one multiply-add (rb * pmul + ix);
+        // left relative to `s`, every step re-derived the shared window base (S2UR SR_CgaCtaId, ULEA, LEA) and added it six times
+        ix[i][j] += (int)__cvta_generic_to_shared(s);
         // opaque to the optimiser: otherwise the decode above is rematerialised inside the per-dof loop
         asm volatile("" : "+r"(ix[i][j]), "+f"(sg[i][j]));
 #endif
@@ -696,6 +699,7 @@ struct BtEnv {
         const float* recp = cdof() + 12 * kc;
         const float* xp = X + kc;
         float* dp = Dinv() + kc;
+        float* ddp = Dd() + kc;   // (its own cursor: addressed off `s`, the store re-derived the shared window base in every step)
         float* outp[kNR];
 #pragma unroll
         for (int i = 0; i < kNR; i++) outp[i] = s + rbase[i] + kc * rstride[i];
@@ -714,7 +718,11 @@ struct BtEnv {
 #endif
 #pragma unroll
               for (int j = 0; j < 6; j++)
+#ifdef __CUDACC__
+                a[i][j] += sg[i][j] * *reinterpret_cast<const float*>(__cvta_shared_to_generic((size_t)(unsigned)(off + ix[i][j])));
+#else
                 a[i][j] += sg[i][j] * *reinterpret_cast<const float*>(reinterpret_cast<const char*>(s) + off + ix[i][j]);
+#endif
             }
           }
           bt_ld6(recp, S);
@@ -735,12 +743,12 @@ struct BtEnv {
               // one store per row: G_k[row] = U_row / D (rows 0..5); qfrc_smooth_k = x_k (row 6; a scratch slot when !kRne);
               // xv_k = g_k = u_k / D_k (row 7, consumed by solve_down)
               *outp[i] = rc[i][2] * ui + rc[i][3] * xk;
-              if (rl + i == 0) { *dp = inv; Dd()[kc] = D; }
+              if (rl + i == 0) { *dp = inv; if (kRne) *ddp = D; }   // (the pivots themselves are only read by M v, after the qM factor)
               bt_axpy6(a[i], U, -ui);
             }
           }
           if (t + 1 < nstep) {
-            kc--; recp -= 12; xp--; dp--;
+            kc--; recp -= 12; xp--; dp--; ddp--;
 #pragma unroll
             for (int i = 0; i < kNR; i++) outp[i] -= rstride[i];
           }
