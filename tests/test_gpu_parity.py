@@ -251,8 +251,9 @@ def test_poisoned_scratch_and_scheduling_invariance():
     """compute-sanitizer is closed on this pool (profiles/r2a_sanitizer.txt); what stands in for initcheck / racecheck:
       * `poison`: every program first fills its shared-memory slice with NaN -- a read of anything it did not write itself would
         surface in the outputs; they must be bit-identical to the unpoisoned run;
-      * scheduling: warps per CTA (which warps share an SM / a barrier), barrier placement (BT_SYNC) and the position of an
-        environment in the batch change every inter-warp timing; outputs must not change by a single bit."""
+      * scheduling: warps per CTA (which warps share an SM / a barrier), barrier placement (BT_SYNC), where the constant records are
+        read from (staged in shared memory or global) and the position of an environment in the batch change every inter-warp
+        timing; outputs must not change by a single bit."""
     import os
     from backends import CudaBackend
     from brax_tracking_b200 import model as model_mod
@@ -284,6 +285,8 @@ def test_poisoned_scratch_and_scheduling_invariance():
                     # every extra alignment point, among the warps of equal parity (incl. the barrier-reduction of the CG loop)
                     "sync=64+1024+2+4+8+16": (dict(tables, sync_mode=np.array([64 + 1024 + 30], np.int32)), None),
                     "sync=1+2+4+8+16": (dict(tables, sync_mode=np.array([31], np.int32)), None),
+                    # constant records read from global memory instead of the copy staged in shared memory (BtEnv::crec)
+                    "stage=0": (dict(tables, sh_stage_floats=np.array([0], np.int32)), None),
                     "warps=3": (tables, {"BT_WARPS": "3"}), "warps=1": (tables, {"BT_WARPS": "1"})}
         for label, (tb, env) in variants.items():
             st, out = rollout(tb, env)
