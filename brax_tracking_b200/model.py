@@ -397,16 +397,23 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
             for ln, c in enumerate(cs[q:q + 32]):
                 row[ln] = desc[c]
             passes.append(row)
-    # the factor sweep walks four chains at a time (8-lane groups), by DEPTH level, deepest first: descriptor per (pass, group)
-    apasses = []
-    for L in range(nclev - 1, -1, -1):
-        cs = [c for c in corder if clevel[c] == L]
-        for q in range(0, len(cs), 4):
-            row = np.zeros((4, 8), dtype=np.int32)
-            row[:, 1] = -1
-            for g, c in enumerate(cs[q:q + 4]):
-                row[g] = desc[c]
-            apasses.append(row)
+    # the factor sweep walks four chains at a time (8-lane groups), leaves first; a pass lasts as long as its longest chain.
+    # List scheduling by critical path: among the chains whose children are all done, a pass takes the four with the longest
+    # remaining way to the root (own dofs + ancestors'), so the chains nobody waits for fill the groups that would idle
+    # (rodent: 24 + 8 + 6 = 38 serial dof steps instead of 24 + 9 + 6 by depth level; two rodents 53 instead of 72)
+    to_root = np.zeros(nchain, dtype=np.int64)
+    for c in sorted(range(nchain), key=lambda c: clevel[c]):
+        to_root[c] = chain_len[c] + (to_root[cparent[c]] if cparent[c] >= 0 else 0)
+    apasses, done_c = [], set()
+    while len(done_c) < nchain:
+        ready = [c for c in range(nchain) if c not in done_c and all(ch in done_c for ch in cchild[c])]
+        take = sorted(ready, key=lambda c: (-to_root[c], c))[:4]
+        row = np.zeros((4, 8), dtype=np.int32)
+        row[:, 1] = -1
+        for g, c in enumerate(take):
+            row[g] = desc[c]
+        apasses.append(row)
+        done_c.update(take)
     S("napass", len(apasses))
     t["apass_desc"] = np.concatenate(apasses).reshape(-1) if apasses else np.zeros(32, np.int32)
     S("nhpass", len(passes))
