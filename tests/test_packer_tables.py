@@ -149,3 +149,47 @@ def test_default_alignment_mode_follows_the_environments_per_sm(monkeypatch):
         monkeypatch.setenv("BT_SYNC", bad)
         with pytest.raises(ValueError):
             model.default_sync_mode(4000)
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_staged_record_table_and_factor_pass_schedule(name):
+    """sh_tab = body_rec | bl_rec | jnt_rec (each padded to 16 bytes); the staged prefix holds whole tables, fits what the
+    environments leave free of the 227 KB, and is empty for the 2-slot (fly) kernel variant.  The factor-sweep passes (critical-path
+    list scheduling) are never longer than the schedule by depth level."""
+    from brax_tracking_b200 import model
+    m, cfg, clip, t = common.setup(name)
+    off = 0
+    for k in ("body_rec", "bl_rec", "jnt_rec"):
+        assert int(t["sho_" + k][0]) == off and off % 4 == 0
+        assert np.array_equal(t["sh_tab"][off:off + t[k].size], t[k])
+        off += t[k].size + (-t[k].size) % 4
+    assert t["sh_tab"].size == off
+    stage = int(t["sh_stage_floats"][0])
+    ends = [int(t["sho_" + k][0]) + t[k].size + (-t[k].size) % 4 for k in ("body_rec", "bl_rec", "jnt_rec")]
+    assert stage in [0] + ends
+    env_bytes = 4 * int(t["smem_floats"][0])
+    small = (m.nv + 31) // 32 <= 2
+    max_warps = 16 if ((m.nv + 31) // 32 <= 3 and (int(t["ncon"][0]) + 31) // 32 <= 1) else 8
+    envs = min(max_warps, model.SMEM_BYTES_PER_SM // env_bytes)
+    assert 4 * stage + envs * env_bytes <= model.SMEM_BYTES_PER_SM          # staging never costs an environment
+    assert (stage == 0) == (small or 4 * ends[0] + envs * env_bytes > model.SMEM_BYTES_PER_SM)
+    # factor passes: serial dof steps = sum over passes of the longest chain; by depth level for comparison
+    desc = t["chain_desc"].reshape(-1, 8)
+    ap = t["apass_desc"].reshape(-1, 4, 8)
+    steps = sum(max(int(r[1] - r[0] + 1) for r in rows) for rows in ap)
+    depth = {}
+    for c in range(len(desc)):
+        pc, d = int(desc[c][2]), 0
+        while pc >= 0:
+            d += 1; pc = int(desc[pc][2])
+        depth[c] = d
+    by_level = 0
+    for L in sorted(set(depth.values())):
+        cs = [c for c in range(len(desc)) if depth[c] == L]
+        for q in range(0, len(cs), 4):
+            by_level += max(int(desc[c][1] - desc[c][0] + 1) for c in cs[q:q + 4])
+    assert steps <= by_level
+    if name == "rodent":
+        assert (steps, by_level) == (38, 39)
+    if name == "rodent_pair":
+        assert (steps, by_level) == (53, 72)
