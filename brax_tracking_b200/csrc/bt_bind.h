@@ -61,6 +61,12 @@ static inline int bt_bind(BtDev* d, int n, const char* const* names, const void*
     idx = bt_find_table(n, names, "con_xref");
     if (counts[idx] != d->ncon) { snprintf(err, errlen, "con_xref must have ncon rows"); return -1; }
   }
+  idx = bt_find_table(n, names, "sh_tab");
+  if (counts[idx] < d->sh_stage_floats || counts[idx] < d->sho_body_rec + 12LL * d->nbody || counts[idx] < d->sho_bl_rec + 16LL * d->nbody ||
+      counts[idx] < d->sho_jnt_rec + 12LL * d->njnt || d->sho_body_rec < 0 || d->sho_bl_rec < 0 || d->sho_jnt_rec < 0) {
+    snprintf(err, errlen, "sh_tab is shorter than its layout");
+    return -1;
+  }
   if (d->clip_len < d->ref_len || d->nv <= 0 || d->nbody <= 1 || d->n_animals < 1 || d->n_clips < 1) { snprintf(err, errlen, "degenerate model"); return -1; }
   if (d->obs_size + 3 > d->smem_floats - d->o_crb) { snprintf(err, errlen, "observation row does not fit the staging region"); return -1; }
   return 0;

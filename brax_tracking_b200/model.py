@@ -713,8 +713,10 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
     # Why: with 14 x 16 KB of scratch the L1 is 22 KB against ~31 KB of tables touched per substep -- a cyclic pattern that an LRU
     # cache misses every time (ncu, rodent: 4.2 M L1 miss sectors per launch at 14 warps per CTA against 1.8 M at 12, where the
     # carve-out leaves 55 KB of L1).  Tables that do not fit are read from global memory as before.  Measured
-    # (profiles/r2l_staged_records.txt): rodent +1.2 %, two rodents +3.1 %, flies +0.5 %; the actuator / dof records gain nothing.
-    order = ("body_rec", "bl_rec", "jnt_rec")
+    # (profiles/r2l_staged_records.txt): rodent +1.1 %, two rodents +0.3 %; the actuator / dof records gain nothing.
+    # (order = staging priority: body_frame reads body_rec -> jnt_rec -> qpos as a chain of DEPENDENT loads, body_local's bl_rec is
+    # one independent load; rodent, 8.5 KB free: body_rec + jnt_rec 3.324 M against body_rec + bl_rec 3.302 M, same-box A/B)
+    order = ("body_rec", "jnt_rec", "bl_rec")
     parts, so = [], 0
     for k in order:
         v = np.asarray(t[k], dtype=np.float32)

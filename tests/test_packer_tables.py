@@ -153,19 +153,19 @@ def test_default_alignment_mode_follows_the_environments_per_sm(monkeypatch):
 
 @pytest.mark.parametrize("name", MODELS)
 def test_staged_record_table_and_factor_pass_schedule(name):
-    """sh_tab = body_rec | bl_rec | jnt_rec (each padded to 16 bytes); the staged prefix holds whole tables, fits what the
+    """sh_tab = body_rec | jnt_rec | bl_rec (each padded to 16 bytes); the staged prefix holds whole tables, fits what the
     environments leave free of the 227 KB, and is empty for the 2-slot (fly) kernel variant.  The factor-sweep passes (critical-path
     list scheduling) are never longer than the schedule by depth level."""
     from brax_tracking_b200 import model
     m, cfg, clip, t = common.setup(name)
     off = 0
-    for k in ("body_rec", "bl_rec", "jnt_rec"):
+    for k in ("body_rec", "jnt_rec", "bl_rec"):
         assert int(t["sho_" + k][0]) == off and off % 4 == 0
         assert np.array_equal(t["sh_tab"][off:off + t[k].size], t[k])
         off += t[k].size + (-t[k].size) % 4
     assert t["sh_tab"].size == off
     stage = int(t["sh_stage_floats"][0])
-    ends = [int(t["sho_" + k][0]) + t[k].size + (-t[k].size) % 4 for k in ("body_rec", "bl_rec", "jnt_rec")]
+    ends = [int(t["sho_" + k][0]) + t[k].size + (-t[k].size) % 4 for k in ("body_rec", "jnt_rec", "bl_rec")]
     assert stage in [0] + ends
     env_bytes = 4 * int(t["smem_floats"][0])
     small = (m.nv + 31) // 32 <= 2
