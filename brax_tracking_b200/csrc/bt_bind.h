@@ -63,7 +63,9 @@ static inline int bt_bind(BtDev* d, int n, const char* const* names, const void*
   }
   idx = bt_find_table(n, names, "sh_tab");
   if (counts[idx] < d->sh_stage_floats || counts[idx] < d->sho_body_rec + 12LL * d->nbody || counts[idx] < d->sho_bl_rec + 16LL * d->nbody ||
-      counts[idx] < d->sho_jnt_rec + 12LL * d->njnt || d->sho_body_rec < 0 || d->sho_bl_rec < 0 || d->sho_jnt_rec < 0) {
+      counts[idx] < d->sho_jnt_rec + 12LL * d->njnt || d->sho_body_rec < 0 || d->sho_bl_rec < 0 || d->sho_jnt_rec < 0 ||
+      d->sho_wrap_rec < 0 || d->sho_dofact_rec < 0 || d->sho_wrap_rec >= counts[idx] || d->sho_dofact_rec >= counts[idx] ||
+      ((d->sho_body_rec | d->sho_bl_rec | d->sho_jnt_rec | d->sho_wrap_rec) & 3) || (d->sho_dofact_rec & 1)) {
     snprintf(err, errlen, "sh_tab is shorter than its layout");
     return -1;
   }

@@ -180,6 +180,17 @@ struct BtEnv {
 #pragma unroll
     for (int q = 0; q < N4; q++) bt_ldg4(tab + idx + 4 * q, o + 4 * q);
   }
+  BT_DEV void crec2(const float* tab, int off, int idx, float* o) const {   // two floats (8-byte aligned)
+#ifdef __CUDACC__
+    extern __shared__ __align__(16) float bt_cta_smem[];
+    if (!kSmallModel && off < m.sh_stage_floats) {
+      const float2 v = *reinterpret_cast<const float2*>(bt_cta_smem + off + idx);
+      o[0] = v.x; o[1] = v.y;
+      return;
+    }
+#endif
+    bt_ldg2(tab + idx, o);
+  }
   // ------------------------------------------------------------------ scratch regions
   BT_DEV float* qpos() const { return s + m.o_qpos; }
   BT_DEV float* qvel() const { return s + m.o_qvel; }
@@ -566,7 +577,7 @@ struct BtEnv {
       float len = 0.f, vel = 0.f;
       for (int w = (int)r[14], w1 = w + (int)r[15]; w < w1; w++) {
         float wr[4];
-        bt_ldg4(m.wrap_rec + 4 * w, wr);
+        crec<1>(m.wrap_rec, m.sho_wrap_rec, 4 * w, wr);
         len += wr[0] * qpos()[(int)wr[1]];
         vel += wr[0] * qvel()[(int)wr[2]];
       }
@@ -595,7 +606,7 @@ struct BtEnv {
       float fa = 0.f;
       for (int k = (int)r[4], k1 = k + (int)r[5]; k < k1; k++) {
         float ar[2];
-        bt_ldg2(m.dofact_rec + 2 * k, ar);
+        crec2(m.dofact_rec, m.sho_dofact_rec, 2 * k, ar);
         fa += ar[0] * aforce()[(int)ar[1]];
       }
       qfrc_smooth()[i] = f + fa;

@@ -20,7 +20,7 @@
   X(o_cbJ) X(o_pvec) X(o_T) X(o_ref) X(o_aforce) X(o_actdot) X(o_qfrc_smooth) X(o_qacc_smooth) X(o_qacc) X(o_x) \
   X(o_search) X(o_qfrc_c) X(o_tmpv) X(o_wrench) X(o_cbA) X(smem_floats)                                            \
   /* CTA-shared constant records (offsets into sh_tab; the first sh_stage_floats floats are staged in shared memory) */ \
-  X(sh_stage_floats) X(sho_body_rec) X(sho_bl_rec) X(sho_jnt_rec)
+  X(sh_stage_floats) X(sho_body_rec) X(sho_bl_rec) X(sho_jnt_rec) X(sho_wrap_rec) X(sho_dofact_rec)
 
 // ---- scalar floats ----
 #define BT_FLT_SCALARS(X) \

@@ -707,36 +707,36 @@ def pack(m: mjcf.Model, cfg: dict, clip: Dict[str, np.ndarray], lanes: int = 32)
     S("smem_floats", off + (-off) % 4)
     S("sync_mode", default_sync_mode(int(t["smem_floats"][0])))
     # ------------------------------------------------------------------ constant records shared by the warps of a CTA
-    # The per-body / per-joint constant records that the body-parallel passes of EVERY substep read (body_frame, body_local: 10.7 KB
-    # for the rodent) are one contiguous table, `sh_tab`; the kernels copy its first `sh_stage_floats` floats (whole record tables,
-    # in this order) into the shared memory that the per-environment slices leave free and read them from there (BtEnv::crec).
-    # Why: with 14 x 16 KB of scratch the L1 is 22 KB against ~31 KB of tables touched per substep -- a cyclic pattern that an LRU
-    # cache misses every time (ncu, rodent: 4.2 M L1 miss sectors per launch at 14 warps per CTA against 1.8 M at 12, where the
-    # carve-out leaves 55 KB of L1).  Tables that do not fit are read from global memory as before.  Measured
-    # (profiles/r2l_staged_records.txt): rodent +1.1 %, two rodents +0.3 %; the actuator / dof records gain nothing.
-    # (order = staging priority: body_frame reads body_rec -> jnt_rec -> qpos as a chain of DEPENDENT loads, body_local's bl_rec is
-    # one independent load; rodent, 8.5 KB free: body_rec + jnt_rec 3.324 M against body_rec + bl_rec 3.302 M, same-box A/B)
-    order = ("body_rec", "jnt_rec", "bl_rec")
-    parts, so = [], 0
-    for k in order:
-        v = np.asarray(t[k], dtype=np.float32)
-        S("sho_" + k, so)
-        pad = (-v.size) % 4
-        parts.append(np.concatenate([v, np.zeros(pad, np.float32)]))
-        so += v.size + pad
-    t["sh_tab"] = np.concatenate(parts)
+    # The constant records that the lane-parallel passes of EVERY substep reach through a chain of dependent loads (body_frame:
+    # body_rec -> jnt_rec -> qpos; smooth_forces: act_rec -> wrap_rec, dof_rec -> dofact_rec) are one contiguous table, `sh_tab`; the
+    # kernels copy its first `sh_stage_floats` floats into the shared memory that the per-environment slices leave free and read them
+    # from there (BtEnv::crec).  Why: with 14 x 16 KB of scratch the L1 is 22 KB against ~31 KB of tables touched per substep -- a
+    # cyclic pattern that an LRU cache misses every time (ncu, rodent: 4.2 M L1 miss sectors per launch at 14 warps per CTA against
+    # 1.8 M at 12, where the carve-out leaves 55 KB of L1) -- and the warps of a CTA all wait for the same first touch.
+    # Tables are taken greedily in the priority order below while they fit (they then form the prefix of sh_tab); the rest is read
+    # from global memory as before.  Measured, same-box A/B (profiles/r2l_staged_records.txt): rodent body_rec + bl_rec +1.1 %,
+    # body_rec + jnt_rec instead +0.65 %, + wrap_rec + dofact_rec +0.9 %; first-level records with independent loads (bl_rec,
+    # act_rec, dof_rec) gain nothing.
+    priority = ("body_rec", "jnt_rec", "wrap_rec", "dofact_rec", "bl_rec")
     env_bytes = 4 * int(t["smem_floats"][0])
     need_ds, need_cs = (nv + 31) // 32, max((ncon + 31) // 32, 1)
     max_warps = MAX_WARPS_PER_CTA if (need_ds <= 3 and need_cs <= 1) else 8      # csrc/bt_ops.h: BT_VARIANT_MAX_WARPS
     budget = SMEM_BYTES_PER_SM - min(max_warps, SMEM_BYTES_PER_SM // env_bytes) * env_bytes   # what the environments leave free
-    stage = 0
     # (the 2-slot kernel variant -- nv <= 64: the fly models -- reads these records from global memory: csrc/bt_impl.h, kSmallModel)
-    nstage = 0 if need_ds <= 2 else int(os.environ.get("BT_STAGE", len(order)))   # BT_STAGE = n: at most the first n tables
-    for k in order[:nstage]:
-        end = int(t["sho_" + k][0]) + t[k].size + (-t[k].size) % 4
-        if 4 * end > budget:
-            break
-        stage = end
+    nstage = 0 if need_ds <= 2 else int(os.environ.get("BT_STAGE", len(priority)))   # BT_STAGE = n: only the first n candidates
+    padded = lambda k: t[k].size + (-t[k].size) % 4
+    staged, used = [], 0
+    for k in priority[:nstage]:
+        if 4 * (used + padded(k)) <= budget:
+            staged.append(k); used += padded(k)
+    parts, so = [], 0
+    for k in staged + [k for k in priority if k not in staged]:
+        v = np.asarray(t[k], dtype=np.float32)
+        S("sho_" + k, so)
+        parts.append(np.concatenate([v, np.zeros(padded(k) - v.size, np.float32)]))
+        so += padded(k)
+    t["sh_tab"] = np.concatenate(parts)
+    stage = used
     S("sh_stage_floats", stage)
     return t
 

@@ -153,26 +153,34 @@ def test_default_alignment_mode_follows_the_environments_per_sm(monkeypatch):
 
 @pytest.mark.parametrize("name", MODELS)
 def test_staged_record_table_and_factor_pass_schedule(name):
-    """sh_tab = body_rec | jnt_rec | bl_rec (each padded to 16 bytes); the staged prefix holds whole tables, fits what the
-    environments leave free of the 227 KB, and is empty for the 2-slot (fly) kernel variant.  The factor-sweep passes (critical-path
-    list scheduling) are never longer than the schedule by depth level."""
+    """sh_tab holds body_rec, jnt_rec, wrap_rec, dofact_rec, bl_rec (each padded to 16 bytes), the staged ones first: taken
+    greedily in that priority order while they fit what the environments leave free of the 227 KB (staging never costs an
+    environment); nothing is staged for the 2-slot (fly) kernel variant.  The factor-sweep passes (critical-path list scheduling)
+    are never longer than the schedule by depth level."""
     from brax_tracking_b200 import model
     m, cfg, clip, t = common.setup(name)
-    off = 0
-    for k in ("body_rec", "jnt_rec", "bl_rec"):
-        assert int(t["sho_" + k][0]) == off and off % 4 == 0
-        assert np.array_equal(t["sh_tab"][off:off + t[k].size], t[k])
-        off += t[k].size + (-t[k].size) % 4
-    assert t["sh_tab"].size == off
+    prio = ("body_rec", "jnt_rec", "wrap_rec", "dofact_rec", "bl_rec")
+    pad = lambda k: t[k].size + (-t[k].size) % 4
+    offs = {k: int(t["sho_" + k][0]) for k in prio}
+    for k in prio:
+        assert offs[k] % 4 == 0 and np.array_equal(t["sh_tab"][offs[k]:offs[k] + t[k].size], t[k])
+    assert t["sh_tab"].size == sum(pad(k) for k in prio)
+    assert sorted((offs[k], offs[k] + pad(k)) for k in prio) == [(a, b) for a, b in zip(np.cumsum([0] + [pad(k) for k in sorted(prio, key=offs.get)][:-1]),
+                                                                                       np.cumsum([pad(k) for k in sorted(prio, key=offs.get)]))]
     stage = int(t["sh_stage_floats"][0])
-    ends = [int(t["sho_" + k][0]) + t[k].size + (-t[k].size) % 4 for k in ("body_rec", "jnt_rec", "bl_rec")]
-    assert stage in [0] + ends
     env_bytes = 4 * int(t["smem_floats"][0])
     small = (m.nv + 31) // 32 <= 2
     max_warps = 16 if ((m.nv + 31) // 32 <= 3 and (int(t["ncon"][0]) + 31) // 32 <= 1) else 8
     envs = min(max_warps, model.SMEM_BYTES_PER_SM // env_bytes)
-    assert 4 * stage + envs * env_bytes <= model.SMEM_BYTES_PER_SM          # staging never costs an environment
-    assert (stage == 0) == (small or 4 * ends[0] + envs * env_bytes > model.SMEM_BYTES_PER_SM)
+    budget = model.SMEM_BYTES_PER_SM - envs * env_bytes
+    want, used = [], 0
+    for k in ([] if small else prio):
+        if 4 * (used + pad(k)) <= budget:
+            want.append(k); used += pad(k)
+    assert stage == used and 4 * stage + envs * env_bytes <= model.SMEM_BYTES_PER_SM
+    assert {k for k in prio if offs[k] < stage} == set(want)                  # the staged tables are exactly the prefix
+    if name == "rodent":
+        assert want == ["body_rec", "jnt_rec", "wrap_rec", "dofact_rec"]
     # factor passes: serial dof steps = sum over passes of the longest chain; by depth level for comparison
     desc = t["chain_desc"].reshape(-1, 8)
     ap = t["apass_desc"].reshape(-1, 4, 8)
